@@ -1,0 +1,99 @@
+"""ctypes binding of libcdc_b200.so (include/cdc_b200.h).  No torch types cross this boundary:
+only raw device pointers (tensor.data_ptr()), sizes and the CUDA stream handle."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcdc_b200.so")
+
+# every symbol include/cdc_b200.h declares
+SYMBOLS = [
+    "cdc_create", "cdc_destroy", "cdc_last_error", "cdc_abi_version", "cdc_load_weights", "cdc_finalize_weights",
+    "cdc_has_context_net", "cdc_set_schedule", "cdc_schedule_index", "cdc_schedule_coeffs", "cdc_bind_io",
+    "cdc_set_cond", "cdc_set_latent", "cdc_set_x", "cdc_get_x", "cdc_get_x0", "cdc_denoise_step", "cdc_decode",
+    "cdc_decode_host", "cdc_launches_per_step", "cdc_launches_context", "cdc_flops_per_step", "cdc_num_step_ops",
+    "cdc_step_op_name", "cdc_step_op_flops", "cdc_step_op_bytes", "cdc_run_step_op", "cdc_quantize",
+    "cdc_cdf_lookup", "cdc_test_conv", "cdc_test_attention", "cdc_test_gn",
+]
+
+
+class CdcConfig(C.Structure):
+    _fields_ = [("base", C.c_int32), ("mults", C.c_int32 * 4), ("groups", C.c_int32), ("heads", C.c_int32),
+                ("head_dim", C.c_int32), ("temb", C.c_int32), ("T", C.c_int32), ("latent_ch", C.c_int32),
+                ("gn_eps", C.c_float)]
+
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile the extension in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    import subprocess
+    script = os.path.join(_HERE, "csrc", "build.sh")
+    r = subprocess.run(["bash", script], capture_output=True, text=True)
+    if verbose or r.returncode:
+        print(r.stdout + r.stderr)
+    if r.returncode:
+        raise RuntimeError("building libcdc_b200.so failed:\n" + r.stdout + r.stderr)
+    return LIB_PATH
+
+
+def lib():
+    """Load the shared library; fail loudly if it is missing (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(cdc_b200 has no CPU or PyTorch fallback)")
+    L = C.CDLL(LIB_PATH)
+    p, i32, i64, f32p, i32p = C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p
+    L.cdc_create.argtypes = [C.POINTER(CdcConfig), i32, C.POINTER(p)]
+    L.cdc_destroy.argtypes = [p]
+    L.cdc_destroy.restype = None
+    L.cdc_last_error.argtypes = [p]
+    L.cdc_last_error.restype = C.c_char_p
+    L.cdc_load_weights.argtypes = [p, C.c_char_p, p, C.POINTER(i64), i32]
+    L.cdc_finalize_weights.argtypes = [p]
+    L.cdc_has_context_net.argtypes = [p]
+    L.cdc_set_schedule.argtypes = [p, i32]
+    L.cdc_schedule_index.argtypes = [p, i32]
+    L.cdc_schedule_coeffs.argtypes = [p, i32, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.cdc_bind_io.argtypes = [p, i32, i32, i32]
+    L.cdc_set_cond.argtypes = [p, f32p, f32p, f32p, f32p, p]
+    L.cdc_set_latent.argtypes = [p, f32p, p]
+    L.cdc_set_x.argtypes = [p, f32p, p]
+    L.cdc_get_x.argtypes = [p, f32p, i32, p]
+    L.cdc_get_x0.argtypes = [p, f32p, p]
+    L.cdc_denoise_step.argtypes = [p, i32, p]
+    L.cdc_decode.argtypes = [p, p]
+    L.cdc_decode_host.argtypes = [p, f32p, f32p, f32p, p]
+    L.cdc_launches_per_step.argtypes = [p]
+    L.cdc_launches_context.argtypes = [p]
+    L.cdc_flops_per_step.argtypes = [p]
+    L.cdc_flops_per_step.restype = C.c_double
+    L.cdc_num_step_ops.argtypes = [p]
+    L.cdc_step_op_name.argtypes = [p, i32]
+    L.cdc_step_op_name.restype = C.c_char_p
+    L.cdc_step_op_flops.argtypes = [p, i32]
+    L.cdc_step_op_flops.restype = C.c_double
+    L.cdc_step_op_bytes.argtypes = [p, i32]
+    L.cdc_step_op_bytes.restype = C.c_double
+    L.cdc_run_step_op.argtypes = [p, i32, i32, p]
+    L.cdc_quantize.argtypes = [f32p, f32p, i32p, f32p, i64, i64, i64, p]
+    L.cdc_cdf_lookup.argtypes = [i32p, f32p, i32p, i32p, i32p, i32p, f32p, i32, i64, i32p, i32p, i32p, i32p, i32p,
+                                 i64, p]
+    L.cdc_test_conv.argtypes = [i32, p, i32, p, i32, i32, i32, i32, f32p, f32p, i32, i32, i32, i32, p, p, f32p,
+                                C.POINTER(i32), p]
+    L.cdc_test_attention.argtypes = [p, p, i32, i32, i32, p]
+    L.cdc_test_gn.argtypes = [p, p, p, f32p, f32p, f32p, i32, i32, i32, i32, C.c_float, p]
+    for s in SYMBOLS:
+        getattr(L, s)  # raises AttributeError if the header and the library disagree
+    _lib = L
+    return L
+
+
+def check(ctx, rc, what):
+    if rc != 0:
+        msg = lib().cdc_last_error(ctx)
+        raise RuntimeError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")

@@ -1,0 +1,348 @@
+// K-conv: persistent, warp-specialised tcgen05 implicit-GEMM convolution for sm_100a.
+//
+//   M tile  = 128 output pixels forming a BH x BW rectangle of one image
+//   N tile  = BN output channels (UMMA 128 x BN x 16, cta_group::1, fp32 accumulators in TMEM)
+//   K block = 64 input channels of one filter tap: ONE 4-D TMA box {64 ch, BW, BH, 1} of the NHWC
+//             activation tensor at the tap-shifted origin.  Out-of-image pixels are zero-filled by
+//             TMA, which is exactly the conv zero padding, and the box lands in shared memory as
+//             128 rows x 128 B with the 128-byte swizzle, i.e. already the K-major UMMA operand.
+//
+//   warp 0 : TMA producer (one elected lane)        smem ring: full[] / empty[] mbarriers
+//   warp 1 : tcgen05.mma issuer (one elected lane)  TMEM ring: tfull[] / tempty[] (2 accumulators)
+//   warp 2 : TMEM allocator
+//   warps 4-7 : epilogue (tcgen05.ld -> +bias -> GroupNorm partials / residual / DDIM -> global)
+//
+// Oracle counterpart: oracle/unet.py `conv`, `Up`, `RB` (the reference ships no code).
+#include <stdio.h>
+
+#include "conv_tc.cuh"
+#include "ptx.cuh"
+
+namespace cdc {
+
+template <int BN>
+struct ConvCfg {
+    static constexpr int A_BYTES = 128 * 128;
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int NS = (BN >= 256) ? 4 : (BN >= 192) ? 5 : (BN >= 128) ? 6 : 8;
+    static constexpr int ACC_STRIDE = BN < 32 ? 32 : BN;
+    static constexpr int TMEM_COLS = (2 * ACC_STRIDE <= 32)    ? 32
+                                     : (2 * ACC_STRIDE <= 64)  ? 64
+                                     : (2 * ACC_STRIDE <= 128) ? 128
+                                     : (2 * ACC_STRIDE <= 256) ? 256
+                                                               : 512;
+    // aux region after the stage ring: barriers (8 B each), TMEM base, bias copy, stats scratch
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int BIAS_BYTES = 768 * 4;
+    static constexpr int RED_BYTES = 2 * 4 * 32 * 2 * 4;
+    static constexpr int SMEM_BYTES = 1024 + NS * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + RED_BYTES;
+};
+
+template <int G>
+__device__ __forceinline__ float warp_group_reduce(float (&s)[G], int lane) {
+    // Butterfly reduce-scatter over the warp: on return lane L holds the warp total of group
+    // L >> (5 - log2 G).  Fixed shuffle order => bitwise reproducible.
+    constexpr int LOG2G = (G == 32) ? 5 : (G == 16) ? 4 : (G == 8) ? 3 : (G == 4) ? 2 : (G == 2) ? 1 : 0;
+    static_assert((1 << LOG2G) == G, "G must be a power of two <= 32");
+#pragma unroll
+    for (int step = 0; step < LOG2G; ++step) {
+        const int m = 16 >> step;
+        const int half = G >> (step + 1);
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < G / 2; ++i) {
+            if (i < half) {
+                const float send = up ? s[i] : s[i + half];
+                const float keep = up ? s[i + half] : s[i];
+                s[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+            }
+        }
+    }
+    float r = s[0];
+#pragma unroll
+    for (int m = (16 >> LOG2G); m >= 1; m >>= 1) r += __shfl_xor_sync(0xffffffffu, r, m);
+    return r;
+}
+
+template <int BN, int CPG, int EPI>
+__global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+    using Cfg = ConvCfg<BN>;
+    constexpr int NS = Cfg::NS;
+    constexpr int G = (EPI == EPI_STATS) ? BN / CPG : 1;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_u32 = smem_u32(smem_raw);
+    const uint32_t base = (raw_u32 + 1023u) & ~1023u;  // 128B-swizzle atoms need 1024 B alignment
+    uint8_t* gen = smem_raw + (base - raw_u32);
+    const uint32_t aux = base + NS * Cfg::STAGE_BYTES;
+    uint8_t* aux_gen = gen + NS * Cfg::STAGE_BYTES;
+    const uint32_t bar_full = aux, bar_empty = aux + 8 * NS, bar_tfull = aux + 16 * NS, bar_tempty = aux + 16 * NS + 16;
+    volatile uint32_t* tmem_holder = reinterpret_cast<volatile uint32_t*>(aux_gen + 16 * NS + 32);
+    float* bias_s = reinterpret_cast<float*>(aux_gen + Cfg::BAR_BYTES);
+    float* red_s = reinterpret_cast<float*>(aux_gen + Cfg::BAR_BYTES + Cfg::BIAS_BYTES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int BWl = p.bw_log2, BW = 1 << BWl, BH = 128 >> BWl;
+    const int total_tiles = p.n_tiles * p.nphase * p.batch * p.tiles_h * p.tiles_w;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&p.wmap);
+        prefetch_tensormap(&p.amap[0]);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar_tfull + 8 * s, 1);
+            mbar_init(bar_tempty + 8 * s, 128);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_holder)), Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    for (int i = threadIdx.x; i < p.n_total; i += 256) bias_s[i] = p.bias[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    auto decode = [&](int tile, int& nt, int& ph, int& b, int& th, int& tw) {
+        nt = tile % p.n_tiles;
+        int m = tile / p.n_tiles;
+        tw = m % p.tiles_w;
+        m /= p.tiles_w;
+        th = m % p.tiles_h;
+        m /= p.tiles_h;
+        ph = m % p.nphase;
+        b = m / p.nphase;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------------------ TMA producer
+            uint32_t stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int nt, ph, b, th, tw;
+                decode(tile, nt, ph, b, th, tw);
+                const KBlock* tab = p.kb + ph * p.nkb;
+                const int w0 = tw * BW, h0 = th * BH;
+                for (int i = 0; i < p.nkb; ++i) {
+                    const KBlock e = tab[i];
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t full = bar_full + 8 * stage;
+                    mbar_expect_tx(full, Cfg::STAGE_BYTES);
+                    tma_load_4d(sa, &p.amap[e.map], full, e.c0, w0 + e.dw, h0 + e.dh, b);
+                    tma_load_2d(sa + Cfg::A_BYTES, &p.wmap, full, e.wk, nt * BN);
+                    if (++stage == NS) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ------------------------------------------------------------ MMA issuer
+            constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+            uint32_t stage = 0, phase = 0, it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
+                for (int i = 0; i < p.nkb; ++i) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
+                    const uint64_t adesc = make_sw128_desc(sa);
+                    const uint64_t bdesc = make_sw128_desc(sa + Cfg::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)  // 4 x (K = 16): +32 B inside the 128 B swizzle row
+                        umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0);
+                    umma_commit(bar_empty + 8 * stage);  // frees the smem slot once these MMAs retire
+                    if (++stage == NS) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(bar_tfull + 8 * as);  // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ---------------------------------------------------------------- epilogue
+        const int q = warp & 3;  // TMEM sub-partition: lanes 32q .. 32q+31
+        const int row = q * 32 + lane;
+        const int ty = row >> BWl, tx = row & (BW - 1);
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            int nt, ph, b, th, tw;
+            decode(tile, nt, ph, b, th, tw);
+            const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+            const int gy = th * BH + ty, gx = tw * BW + tx;
+            const bool valid = (gy < p.gh) && (gx < p.gw);
+            const int oy = gy * p.os + (ph >> 1), ox = gx * p.os + (ph & 1);
+            const size_t pix = (static_cast<size_t>(b) * p.OH + oy) * p.OW + ox;
+
+            mbar_wait(bar_tfull + 8 * as, aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE;
+
+            if constexpr (EPI == EPI_DDIM) {
+                uint32_t v[16];
+                tmem_ld16(taddr, v);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(bar_tempty + 8 * as);
+                if (valid) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float x0 = __uint_as_float(v[c]) + bias_s[c];
+                        const float xt = p.x[pix * 3 + c];
+                        const float xn = p.c0 * fminf(fmaxf(x0, -1.0f), 1.0f) + p.c1 * xt;
+                        p.x[pix * 3 + c] = xn;
+                        p.xpad[pix * 64 + c] = __float2bfloat16_rn(xn);
+                        if (p.x0_out) p.x0_out[pix * 3 + c] = x0;
+                    }
+                }
+            } else {
+                float gs[G], gq[G];
+#pragma unroll
+                for (int g = 0; g < G; ++g) gs[g] = gq[g] = 0.0f;
+                __nv_bfloat16* orow = p.out + pix * p.ldc + nt * BN;
+                const __nv_bfloat16* rrow = p.residual ? p.residual + pix * p.ldc + nt * BN : nullptr;
+                const float* bs = bias_s + nt * BN;
+#pragma unroll
+                for (int ch = 0; ch < BN / 32; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + ch * 32, v);
+                    tmem_ld_wait();
+                    if (ch == BN / 32 - 1) {  // accumulator drained: hand the TMEM stage back early
+                        tc_fence_before();
+                        mbar_arrive(bar_tempty + 8 * as);
+                    }
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bs[ch * 32 + j];
+                    if constexpr (EPI == EPI_STATS) {
+                        const float msk = valid ? 1.0f : 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int g = (ch * 32 + j) / CPG;
+                            const float x = f[j] * msk;
+                            gs[g] += x;
+                            gq[g] += x * x;
+                        }
+                    }
+                    if (valid) {
+                        uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
+#pragma unroll
+                        for (int s4 = 0; s4 < 4; ++s4) {
+                            if (rrow) {
+                                const uint4 r = *reinterpret_cast<const uint4*>(rrow + ch * 32 + s4 * 8);
+                                f[s4 * 8 + 0] += bf16_lo(r.x);
+                                f[s4 * 8 + 1] += bf16_hi(r.x);
+                                f[s4 * 8 + 2] += bf16_lo(r.y);
+                                f[s4 * 8 + 3] += bf16_hi(r.y);
+                                f[s4 * 8 + 4] += bf16_lo(r.z);
+                                f[s4 * 8 + 5] += bf16_hi(r.z);
+                                f[s4 * 8 + 6] += bf16_lo(r.w);
+                                f[s4 * 8 + 7] += bf16_hi(r.w);
+                            }
+                            uint4 o;
+                            o.x = pack_bf16x2(f[s4 * 8 + 0], f[s4 * 8 + 1]);
+                            o.y = pack_bf16x2(f[s4 * 8 + 2], f[s4 * 8 + 3]);
+                            o.z = pack_bf16x2(f[s4 * 8 + 4], f[s4 * 8 + 5]);
+                            o.w = pack_bf16x2(f[s4 * 8 + 6], f[s4 * 8 + 7]);
+                            dst[s4] = o;
+                        }
+                    }
+                }
+                if constexpr (EPI == EPI_STATS) {
+                    // warp butterfly -> 4 warps through smem -> one fixed-order partial per (tile, group)
+                    const float ws = warp_group_reduce<G>(gs, lane);
+                    const float wq = warp_group_reduce<G>(gq, lane);
+                    constexpr int REP = 32 / G;
+                    float* red = red_s + (it & 1) * (4 * 32 * 2);
+                    if ((lane & (REP - 1)) == 0) {
+                        const int g = lane / REP;
+                        red[(q * 32 + g) * 2 + 0] = ws;
+                        red[(q * 32 + g) * 2 + 1] = wq;
+                    }
+                    named_bar_sync(1, 128);
+                    if (row < G) {
+                        const float s = ((red[(0 * 32 + row) * 2] + red[(1 * 32 + row) * 2]) +
+                                         red[(2 * 32 + row) * 2]) + red[(3 * 32 + row) * 2];
+                        const float s2 = ((red[(0 * 32 + row) * 2 + 1] + red[(1 * 32 + row) * 2 + 1]) +
+                                          red[(2 * 32 + row) * 2 + 1]) + red[(3 * 32 + row) * 2 + 1];
+                        const int PT = p.nphase * p.tiles_h * p.tiles_w;
+                        const int pt = (ph * p.tiles_h + th) * p.tiles_w + tw;
+                        float* dst = p.stats + ((static_cast<size_t>(b) * PT + pt) * 32 + nt * G + row) * 2;
+                        dst[0] = s;
+                        dst[1] = s2;
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int BN, int CPG, int EPI>
+static cudaError_t configure_one() {
+    return cudaFuncSetAttribute(conv_tc_kernel<BN, CPG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                ConvCfg<BN>::SMEM_BYTES);
+}
+
+template <int BN, int CPG, int EPI>
+static cudaError_t launch_one(const ConvParams& p, int num_sms, cudaStream_t stream) {
+    using Cfg = ConvCfg<BN>;
+    auto kern = conv_tc_kernel<BN, CPG, EPI>;
+    const int total = p.n_tiles * p.nphase * p.batch * p.tiles_h * p.tiles_w;
+    const int grid = total < num_sms ? total : num_sms;
+    kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(p);
+    return cudaGetLastError();
+}
+
+#define CDC_ALL_CASES()          \
+    CDC_CASE(64, 1, EPI_STORE)   \
+    CDC_CASE(128, 1, EPI_STORE)  \
+    CDC_CASE(192, 1, EPI_STORE)  \
+    CDC_CASE(256, 1, EPI_STORE)  \
+    CDC_CASE(64, 2, EPI_STATS)   \
+    CDC_CASE(64, 4, EPI_STATS)   \
+    CDC_CASE(64, 8, EPI_STATS)   \
+    CDC_CASE(128, 4, EPI_STATS)  \
+    CDC_CASE(128, 8, EPI_STATS)  \
+    CDC_CASE(192, 6, EPI_STATS)  \
+    CDC_CASE(256, 8, EPI_STATS)  \
+    CDC_CASE(16, 1, EPI_DDIM)
+
+cudaError_t configure_conv_kernels() {
+    cudaError_t e;
+#define CDC_CASE(BN_, CPG_, EPI_) \
+    if ((e = configure_one<BN_, CPG_, EPI_>()) != cudaSuccess) return e;
+    CDC_ALL_CASES()
+#undef CDC_CASE
+    return cudaSuccess;
+}
+
+cudaError_t launch_conv(const ConvParams& p, int bn, int cpg, int epi, int num_sms, cudaStream_t stream) {
+    if (epi != EPI_STATS) cpg = 1;
+#define CDC_CASE(BN_, CPG_, EPI_) \
+    if (bn == BN_ && cpg == CPG_ && epi == EPI_) return launch_one<BN_, CPG_, EPI_>(p, num_sms, stream);
+    CDC_ALL_CASES()
+#undef CDC_CASE
+    return cudaErrorInvalidValue;
+}
+
+
+}  // namespace cdc

@@ -1,0 +1,334 @@
+// HBM-/latency-bound kernels around K-conv: GroupNorm statistics / finalize / apply(+SiLU,+residual),
+// time-embedding MLP + FiLM vectors, layout conversion at the API boundary, weight repack.
+// Oracle counterparts: oracle/unet.py RB, Attn.gn, TimeEmbed; SURVEY.md 2.2 C5, C6, C8.
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace cdc {
+
+// ------------------------------------------------------------------------------------------------
+// Standalone GN statistics (used where the producer is not a conv epilogue: attention input).
+// One CTA per (image, 64-pixel chunk); fixed-order reductions only.
+constexpr int kStatsPix = 64;
+
+int gn_stats_num_partials(int HW) { return (HW + kStatsPix - 1) / kStatsPix; }
+
+__global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partials,
+                                                       int HW, int C, int PT) {
+    __shared__ float s_sum[8][512], s_sq[8][512];  // [row-in-pass][channel] (C <= 512)
+    const int b = blockIdx.y, pt = blockIdx.x;
+    const int vecs = C / 8;                 // uint4 per pixel
+    const int rows = 256 / vecs;            // pixels per pass
+    const int t = threadIdx.x, cv = t % vecs, pr = t / vecs;
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    const int p0 = pt * kStatsPix;
+    if (pr < rows) {
+        for (int pp = pr; pp < kStatsPix && p0 + pp < HW; pp += rows) {
+            const uint4 u = *reinterpret_cast<const uint4*>(x + (static_cast<size_t>(b) * HW + p0 + pp) * C + cv * 8);
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float a = bf16_lo(w[j]), c = bf16_hi(w[j]);
+                s[2 * j] += a;
+                q[2 * j] += a * a;
+                s[2 * j + 1] += c;
+                q[2 * j + 1] += c * c;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            s_sum[pr][cv * 8 + j] = s[j];
+            s_sq[pr][cv * 8 + j] = q[j];
+        }
+    }
+    __syncthreads();
+    // per-channel totals over the pass rows, then per-group totals, all in fixed order
+    __shared__ float c_sum[512], c_sq[512];
+    for (int c = t; c < C; c += 256) {
+        float a = 0.f, d = 0.f;
+        for (int r = 0; r < rows && r < 8; ++r) {
+            a += s_sum[r][c];
+            d += s_sq[r][c];
+        }
+        c_sum[c] = a;
+        c_sq[c] = d;
+    }
+    __syncthreads();
+    if (t < 32) {
+        const int cpg = C / 32;
+        float a = 0.f, d = 0.f;
+        for (int j = 0; j < cpg; ++j) {
+            a += c_sum[t * cpg + j];
+            d += c_sq[t * cpg + j];
+        }
+        float* dst = partials + ((static_cast<size_t>(b) * PT + pt) * 32 + t) * 2;
+        dst[0] = a;
+        dst[1] = d;
+    }
+}
+
+cudaError_t launch_gn_stats(const __nv_bfloat16* x, float* partials, int B, int HW, int C, int* PT_out,
+                            cudaStream_t s) {
+    if (C % 32 != 0 || C > 512 || (256 % (C / 8)) != 0 || 256 / (C / 8) > 8) return cudaErrorInvalidValue;
+    const int PT = gn_stats_num_partials(HW);
+    if (PT_out) *PT_out = PT;
+    gn_stats_kernel<<<dim3(PT, B), 256, 0, s>>>(x, partials, HW, C, PT);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Finalize: one CTA per image, one warp per group.  Lane l sums partials l, l+32, ... in order,
+// then a fixed shuffle tree; double accumulation for the final mean / variance.
+__global__ void __launch_bounds__(1024) gn_finalize_kernel(const float* __restrict__ partials, int PT,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta,
+                                                           const float* __restrict__ film, float2* __restrict__ ab,
+                                                           int C, int HW, float eps) {
+    __shared__ float s_mean[32], s_rstd[32];
+    const int b = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float2* src = reinterpret_cast<const float2*>(partials) + static_cast<size_t>(b) * PT * 32 + g;
+    double s = 0.0, q = 0.0;
+    for (int pt = lane; pt < PT; pt += 32) {
+        const float2 v = src[static_cast<size_t>(pt) * 32];
+        s += v.x;
+        q += v.y;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, m);
+        q += __shfl_xor_sync(0xffffffffu, q, m);
+    }
+    if (lane == 0) {
+        const double n = static_cast<double>(C / 32) * HW;
+        const double mean = s / n;
+        double var = q / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[g] = static_cast<float>(mean);
+        s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 1024) {
+        const int gg = c / (C / 32);
+        float a = gamma[c] * s_rstd[gg];
+        float bb = beta[c] - s_mean[gg] * a;
+        if (film) {
+            const float sc = 1.0f + film[c], sh = film[C + c];
+            a *= sc;
+            bb = bb * sc + sh;
+        }
+        ab[static_cast<size_t>(b) * C + c] = make_float2(a, bb);
+    }
+}
+
+cudaError_t launch_gn_finalize(const float* partials, int PT, const float* gamma, const float* beta, const float* film,
+                               float2* ab, int B, int C, int HW, float eps, cudaStream_t s) {
+    gn_finalize_kernel<<<B, 1024, 0, s>>>(partials, PT, gamma, beta, film, ab, C, HW, eps);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Apply: y = SiLU(a*x + b) (+ r), 8 channels (16 B) per thread, grid-stride.
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+
+template <bool SILU, bool RES>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* __restrict__ x, const float2* __restrict__ ab,
+                                                       const uint4* __restrict__ r, uint4* __restrict__ y,
+                                                       long long nvec, int vecs_per_pix, long long vecs_per_img) {
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < nvec; i += gridDim.x * 256LL) {
+        const int cv = static_cast<int>(i % vecs_per_pix);
+        const int b = static_cast<int>(i / vecs_per_img);
+        const float4* abp = reinterpret_cast<const float4*>(ab + (static_cast<size_t>(b) * vecs_per_pix + cv) * 8);
+        const uint4 u = x[i];
+        uint4 rr = make_uint4(0, 0, 0, 0);
+        if (RES) rr = r[i];
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 c = abp[j];  // (a0, b0, a1, b1)
+            float v0 = c.x * bf16_lo(w[j]) + c.y;
+            float v1 = c.z * bf16_hi(w[j]) + c.w;
+            if (SILU) {
+                v0 = silu_f(v0);
+                v1 = silu_f(v1);
+            }
+            if (RES) {
+                v0 += bf16_lo(rw[j]);
+                v1 += bf16_hi(rw[j]);
+            }
+            o[j] = pack_bf16x2(v0, v1);
+        }
+        y[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+cudaError_t launch_gn_apply(const __nv_bfloat16* x, const float2* ab, const __nv_bfloat16* r, __nv_bfloat16* y, int B,
+                            int HW, int C, int silu, int num_sms, cudaStream_t s) {
+    const long long nvec = static_cast<long long>(B) * HW * C / 8;
+    const int vpp = C / 8;
+    const long long vpi = static_cast<long long>(HW) * vpp;
+    long long want = (nvec + 255) / 256;
+    const long long cap = static_cast<long long>(num_sms) * 16;
+    const int grid = static_cast<int>(want < cap ? want : cap);
+    const uint4* xv = reinterpret_cast<const uint4*>(x);
+    const uint4* rv = reinterpret_cast<const uint4*>(r);
+    uint4* yv = reinterpret_cast<uint4*>(y);
+    if (silu && r)
+        gn_apply_kernel<true, true><<<grid, 256, 0, s>>>(xv, ab, rv, yv, nvec, vpp, vpi);
+    else if (silu)
+        gn_apply_kernel<true, false><<<grid, 256, 0, s>>>(xv, ab, rv, yv, nvec, vpp, vpi);
+    else if (r)
+        gn_apply_kernel<false, true><<<grid, 256, 0, s>>>(xv, ab, rv, yv, nvec, vpp, vpi);
+    else
+        gn_apply_kernel<false, false><<<grid, 256, 0, s>>>(xv, ab, rv, yv, nvec, vpp, vpi);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Time embedding + all FiLM vectors for every step of the schedule (runs once per set_schedule).
+// One CTA per step.  fp32 throughout, accurate expf (the oracle is fp32 eager).
+__device__ __forceinline__ float silu_acc(float v) { return v / (1.0f + expf(-v)); }
+
+__global__ void __launch_bounds__(256) temb_film_kernel(const __grid_constant__ FilmParams p) {
+    __shared__ float e[64], h1[256], te[256];
+    const int k = blockIdx.x, t = threadIdx.x;
+    if (t < 64) e[t] = p.sinus[k * 64 + t];
+    __syncthreads();
+    for (int o = t; o < p.temb; o += 256) {
+        float acc = p.b1[o];
+        for (int i = 0; i < 64; ++i) acc = fmaf(p.w1[o * 64 + i], e[i], acc);
+        h1[o] = silu_acc(acc);
+    }
+    __syncthreads();
+    for (int o = t; o < p.temb; o += 256) {
+        float acc = p.b2[o];
+        for (int i = 0; i < p.temb; ++i) acc = fmaf(p.w2[o * p.temb + i], h1[i], acc);
+        te[o] = silu_acc(acc);  // every consumer applies SiLU(te) first
+    }
+    __syncthreads();
+    const int warp = t >> 5, lane = t & 31;
+    for (int l = 0; l < p.nlayers; ++l) {
+        const FilmLayer L = p.layer[l];
+        for (int o = warp; o < L.c2; o += 8) {
+            float acc = 0.f;
+            for (int i = lane; i < p.temb; i += 32) acc = fmaf(L.w[o * p.temb + i], te[i], acc);
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+            if (lane == 0) p.out[static_cast<size_t>(k) * p.total + L.offset + o] = acc + L.b[o];
+        }
+    }
+}
+
+cudaError_t launch_temb_film(const FilmParams& p, int K, cudaStream_t s) {
+    if (p.temb > 256) return cudaErrorInvalidValue;
+    temb_film_kernel<<<K, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Layout conversion (API boundary: NCHW fp32 tensors <-> device NHWC bf16 / fp32).
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C, int HW,
+                                    int ldc) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int c = c0 + j, p = p0 + threadIdx.x;
+        tile[j][threadIdx.x] = (c < C && p < HW) ? src[(static_cast<size_t>(b) * C + c) * HW + p] : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int p = p0 + j, c = c0 + threadIdx.x;
+        if (p < HW && c < C) dst[(static_cast<size_t>(b) * HW + p) * ldc + c] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+    }
+}
+cudaError_t launch_nchw_f32_to_nhwc_bf16(const float* src, __nv_bfloat16* dst, int B, int C, int HW, int ldc,
+                                         cudaStream_t s) {
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, B);
+    nchw_to_nhwc_kernel<<<grid, dim3(32, 8), 0, s>>>(src, dst, C, HW, ldc);
+    return cudaGetLastError();
+}
+
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int p = p0 + j, c = c0 + threadIdx.x;
+        tile[j][threadIdx.x] = (c < C && p < HW) ? __bfloat162float(src[(static_cast<size_t>(b) * HW + p) * C + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int c = c0 + j, p = p0 + threadIdx.x;
+        if (p < HW && c < C) dst[(static_cast<size_t>(b) * C + c) * HW + p] = tile[threadIdx.x][j];
+    }
+}
+cudaError_t launch_nhwc_bf16_to_nchw_f32(const __nv_bfloat16* src, float* dst, int B, int C, int HW, cudaStream_t s) {
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, B);
+    nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, s>>>(src, dst, C, HW);
+    return cudaGetLastError();
+}
+
+__global__ void x_in_kernel(const float* __restrict__ x, float* __restrict__ xs, __nv_bfloat16* __restrict__ xpad,
+                            long long n, int HW) {
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
+        const long long b = i / HW, p = i % HW;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = x[(b * 3 + c) * HW + p];
+            xs[i * 3 + c] = v;
+            xpad[i * 64 + c] = __float2bfloat16_rn(v);
+        }
+    }
+}
+cudaError_t launch_x_in(const float* x_nchw, float* xs, __nv_bfloat16* xpad, int B, int HW, cudaStream_t s) {
+    const long long n = static_cast<long long>(B) * HW;
+    x_in_kernel<<<static_cast<int>((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096), 256, 0, s>>>(x_nchw, xs, xpad, n, HW);
+    return cudaGetLastError();
+}
+
+__global__ void x_out_kernel(const float* __restrict__ xs, float* __restrict__ x, long long n, int HW, int to_image) {
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
+        const long long b = i / HW, p = i % HW;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float v = xs[i * 3 + c];
+            if (to_image) v = (fminf(fmaxf(v, -1.0f), 1.0f) + 1.0f) / 2.0f;
+            x[(b * 3 + c) * HW + p] = v;
+        }
+    }
+}
+cudaError_t launch_x_out(const float* xs, float* x_nchw, int B, int HW, int to_image, cudaStream_t s) {
+    const long long n = static_cast<long long>(B) * HW;
+    x_out_kernel<<<static_cast<int>((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096), 256, 0, s>>>(xs, x_nchw, n, HW,
+                                                                                                  to_image);
+    return cudaGetLastError();
+}
+
+// OIHW fp32 -> [O_pad][taps][I_pad] bf16; input channel i < split keeps slot i, i >= split moves to
+// split_pad + (i - split); everything else is zero.
+__global__ void repack_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int O, int I,
+                                     int taps, int O_pad, int I_pad, int split, int split_pad) {
+    const long long n = static_cast<long long>(O_pad) * taps * I_pad;
+    for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < n; idx += gridDim.x * 256LL) {
+        const int slot = static_cast<int>(idx % I_pad);
+        const int tap = static_cast<int>((idx / I_pad) % taps);
+        const int o = static_cast<int>(idx / (static_cast<long long>(I_pad) * taps));
+        int i = -1;
+        if (slot < split) i = slot;
+        else if (slot >= split_pad && slot - split_pad + split < I) i = slot - split_pad + split;
+        float v = 0.f;
+        if (o < O && i >= 0 && i < I) v = src[(static_cast<size_t>(o) * I + i) * taps + tap];
+        dst[idx] = __float2bfloat16_rn(v);
+    }
+}
+cudaError_t launch_repack_weight(const float* src, __nv_bfloat16* dst, int O, int I, int taps, int O_pad, int I_pad,
+                                 int split, int split_pad, cudaStream_t s) {
+    const long long n = static_cast<long long>(O_pad) * taps * I_pad;
+    repack_weight_kernel<<<static_cast<int>((n + 255) / 256 < 2048 ? (n + 255) / 256 : 2048), 256, 0, s>>>(
+        src, dst, O, I, taps, O_pad, I_pad, split, split_pad);
+    return cudaGetLastError();
+}
+
+}  // namespace cdc

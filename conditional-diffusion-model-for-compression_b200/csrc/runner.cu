@@ -1,0 +1,1249 @@
+// Host runtime of the decode hot path: weight store, schedule, workspace arena, per-layer TMA
+// tensor maps, the launch plan of one denoise step (and of the context net), CUDA-graph capture
+// of the K-step loop, and the extern "C" ABI declared in include/cdc_b200.h.
+//
+// Oracle counterparts (the reference ships no code): oracle/unet.py UNet.forward,
+// oracle/sampler.py make_schedule / denoise_step / decode, oracle/codec.py ContextNet.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/cdc_b200.h"
+#include "conv_tc.cuh"
+#include "kernels.cuh"
+
+namespace cdc {
+
+static std::string g_create_err;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+struct Act {  // NHWC bf16 activation, batch implied by the plan
+    __nv_bfloat16* p = nullptr;
+    int C = 0, H = 0, W = 0;
+};
+
+struct ConvW {  // repacked conv weights: bf16 [n_pad][taps][c_pad], fp32 bias [n_pad]
+    __nv_bfloat16* w = nullptr;
+    float* bias = nullptr;
+    int n_true = 0, n_pad = 0, taps = 0, c_pad = 0, c_true = 0;
+};
+
+struct Op {
+    std::string name;
+    double flops = 0, bytes = 0;
+    std::function<cudaError_t(cudaStream_t, int)> run;
+};
+
+enum ConvMode { MODE_S1 = 0, MODE_S2 = 1, MODE_UP2 = 2 };
+
+static bool stats_inst_ok(int bn, int cpg) {
+    return (bn == 64 && (cpg == 2 || cpg == 4 || cpg == 8)) || (bn == 128 && (cpg == 4 || cpg == 8)) ||
+           (bn == 192 && cpg == 6) || (bn == 256 && cpg == 8);
+}
+
+struct Arena {
+    std::vector<void*> ptrs;
+    size_t total = 0;
+    cudaError_t alloc(void** p, size_t bytes) {
+        bytes = (bytes + 255) & ~size_t(255);
+        cudaError_t e = cudaMalloc(p, bytes);
+        if (e == cudaSuccess) {
+            ptrs.push_back(*p);
+            total += bytes;
+        }
+        return e;
+    }
+    void release() {
+        for (void* p : ptrs) cudaFree(p);
+        ptrs.clear();
+        total = 0;
+    }
+};
+
+struct ConvBuild {
+    std::string name;
+    std::vector<Act> srcs;
+    const ConvW* w = nullptr;
+    int mode = MODE_S1;
+    int ksize = 3;
+    Act out;
+    int epi = EPI_STORE;
+    int cpg = 1;
+    float* stats = nullptr;
+    const __nv_bfloat16* residual = nullptr;
+    int force_bn = 0;
+    // DDIM
+    float* x = nullptr;
+    __nv_bfloat16* xpad = nullptr;
+    float* x0_out = nullptr;
+    const std::vector<float>* c0 = nullptr;  // per-step sampler coefficients (host)
+    const std::vector<float>* c1 = nullptr;
+};
+
+static int encode_act_map(CUtensorMap* m, const __nv_bfloat16* base, int C, int Wd, int Hd, int B, size_t sW, size_t sH,
+                          size_t sB, int BW, int BH) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return -1;
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(Wd), static_cast<cuuint64_t>(Hd),
+                          static_cast<cuuint64_t>(B)};
+    cuuint64_t strides[3] = {sW * 2, sH * 2, sB * 2};
+    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(BW), static_cast<cuuint32_t>(BH), 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
+}
+
+static int encode_w_map(CUtensorMap* m, const __nv_bfloat16* w, int K, int N, int BN) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return -1;
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(N)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(K) * 2};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(BN)};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(w), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
+}
+
+// Number of GroupNorm partial rows a stats-conv writes per image (must match conv_tc.cu).
+static void conv_geometry(const ConvBuild& cb, int& gw, int& gh, int& nphase, int& os, int& bwl, int& tiles_w,
+                          int& tiles_h) {
+    const Act& a = cb.srcs[0];
+    nphase = 1;
+    os = 1;
+    if (cb.mode == MODE_S2) {
+        gw = a.W / 2;
+        gh = a.H / 2;
+    } else if (cb.mode == MODE_UP2) {
+        gw = a.W;
+        gh = a.H;
+        nphase = 4;
+        os = 2;
+    } else {
+        gw = a.W;
+        gh = a.H;
+    }
+    long best = -1;
+    bwl = 7;
+    for (int l = 7; l >= 2; --l) {
+        const int BW = 1 << l, BH = 128 >> l;
+        const long t = static_cast<long>((gw + BW - 1) / BW) * ((gh + BH - 1) / BH);
+        if (best < 0 || t < best) {
+            best = t;
+            bwl = l;
+        }
+    }
+    const int BW = 1 << bwl, BH = 128 >> bwl;
+    tiles_w = (gw + BW - 1) / BW;
+    tiles_h = (gh + BH - 1) / BH;
+}
+
+static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::string* err) {
+    auto fail = [&](const std::string& m) {
+        *err = "conv " + cb.name + ": " + m;
+        return CDC_ERR_SHAPE;
+    };
+    if (cb.srcs.empty() || cb.srcs.size() > 2) return fail("1 or 2 sources required");
+    int ctot = 0;
+    for (const Act& a : cb.srcs) {
+        if (a.C % 64) return fail("source channels must be a multiple of 64");
+        if (a.H != cb.srcs[0].H || a.W != cb.srcs[0].W) return fail("sources differ in size");
+        ctot += a.C;
+    }
+    const ConvW& w = *cb.w;
+    const int taps = cb.ksize * cb.ksize;
+    if (ctot != w.c_pad || taps != w.taps) return fail("weight layout does not match the sources");
+    auto cp = std::shared_ptr<ConvParams>(new ConvParams());
+    memset(cp.get(), 0, sizeof(ConvParams));
+    int gw, gh, nphase, os, bwl, tiles_w, tiles_h;
+    conv_geometry(cb, gw, gh, nphase, os, bwl, tiles_w, tiles_h);
+    const int BW = 1 << bwl, BH = 128 >> bwl;
+    if (cb.mode == MODE_S2 && ((cb.srcs[0].W | cb.srcs[0].H) & 1)) return fail("stride 2 needs even H, W");
+    const int OH = cb.mode == MODE_UP2 ? 2 * gh : gh, OW = cb.mode == MODE_UP2 ? 2 * gw : gw;
+    if (cb.epi != EPI_DDIM && (cb.out.H != OH || cb.out.W != OW || cb.out.C != w.n_pad))
+        return fail("output tensor shape mismatch");
+
+    // N tile
+    const long m_tiles = static_cast<long>(nphase) * B * tiles_w * tiles_h;
+    int bn = 0;
+    if (cb.epi == EPI_DDIM) {
+        bn = 16;
+    } else if (cb.force_bn) {
+        bn = cb.force_bn;
+    } else {
+        const int cands[4] = {256, 192, 128, 64};
+        int smallest = 0;
+        for (int c : cands) {
+            if (w.n_pad % c) continue;
+            if (cb.epi == EPI_STATS && !stats_inst_ok(c, cb.cpg)) continue;
+            smallest = c;
+            if (!bn && m_tiles * (w.n_pad / c) >= num_sms) bn = c;
+        }
+        if (!bn) bn = smallest;
+    }
+    if (!bn || w.n_pad % bn) return fail("no N tile for C_out");
+    if (cb.epi == EPI_STATS && !stats_inst_ok(bn, cb.cpg)) return fail("no stats instantiation for (BN, cpg)");
+
+    // tensor maps
+    int nmaps = 0;
+    for (size_t s = 0; s < cb.srcs.size(); ++s) {
+        const Act& a = cb.srcs[s];
+        if (cb.mode == MODE_S2) {
+            for (int py = 0; py < 2; ++py)
+                for (int px = 0; px < 2; ++px) {
+                    const __nv_bfloat16* base = a.p + (static_cast<size_t>(py) * a.W + px) * a.C;
+                    if (encode_act_map(&cp->amap[nmaps++], base, a.C, a.W / 2, a.H / 2, B, 2 * static_cast<size_t>(a.C),
+                                       2 * static_cast<size_t>(a.W) * a.C, static_cast<size_t>(a.H) * a.W * a.C, BW, BH))
+                        return fail("cuTensorMapEncodeTiled (stride-2 view) failed");
+                }
+        } else {
+            if (encode_act_map(&cp->amap[nmaps++], a.p, a.C, a.W, a.H, B, static_cast<size_t>(a.C),
+                               static_cast<size_t>(a.W) * a.C, static_cast<size_t>(a.H) * a.W * a.C, BW, BH))
+                return fail("cuTensorMapEncodeTiled (activation) failed");
+        }
+    }
+    if (encode_w_map(&cp->wmap, w.w, w.taps * w.c_pad, w.n_pad, bn)) return fail("cuTensorMapEncodeTiled (weights) failed");
+
+    // K-block table
+    int nkb = taps * (ctot / 64);
+    if (nkb * nphase > kMaxKBlocks) return fail("K-block table overflow");
+    const int pad = cb.ksize / 2;
+    for (int ph = 0; ph < nphase; ++ph) {
+        const int py = ph >> 1, px = ph & 1;
+        int i = 0;
+        for (int kh = 0; kh < cb.ksize; ++kh)
+            for (int kw = 0; kw < cb.ksize; ++kw) {
+                int dh = kh - pad, dw = kw - pad, msel = 0;
+                if (cb.mode == MODE_S2) {
+                    const int qy = dh & 1, qx = dw & 1;  // parity of the source row / column
+                    msel = qy * 2 + qx;
+                    dh = (dh - qy) / 2;
+                    dw = (dw - qx) / 2;
+                } else if (cb.mode == MODE_UP2) {
+                    dh = static_cast<int>(floor((py + kh - 1) / 2.0));
+                    dw = static_cast<int>(floor((px + kw - 1) / 2.0));
+                }
+                int soff = 0;
+                for (size_t s = 0; s < cb.srcs.size(); ++s) {
+                    for (int c = 0; c < cb.srcs[s].C; c += 64) {
+                        KBlock& e = cp->kb[ph * nkb + i++];
+                        e.map = static_cast<int8_t>(cb.mode == MODE_S2 ? s * 4 + msel : s);
+                        e.dw = static_cast<int8_t>(dw);
+                        e.dh = static_cast<int8_t>(dh);
+                        e.pad = 0;
+                        e.c0 = static_cast<uint16_t>(c);
+                        e.wk = static_cast<uint16_t>((kh * cb.ksize + kw) * ctot + soff + c);
+                    }
+                    soff += cb.srcs[s].C;
+                }
+            }
+    }
+    cp->nkb = nkb;
+    cp->nphase = nphase;
+    cp->tiles_w = tiles_w;
+    cp->tiles_h = tiles_h;
+    cp->batch = B;
+    cp->bw_log2 = bwl;
+    cp->gw = gw;
+    cp->gh = gh;
+    cp->OH = OH;
+    cp->OW = OW;
+    cp->os = os;
+    cp->ldc = cb.epi == EPI_DDIM ? 3 : cb.out.C;
+    cp->n_total = w.n_pad;
+    cp->n_tiles = w.n_pad / bn;
+    cp->out = cb.out.p;
+    cp->bias = w.bias;
+    cp->residual = cb.residual;
+    cp->stats = cb.stats;
+    cp->x = cb.x;
+    cp->xpad = cb.xpad;
+    cp->x0_out = cb.x0_out;
+
+    const double M = static_cast<double>(B) * OH * OW;
+    op->name = cb.name;
+    op->flops = 2.0 * M * w.n_true * (static_cast<double>(taps) * w.c_true);
+    const double m_in = static_cast<double>(B) * cb.srcs[0].H * cb.srcs[0].W;
+    op->bytes = 2.0 * (m_in * w.c_true + M * w.n_true + static_cast<double>(taps) * w.c_true * w.n_true);
+    const int epi = cb.epi, cpg = cb.cpg;
+    const std::vector<float>*c0 = cb.c0, *c1 = cb.c1;
+    op->run = [cp, bn, cpg, epi, num_sms, c0, c1](cudaStream_t s, int k) -> cudaError_t {
+        if (epi == EPI_DDIM) {
+            if (!c0 || k < 0 || k >= static_cast<int>(c0->size())) return cudaErrorInvalidValue;
+            ConvParams q = *cp;
+            q.c0 = (*c0)[k];
+            q.c1 = (*c1)[k];
+            return launch_conv(q, bn, cpg, epi, num_sms, s);
+        }
+        return launch_conv(*cp, bn, cpg, epi, num_sms, s);
+    };
+    return CDC_OK;
+}
+
+static int conv_num_partials(const ConvBuild& cb) {
+    int gw, gh, nphase, os, bwl, tw, th;
+    conv_geometry(cb, gw, gh, nphase, os, bwl, tw, th);
+    return nphase * tw * th;
+}
+
+}  // namespace cdc
+
+using namespace cdc;
+
+struct WeightT {
+    float* p = nullptr;
+    std::vector<int64_t> shape;
+    size_t numel = 0;
+};
+
+struct cdc_ctx {
+    cdc_config cfg;
+    int device = 0, num_sms = 148;
+    std::string err;
+    std::map<std::string, WeightT> w;
+    std::map<std::string, ConvW> convs;
+    Arena warena;  // weights
+    bool finalized = false, has_ctx = false;
+    int C[4];
+
+    // schedule
+    int K = 0;
+    std::vector<int> idx;
+    std::vector<float> c0, c1;
+    float* film = nullptr;   // [K][film_total]
+    float* sinus = nullptr;  // [K][64]
+    int film_total = 0;
+    std::vector<int> film_off;  // per RB
+
+    // plan
+    Arena arena;
+    int B = 0, H = 0, W = 0;
+    std::vector<Op> step_ops, ctx_ops;
+    Act cond[4], xpad, latent;
+    float *xs = nullptr, *x0s = nullptr, *partials = nullptr;
+    float2* ab = nullptr;
+    float *stage_f32 = nullptr;  // NCHW fp32 staging for host-buffer calls
+    size_t stage_elems = 0;
+    float *pin_in = nullptr, *pin_x = nullptr, *pin_out = nullptr;
+    cudaGraphExec_t graph = nullptr;
+    int graph_K = 0;
+    cudaStream_t cap_stream = nullptr;
+
+    int fail(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+};
+
+#define CK(expr)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess) return ctx->fail(CDC_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+static cudaStream_t S(cdc_stream s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ------------------------------------------------------------------------------------------------ weights
+static const WeightT* find_w(cdc_ctx* ctx, const std::string& name) {
+    auto it = ctx->w.find(name);
+    return it == ctx->w.end() ? nullptr : &it->second;
+}
+
+// Repack "<pfx>.weight"/".bias" (OIHW fp32) to the K-conv layout.  `split`/`split_pad`: input channels
+// >= split start at slot split_pad (stem: 3 image channels padded to 64, then the 64 context channels).
+static int make_conv_w(cdc_ctx* ctx, Arena& ar, const float* wsrc, const float* bsrc, int O, int I, int ks, int split,
+                       int split_pad, bool is_final, ConvW* out, cudaStream_t s) {
+    const int taps = ks * ks;
+    const int c_pad = (split < I && split_pad > split) ? split_pad + ((I - split + 63) / 64) * 64 : ((I + 63) / 64) * 64;
+    const int n_pad = is_final ? 16 : ((O + 63) / 64) * 64;
+    ConvW cw;
+    cw.n_true = O;
+    cw.n_pad = n_pad;
+    cw.taps = taps;
+    cw.c_pad = c_pad;
+    cw.c_true = I;
+    CK(ar.alloc(reinterpret_cast<void**>(&cw.w), static_cast<size_t>(n_pad) * taps * c_pad * 2));
+    CK(ar.alloc(reinterpret_cast<void**>(&cw.bias), static_cast<size_t>(n_pad) * 4));
+    CK(cudaMemsetAsync(cw.bias, 0, static_cast<size_t>(n_pad) * 4, s));
+    CK(cudaMemcpyAsync(cw.bias, bsrc, static_cast<size_t>(O) * 4, cudaMemcpyDeviceToDevice, s));
+    const int sp = (split < I && split_pad > split) ? split : I;
+    const int spp = (split < I && split_pad > split) ? split_pad : I;
+    CK(launch_repack_weight(wsrc, cw.w, O, I, taps, n_pad, c_pad, sp, spp, s));
+    *out = cw;
+    return CDC_OK;
+}
+
+static int conv_from_store(cdc_ctx* ctx, const std::string& pfx, int O, int I, int ks, int split, int split_pad,
+                           bool is_final) {
+    const WeightT* w = find_w(ctx, pfx + ".weight");
+    const WeightT* b = find_w(ctx, pfx + ".bias");
+    if (!w || !b) return ctx->fail(CDC_ERR_WEIGHT, "missing weight tensor %s.weight/.bias", pfx.c_str());
+    if (w->shape.size() != 4 || w->shape[0] != O || w->shape[1] != I || w->shape[2] != ks || w->shape[3] != ks ||
+        b->numel != static_cast<size_t>(O))
+        return ctx->fail(CDC_ERR_WEIGHT, "%s: expected conv weight [%d,%d,%d,%d]", pfx.c_str(), O, I, ks, ks);
+    ConvW cw;
+    int r = make_conv_w(ctx, ctx->warena, w->p, b->p, O, I, ks, split, split_pad, is_final, &cw, nullptr);
+    if (r) return r;
+    ctx->convs[pfx] = cw;
+    return CDC_OK;
+}
+
+static int need_vec(cdc_ctx* ctx, const std::string& name, size_t n) {
+    const WeightT* w = find_w(ctx, name);
+    if (!w) return ctx->fail(CDC_ERR_WEIGHT, "missing weight tensor %s", name.c_str());
+    if (w->numel != n) return ctx->fail(CDC_ERR_WEIGHT, "%s: expected %zu elements, got %zu", name.c_str(), n, w->numel);
+    return CDC_OK;
+}
+
+static int rb_weights(cdc_ctx* ctx, const std::string& pfx, int cin, int cout, bool film) {
+    int r;
+    if ((r = conv_from_store(ctx, pfx + ".conv1", cout, cin, 3, cin, cin, false))) return r;
+    if ((r = conv_from_store(ctx, pfx + ".conv2", cout, cout, 3, cout, cout, false))) return r;
+    if (cin != cout && (r = conv_from_store(ctx, pfx + ".res", cout, cin, 1, cin, cin, false))) return r;
+    for (const char* g : {".gn1", ".gn2"}) {
+        if ((r = need_vec(ctx, pfx + g + ".weight", cout))) return r;
+        if ((r = need_vec(ctx, pfx + g + ".bias", cout))) return r;
+    }
+    if (film) {
+        if ((r = need_vec(ctx, pfx + ".film.weight", static_cast<size_t>(2) * cout * ctx->cfg.temb))) return r;
+        if ((r = need_vec(ctx, pfx + ".film.bias", static_cast<size_t>(2) * cout))) return r;
+    }
+    return CDC_OK;
+}
+
+static std::vector<std::string> film_rb_names(cdc_ctx* ctx, std::vector<int>* couts) {
+    std::vector<std::string> n;
+    for (int i = 0; i < 4; ++i)
+        for (const char* rb : {".rb1", ".rb2"}) {
+            n.push_back("down." + std::to_string(i) + rb);
+            couts->push_back(ctx->C[i]);
+        }
+    for (const char* rb : {"mid.rb1", "mid.rb2"}) {
+        n.push_back(rb);
+        couts->push_back(ctx->C[3]);
+    }
+    for (int i = 3; i >= 0; --i)
+        for (const char* rb : {".rb1", ".rb2"}) {
+            n.push_back("up." + std::to_string(i) + rb);
+            couts->push_back(ctx->C[i]);
+        }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------ plan
+struct PlanB {
+    cdc_ctx* ctx;
+    std::vector<Op>* ops;
+    std::map<std::string, Act> tmp;  // per-shape temporaries shared by the ResBlocks of a level
+    int rc = CDC_OK;
+
+    Act act(int C, int H, int W) {
+        Act a;
+        a.C = C;
+        a.H = H;
+        a.W = W;
+        if (cudaSuccess != ctx->arena.alloc(reinterpret_cast<void**>(&a.p), static_cast<size_t>(ctx->B) * H * W * C * 2)) {
+            rc = ctx->fail(CDC_ERR_CUDA, "workspace allocation failed (%d x %d x %d x %d bf16)", ctx->B, H, W, C);
+            a.p = nullptr;
+        }
+        return a;
+    }
+    Act shared(const std::string& tag, int C, int H, int W) {
+        const std::string key = tag + ":" + std::to_string(C) + "x" + std::to_string(H) + "x" + std::to_string(W);
+        auto it = tmp.find(key);
+        if (it != tmp.end()) return it->second;
+        Act a = act(C, H, W);
+        tmp[key] = a;
+        return a;
+    }
+    void conv(ConvBuild cb) {
+        if (rc) return;
+        Op op;
+        std::string e;
+        int r = build_conv(cb, ctx->B, ctx->num_sms, &op, &e);
+        if (r) {
+            rc = ctx->fail(r, "%s", e.c_str());
+            return;
+        }
+        ops->push_back(op);
+    }
+    // GN finalize (+FiLM of step k) and apply
+    void gn(const std::string& name, const std::string& gnp, int film_idx, int PT, Act x, const __nv_bfloat16* res, Act y,
+            bool silu) {
+        if (rc) return;
+        cdc_ctx* c = ctx;
+        const float* gamma = find_w(c, gnp + ".weight")->p;
+        const float* beta = find_w(c, gnp + ".bias")->p;
+        const int Cc = x.C, HW = x.H * x.W, B = c->B;
+        const int foff = film_idx >= 0 ? c->film_off[film_idx] : -1;
+        Op f;
+        f.name = name + ".finalize";
+        f.bytes = static_cast<double>(B) * PT * 64 * 4;
+        f.run = [c, PT, gamma, beta, foff, Cc, HW, B](cudaStream_t s, int k) {
+            const float* film = foff >= 0 ? c->film + static_cast<size_t>(k) * c->film_total + foff : nullptr;
+            return launch_gn_finalize(c->partials, PT, gamma, beta, film, c->ab, B, Cc, HW, c->cfg.gn_eps, s);
+        };
+        ops->push_back(f);
+        Op a;
+        a.name = name + (silu ? ".apply_silu" : ".apply") + (res ? "_res" : "");
+        a.bytes = static_cast<double>(B) * HW * Cc * 2 * (res ? 3 : 2);
+        const __nv_bfloat16 *xp = x.p, *rp = res;
+        __nv_bfloat16* yp = y.p;
+        const int si = silu ? 1 : 0;
+        a.run = [c, xp, rp, yp, B, HW, Cc, si](cudaStream_t s, int) {
+            return launch_gn_apply(xp, c->ab, rp, yp, B, HW, Cc, si, c->num_sms, s);
+        };
+        ops->push_back(a);
+    }
+    // Time-conditioned ResBlock (oracle/unet.py RB).  film_idx < 0: RBn (context net).
+    void rb(const std::string& name, const std::string& wp, std::vector<Act> in, int cout, int film_idx, Act out) {
+        if (rc) return;
+        const int H = in[0].H, W = in[0].W, cpg = cout / ctx->cfg.groups;
+        int cin = 0;
+        for (auto& a : in) cin += a.C;
+        Act t1 = shared("t1", cout, H, W), t2 = shared("t2", cout, H, W);
+        ConvBuild c1;
+        c1.name = name + ".conv1";
+        c1.srcs = in;
+        c1.w = &ctx->convs[wp + ".conv1"];
+        c1.out = t1;
+        c1.epi = EPI_STATS;
+        c1.cpg = cpg;
+        c1.stats = ctx->partials;
+        conv(c1);
+        gn(name + ".gn1", wp + ".gn1", film_idx, conv_num_partials(c1), t1, nullptr, t1, true);
+        ConvBuild c2;
+        c2.name = name + ".conv2";
+        c2.srcs = {t1};
+        c2.w = &ctx->convs[wp + ".conv2"];
+        c2.out = t2;
+        c2.epi = EPI_STATS;
+        c2.cpg = cpg;
+        c2.stats = ctx->partials;
+        conv(c2);
+        const __nv_bfloat16* resp = in[0].p;
+        if (cin != cout) {
+            Act r = shared("res", cout, H, W);
+            ConvBuild cr;
+            cr.name = name + ".res";
+            cr.srcs = in;
+            cr.w = &ctx->convs[wp + ".res"];
+            cr.ksize = 1;
+            cr.out = r;
+            conv(cr);
+            resp = r.p;
+        }
+        gn(name + ".gn2", wp + ".gn2", -1, conv_num_partials(c2), t2, resp, out, true);
+    }
+};
+
+static size_t max_partials_floats(cdc_ctx* ctx) {
+    // upper bound: one partial row (64 floats) per 128-pixel tile of the largest level, plus slack for ragged tiles
+    const size_t px = static_cast<size_t>(ctx->H) * ctx->W;
+    return static_cast<size_t>(ctx->B) * (px / 64 + 64) * 64;
+}
+
+static int build_plans(cdc_ctx* ctx) {
+    const int B = ctx->B, H = ctx->H, W = ctx->W;
+    const int* C = ctx->C;
+    Arena& ar = ctx->arena;
+    const size_t px = static_cast<size_t>(B) * H * W;
+    CK(ar.alloc(reinterpret_cast<void**>(&ctx->xs), px * 3 * 4));
+    CK(ar.alloc(reinterpret_cast<void**>(&ctx->x0s), px * 3 * 4));
+    CK(ar.alloc(reinterpret_cast<void**>(&ctx->partials), max_partials_floats(ctx) * 4));
+    CK(ar.alloc(reinterpret_cast<void**>(&ctx->ab), static_cast<size_t>(B) * 512 * sizeof(float2)));
+    ctx->stage_elems = px * 64;  // largest NCHW fp32 tensor crossing the boundary (c0)
+    CK(ar.alloc(reinterpret_cast<void**>(&ctx->stage_f32), ctx->stage_elems * 4));
+
+    PlanB pb;
+    pb.ctx = ctx;
+    pb.ops = &ctx->step_ops;
+    ctx->xpad = pb.act(64, H, W);
+    if (pb.rc) return pb.rc;
+    CK(cudaMemset(ctx->xpad.p, 0, px * 64 * 2));
+    for (int i = 0; i < 4; ++i) ctx->cond[i] = pb.act(C[i], H >> i, W >> i);
+    ctx->latent = pb.act(ctx->cfg.latent_ch, H >> 4, W >> 4);
+    if (pb.rc) return pb.rc;
+
+    // ---- one denoise step (oracle/unet.py UNet.forward + sampler.ddim_update) ----
+    int film = 0;
+    Act h = pb.act(C[0], H, W);
+    {
+        ConvBuild cb;
+        cb.name = "stem";
+        cb.srcs = {ctx->xpad, ctx->cond[0]};
+        cb.w = &ctx->convs["stem"];
+        cb.out = h;
+        pb.conv(cb);
+    }
+    Act skip[4];
+    for (int i = 0; i < 4; ++i) {
+        const int Hl = H >> i, Wl = W >> i;
+        const std::string p = "down." + std::to_string(i);
+        Act a = pb.act(C[i], Hl, Wl);
+        std::vector<Act> in = {h};
+        if (i > 0) in.push_back(ctx->cond[i]);
+        pb.rb(p + ".rb1", p + ".rb1", in, C[i], film++, a);
+        skip[i] = pb.act(C[i], Hl, Wl);
+        pb.rb(p + ".rb2", p + ".rb2", {a}, C[i], film++, skip[i]);
+        h = pb.act(C[i], Hl / 2, Wl / 2);
+        ConvBuild cb;
+        cb.name = p + ".down";
+        cb.srcs = {skip[i]};
+        cb.w = &ctx->convs[p + ".down"];
+        cb.mode = MODE_S2;
+        cb.out = h;
+        pb.conv(cb);
+    }
+    {
+        const int Hm = H >> 4, Wm = W >> 4, Cm = C[3], HW = Hm * Wm;
+        Act m1 = pb.act(Cm, Hm, Wm), m2 = pb.act(Cm, Hm, Wm), m3 = pb.act(Cm, Hm, Wm);
+        pb.rb("mid.rb1", "mid.rb1", {h}, Cm, film++, m1);
+        // attention: GN -> qkv 1x1 -> flash attention -> proj 1x1 + residual
+        Act n = pb.act(Cm, Hm, Wm), qkv = pb.act(3 * Cm, Hm, Wm), o = pb.act(Cm, Hm, Wm);
+        if (pb.rc) return pb.rc;
+        cdc_ctx* c = ctx;
+        Op st;
+        st.name = "mid.attn.gn.stats";
+        st.bytes = static_cast<double>(B) * HW * Cm * 2;
+        const __nv_bfloat16* m1p = m1.p;
+        st.run = [c, m1p, B, HW, Cm](cudaStream_t s, int) { return launch_gn_stats(m1p, c->partials, B, HW, Cm, nullptr, s); };
+        ctx->step_ops.push_back(st);
+        pb.gn("mid.attn.gn", "mid.attn.gn", -1, gn_stats_num_partials(HW), m1, nullptr, n, false);
+        ConvBuild cq;
+        cq.name = "mid.attn.qkv";
+        cq.srcs = {n};
+        cq.w = &ctx->convs["mid.attn.qkv"];
+        cq.ksize = 1;
+        cq.out = qkv;
+        pb.conv(cq);
+        Op at;
+        at.name = "mid.attn.sdpa";
+        at.flops = static_cast<double>(B) * ctx->cfg.heads * 4.0 * HW * HW * ctx->cfg.head_dim;
+        at.bytes = static_cast<double>(B) * HW * Cm * 2 * 4;
+        const __nv_bfloat16* qp = qkv.p;
+        __nv_bfloat16* op_ = o.p;
+        const int heads = ctx->cfg.heads;
+        at.run = [qp, op_, B, HW, heads](cudaStream_t s, int) { return launch_attention(qp, op_, B, HW, heads, s); };
+        ctx->step_ops.push_back(at);
+        ConvBuild cpj;
+        cpj.name = "mid.attn.proj";
+        cpj.srcs = {o};
+        cpj.w = &ctx->convs["mid.attn.proj"];
+        cpj.ksize = 1;
+        cpj.out = m2;
+        cpj.residual = m1.p;
+        pb.conv(cpj);
+        pb.rb("mid.rb2", "mid.rb2", {m2}, Cm, film++, m3);
+        h = m3;
+    }
+    for (int i = 3; i >= 0; --i) {
+        const int Hl = H >> i, Wl = W >> i;
+        const std::string p = "up." + std::to_string(i);
+        Act u = pb.act(C[i], Hl, Wl);
+        ConvBuild cb;
+        cb.name = p + ".up";
+        cb.srcs = {h};
+        cb.w = &ctx->convs[p + ".up.up"];
+        cb.mode = MODE_UP2;
+        cb.out = u;
+        pb.conv(cb);
+        Act a = pb.act(C[i], Hl, Wl);
+        pb.rb(p + ".rb1", p + ".rb1", {u, skip[i]}, C[i], film++, a);
+        h = pb.act(C[i], Hl, Wl);
+        pb.rb(p + ".rb2", p + ".rb2", {a}, C[i], film++, h);
+    }
+    {
+        ConvBuild cb;
+        cb.name = "final+ddim";
+        cb.srcs = {h};
+        cb.w = &ctx->convs["final"];
+        cb.epi = EPI_DDIM;
+        cb.x = ctx->xs;
+        cb.xpad = ctx->xpad.p;
+        cb.x0_out = ctx->x0s;
+        cb.c0 = &ctx->c0;
+        cb.c1 = &ctx->c1;
+        pb.conv(cb);
+    }
+    if (pb.rc) return pb.rc;
+
+    // ---- context net (oracle/codec.py ContextNet): cond = context_net(y_hat), once per image ----
+    if (ctx->has_ctx) {
+        PlanB pc;
+        pc.ctx = ctx;
+        pc.ops = &ctx->ctx_ops;
+        Act hh = ctx->latent;
+        for (int i = 3; i >= 0; --i) {
+            const int Hl = H >> i, Wl = W >> i;
+            const std::string p = "context.ups." + std::to_string(i), r = "context.rbs." + std::to_string(i);
+            Act u = pc.act(C[i], Hl, Wl);
+            ConvBuild cb;
+            cb.name = p;
+            cb.srcs = {hh};
+            cb.w = &ctx->convs[p + ".up"];
+            cb.mode = MODE_UP2;
+            cb.out = u;
+            pc.conv(cb);
+            pc.rb(r, r, {u}, C[i], -1, ctx->cond[i]);
+            hh = ctx->cond[i];
+        }
+        if (pc.rc) return pc.rc;
+    }
+    return CDC_OK;
+}
+
+static void drop_graph(cdc_ctx* ctx) {
+    if (ctx->graph) cudaGraphExecDestroy(ctx->graph);
+    ctx->graph = nullptr;
+    ctx->graph_K = 0;
+}
+
+static int capture_graph(cdc_ctx* ctx) {
+    drop_graph(ctx);
+    if (!ctx->cap_stream) CK(cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking));
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(ctx->cap_stream, cudaStreamCaptureModeThreadLocal));
+    cudaError_t e = cudaSuccess;
+    std::string bad;
+    for (int k = 0; k < ctx->K && e == cudaSuccess; ++k)
+        for (Op& op : ctx->step_ops) {
+            e = op.run(ctx->cap_stream, k);
+            if (e != cudaSuccess) {
+                bad = op.name;
+                break;
+            }
+        }
+    cudaError_t e2 = cudaStreamEndCapture(ctx->cap_stream, &g);
+    if (e != cudaSuccess) {
+        if (g) cudaGraphDestroy(g);
+        return ctx->fail(CDC_ERR_CUDA, "graph capture: %s failed: %s", bad.c_str(), cudaGetErrorString(e));
+    }
+    CK(e2);
+    e = cudaGraphInstantiate(&ctx->graph, g, 0);
+    cudaGraphDestroy(g);
+    CK(e);
+    ctx->graph_K = ctx->K;
+    return CDC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+int cdc_abi_version(void) { return 1; }
+
+const char* cdc_last_error(cdc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int cdc_create(const cdc_config* cfg, int device, cdc_ctx** out) {
+    if (!cfg || !out) {
+        g_create_err = "null argument";
+        return CDC_ERR_SHAPE;
+    }
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        g_create_err = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
+        return CDC_ERR_CUDA;
+    }
+    if (prop.major != 10) {
+        g_create_err = "device is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                       "; this library is sm_100a only and has no fallback";
+        return CDC_ERR_ARCH;
+    }
+    if (cfg->groups != 32 || cfg->head_dim != 64 || cfg->heads * cfg->head_dim != cfg->base * cfg->mults[3] ||
+        cfg->base != 64 || cfg->temb > 256 || cfg->latent_ch % 64) {
+        g_create_err = "unsupported config (need base 64, 32 groups, head_dim 64, temb <= 256)";
+        return CDC_ERR_SHAPE;
+    }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) {
+        g_create_err = cudaGetErrorString(e);
+        return CDC_ERR_CUDA;
+    }
+    if (!get_encode()) {
+        g_create_err = "cuTensorMapEncodeTiled entry point not found";
+        return CDC_ERR_CUDA;
+    }
+    if ((e = configure_conv_kernels()) != cudaSuccess) {
+        g_create_err = std::string("cudaFuncSetAttribute(conv_tc_kernel): ") + cudaGetErrorString(e);
+        return CDC_ERR_CUDA;
+    }
+    cdc_ctx* ctx = new cdc_ctx();
+    ctx->cfg = *cfg;
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    for (int i = 0; i < 4; ++i) ctx->C[i] = cfg->base * cfg->mults[i];
+    *out = ctx;
+    return CDC_OK;
+}
+
+void cdc_destroy(cdc_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    drop_graph(ctx);
+    if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
+    ctx->arena.release();
+    ctx->warena.release();
+    if (ctx->film) cudaFree(ctx->film);
+    if (ctx->sinus) cudaFree(ctx->sinus);
+    if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
+    if (ctx->pin_x) cudaFreeHost(ctx->pin_x);
+    if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
+    delete ctx;
+}
+
+int cdc_load_weights(cdc_ctx* ctx, const char* name, const void* dev_ptr, const int64_t* shape, int ndim) {
+    if (!ctx || !name || !dev_ptr || ndim < 1 || ndim > 4) return ctx ? ctx->fail(CDC_ERR_SHAPE, "bad argument") : CDC_ERR_SHAPE;
+    if (ctx->finalized) return ctx->fail(CDC_ERR_STATE, "weights already finalized");
+    WeightT t;
+    t.numel = 1;
+    for (int i = 0; i < ndim; ++i) {
+        t.shape.push_back(shape[i]);
+        t.numel *= static_cast<size_t>(shape[i]);
+    }
+    CK(ctx->warena.alloc(reinterpret_cast<void**>(&t.p), t.numel * 4));
+    CK(cudaMemcpy(t.p, dev_ptr, t.numel * 4, cudaMemcpyDeviceToDevice));
+    ctx->w[name] = t;
+    return CDC_OK;
+}
+
+int cdc_finalize_weights(cdc_ctx* ctx) {
+    if (!ctx) return CDC_ERR_STATE;
+    if (ctx->finalized) return CDC_OK;
+    const int* C = ctx->C;
+    int r;
+    // stem: cat[x_t (3), c0 (64)] -> image channels padded to 64, context follows at slot 64
+    if ((r = conv_from_store(ctx, "stem", C[0], 3 + C[0], 3, 3, 64, false))) return r;
+    for (int i = 0; i < 4; ++i) {
+        const std::string p = "down." + std::to_string(i);
+        const int cin = i == 0 ? C[0] : C[i - 1] + C[i];
+        if ((r = rb_weights(ctx, p + ".rb1", cin, C[i], true))) return r;
+        if ((r = rb_weights(ctx, p + ".rb2", C[i], C[i], true))) return r;
+        if ((r = conv_from_store(ctx, p + ".down", C[i], C[i], 3, C[i], C[i], false))) return r;
+    }
+    if ((r = rb_weights(ctx, "mid.rb1", C[3], C[3], true))) return r;
+    if ((r = rb_weights(ctx, "mid.rb2", C[3], C[3], true))) return r;
+    if ((r = need_vec(ctx, "mid.attn.gn.weight", C[3])) || (r = need_vec(ctx, "mid.attn.gn.bias", C[3]))) return r;
+    if ((r = conv_from_store(ctx, "mid.attn.qkv", 3 * C[3], C[3], 1, C[3], C[3], false))) return r;
+    if ((r = conv_from_store(ctx, "mid.attn.proj", C[3], C[3], 1, C[3], C[3], false))) return r;
+    int prev = C[3];
+    for (int i = 3; i >= 0; --i) {
+        const std::string p = "up." + std::to_string(i);
+        if ((r = conv_from_store(ctx, p + ".up.up", C[i], prev, 3, prev, prev, false))) return r;
+        if ((r = rb_weights(ctx, p + ".rb1", 2 * C[i], C[i], true))) return r;
+        if ((r = rb_weights(ctx, p + ".rb2", C[i], C[i], true))) return r;
+        prev = C[i];
+    }
+    if ((r = conv_from_store(ctx, "final", 3, C[0], 3, C[0], C[0], true))) return r;
+    const int te = ctx->cfg.temb;
+    if ((r = need_vec(ctx, "temb.lin1.weight", static_cast<size_t>(te) * 64)) || (r = need_vec(ctx, "temb.lin1.bias", te)) ||
+        (r = need_vec(ctx, "temb.lin2.weight", static_cast<size_t>(te) * te)) || (r = need_vec(ctx, "temb.lin2.bias", te)))
+        return r;
+    // optional context net
+    ctx->has_ctx = find_w(ctx, "context.ups.3.up.weight") != nullptr;
+    if (ctx->has_ctx) {
+        prev = ctx->cfg.latent_ch;
+        for (int i = 3; i >= 0; --i) {
+            const std::string s = std::to_string(i);
+            if ((r = conv_from_store(ctx, "context.ups." + s + ".up", C[i], prev, 3, prev, prev, false))) return r;
+            if ((r = rb_weights(ctx, "context.rbs." + s, C[i], C[i], false))) return r;
+            prev = C[i];
+        }
+    }
+    // FiLM offsets
+    std::vector<int> couts;
+    film_rb_names(ctx, &couts);
+    ctx->film_off.clear();
+    int off = 0;
+    for (int c : couts) {
+        ctx->film_off.push_back(off);
+        off += 2 * c;
+    }
+    ctx->film_total = off;
+    CK(cudaDeviceSynchronize());
+    ctx->finalized = true;
+    return CDC_OK;
+}
+
+int cdc_has_context_net(cdc_ctx* ctx) { return ctx && ctx->has_ctx ? 1 : 0; }
+
+int cdc_set_schedule(cdc_ctx* ctx, int K) {
+    if (!ctx || !ctx->finalized) return ctx ? ctx->fail(CDC_ERR_STATE, "finalize weights first") : CDC_ERR_STATE;
+    if (K < 1 || K > ctx->cfg.T) return ctx->fail(CDC_ERR_SHAPE, "steps must be in [1, T]");
+    const int T = ctx->cfg.T;
+    // cosine schedule, float64 (oracle/sampler.py alphas_cumprod)
+    std::vector<double> ab(T);
+    auto f = [&](double u) {
+        const double c = cos((u / T + 0.008) / 1.008 * M_PI / 2.0);
+        return c * c;
+    };
+    double cum = 1.0;
+    for (int t = 0; t < T; ++t) {
+        double beta = 1.0 - f(t + 1.0) / f(static_cast<double>(t));
+        beta = beta < 0.0 ? 0.0 : (beta > 0.999 ? 0.999 : beta);
+        cum *= 1.0 - beta;
+        ab[t] = cum;
+    }
+    std::vector<int> idx(K);
+    std::vector<float> c0(K), c1(K);
+    for (int k = 0; k < K; ++k)
+        idx[k] = K == 1 ? T - 1 : static_cast<int>((static_cast<long long>(K - 1 - k) * (T - 1) + (K - 1) / 2) / (K - 1));
+    for (int k = 0; k < K; ++k) {
+        const double at = ab[idx[k]], ap = k + 1 < K ? ab[idx[k + 1]] : 1.0;
+        const double v1 = sqrt(1.0 - ap) / sqrt(1.0 - at);
+        c1[k] = static_cast<float>(v1);
+        c0[k] = static_cast<float>(sqrt(ap) - v1 * sqrt(at));
+    }
+    // the graph bakes per-step pointers/coefficients: any schedule change invalidates it
+    drop_graph(ctx);
+    ctx->K = K;
+    ctx->idx = idx;
+    ctx->c0 = c0;
+    ctx->c1 = c1;
+
+    // sinusoidal embedding per step (host, float64 -> fp32), then MLP + FiLM on the device
+    std::vector<float> sin_h(static_cast<size_t>(K) * 64);
+    for (int k = 0; k < K; ++k)
+        for (int j = 0; j < 32; ++j) {
+            const float fj = static_cast<float>(exp(-log(10000.0) * j / 32.0));
+            const float a = static_cast<float>(idx[k]) * fj;  // fp32 product like the oracle
+            sin_h[static_cast<size_t>(k) * 64 + j] = static_cast<float>(sin(static_cast<double>(a)));
+            sin_h[static_cast<size_t>(k) * 64 + 32 + j] = static_cast<float>(cos(static_cast<double>(a)));
+        }
+    if (ctx->film) cudaFree(ctx->film);
+    if (ctx->sinus) cudaFree(ctx->sinus);
+    ctx->film = nullptr;
+    ctx->sinus = nullptr;
+    CK(cudaMalloc(&ctx->film, static_cast<size_t>(K) * ctx->film_total * 4));
+    CK(cudaMalloc(&ctx->sinus, sin_h.size() * 4));
+    CK(cudaMemcpy(ctx->sinus, sin_h.data(), sin_h.size() * 4, cudaMemcpyHostToDevice));
+    FilmParams fp;
+    memset(&fp, 0, sizeof fp);
+    fp.sinus = ctx->sinus;
+    fp.w1 = find_w(ctx, "temb.lin1.weight")->p;
+    fp.b1 = find_w(ctx, "temb.lin1.bias")->p;
+    fp.w2 = find_w(ctx, "temb.lin2.weight")->p;
+    fp.b2 = find_w(ctx, "temb.lin2.bias")->p;
+    std::vector<int> couts;
+    std::vector<std::string> names = film_rb_names(ctx, &couts);
+    fp.nlayers = static_cast<int>(names.size());
+    for (int i = 0; i < fp.nlayers; ++i) {
+        fp.layer[i].w = find_w(ctx, names[i] + ".film.weight")->p;
+        fp.layer[i].b = find_w(ctx, names[i] + ".film.bias")->p;
+        fp.layer[i].c2 = 2 * couts[i];
+        fp.layer[i].offset = ctx->film_off[i];
+    }
+    fp.temb = ctx->cfg.temb;
+    fp.total = ctx->film_total;
+    fp.out = ctx->film;
+    CK(launch_temb_film(fp, K, nullptr));
+    CK(cudaDeviceSynchronize());
+    return CDC_OK;
+}
+
+int cdc_schedule_index(cdc_ctx* ctx, int k) { return (ctx && k >= 0 && k < ctx->K) ? ctx->idx[k] : -1; }
+
+int cdc_schedule_coeffs(cdc_ctx* ctx, int k, float* c0, float* c1) {
+    if (!ctx || k < 0 || k >= ctx->K) return CDC_ERR_SHAPE;
+    *c0 = ctx->c0[k];
+    *c1 = ctx->c1[k];
+    return CDC_OK;
+}
+
+int cdc_bind_io(cdc_ctx* ctx, int B, int H, int W) {
+    if (!ctx || !ctx->finalized) return ctx ? ctx->fail(CDC_ERR_STATE, "finalize weights first") : CDC_ERR_STATE;
+    if (B < 1 || H < 64 || W < 64 || (H % 64) || (W % 64)) return ctx->fail(CDC_ERR_SHAPE, "H and W must be multiples of 64, batch >= 1");
+    if (B == ctx->B && H == ctx->H && W == ctx->W && !ctx->step_ops.empty()) return CDC_OK;
+    CK(cudaDeviceSynchronize());
+    drop_graph(ctx);
+    ctx->step_ops.clear();
+    ctx->ctx_ops.clear();
+    ctx->arena.release();
+    ctx->B = B;
+    ctx->H = H;
+    ctx->W = W;
+    int r = build_plans(ctx);
+    if (r) {
+        ctx->step_ops.clear();
+        ctx->ctx_ops.clear();
+        ctx->arena.release();
+        ctx->B = ctx->H = ctx->W = 0;
+        return r;
+    }
+    CK(cudaDeviceSynchronize());
+    return CDC_OK;
+}
+
+#define NEED_PLAN()                                                                     \
+    if (!ctx || ctx->step_ops.empty()) return ctx ? ctx->fail(CDC_ERR_STATE, "call cdc_bind_io first") : CDC_ERR_STATE
+
+int cdc_set_cond(cdc_ctx* ctx, const float* c0, const float* c1, const float* c2, const float* c3, cdc_stream s) {
+    NEED_PLAN();
+    const float* src[4] = {c0, c1, c2, c3};
+    for (int i = 0; i < 4; ++i) {
+        const Act& a = ctx->cond[i];
+        CK(launch_nchw_f32_to_nhwc_bf16(src[i], a.p, ctx->B, a.C, a.H * a.W, a.C, S(s)));
+    }
+    return CDC_OK;
+}
+
+int cdc_set_latent(cdc_ctx* ctx, const float* y_hat, cdc_stream s) {
+    NEED_PLAN();
+    if (!ctx->has_ctx) return ctx->fail(CDC_ERR_WEIGHT, "context-net weights (context.*) were not loaded");
+    const Act& a = ctx->latent;
+    CK(launch_nchw_f32_to_nhwc_bf16(y_hat, a.p, ctx->B, a.C, a.H * a.W, a.C, S(s)));
+    for (Op& op : ctx->ctx_ops) {
+        cudaError_t e = op.run(S(s), 0);
+        if (e != cudaSuccess) return ctx->fail(CDC_ERR_CUDA, "%s: %s", op.name.c_str(), cudaGetErrorString(e));
+    }
+    return CDC_OK;
+}
+
+int cdc_set_x(cdc_ctx* ctx, const float* x, cdc_stream s) {
+    NEED_PLAN();
+    CK(launch_x_in(x, ctx->xs, ctx->xpad.p, ctx->B, ctx->H * ctx->W, S(s)));
+    return CDC_OK;
+}
+
+int cdc_get_x(cdc_ctx* ctx, float* x, int to_image, cdc_stream s) {
+    NEED_PLAN();
+    CK(launch_x_out(ctx->xs, x, ctx->B, ctx->H * ctx->W, to_image, S(s)));
+    return CDC_OK;
+}
+
+int cdc_get_x0(cdc_ctx* ctx, float* x0, cdc_stream s) {
+    NEED_PLAN();
+    CK(launch_x_out(ctx->x0s, x0, ctx->B, ctx->H * ctx->W, 0, S(s)));
+    return CDC_OK;
+}
+
+int cdc_denoise_step(cdc_ctx* ctx, int k, cdc_stream s) {
+    NEED_PLAN();
+    if (k < 0 || k >= ctx->K) return ctx->fail(CDC_ERR_SHAPE, "step %d outside the %d-step schedule", k, ctx->K);
+    for (Op& op : ctx->step_ops) {
+        cudaError_t e = op.run(S(s), k);
+        if (e != cudaSuccess) return ctx->fail(CDC_ERR_CUDA, "%s: %s", op.name.c_str(), cudaGetErrorString(e));
+    }
+    return CDC_OK;
+}
+
+int cdc_decode(cdc_ctx* ctx, cdc_stream s) {
+    NEED_PLAN();
+    if (ctx->K < 1) return ctx->fail(CDC_ERR_STATE, "call cdc_set_schedule first");
+    if (!ctx->graph || ctx->graph_K != ctx->K) {
+        int r = capture_graph(ctx);
+        if (r) return r;
+    }
+    CK(cudaGraphLaunch(ctx->graph, S(s)));
+    return CDC_OK;
+}
+
+int cdc_decode_host(cdc_ctx* ctx, const float* latent_host, const float* xT_host, float* image_host, cdc_stream s) {
+    NEED_PLAN();
+    const size_t nl = static_cast<size_t>(ctx->B) * ctx->cfg.latent_ch * (ctx->H / 16) * (ctx->W / 16);
+    const size_t nx = static_cast<size_t>(ctx->B) * 3 * ctx->H * ctx->W;
+    if (!ctx->pin_in) {
+        CK(cudaMallocHost(&ctx->pin_in, nl * 4));
+        CK(cudaMallocHost(&ctx->pin_x, nx * 4));
+        CK(cudaMallocHost(&ctx->pin_out, nx * 4));
+    }
+    memcpy(ctx->pin_in, latent_host, nl * 4);
+    memcpy(ctx->pin_x, xT_host, nx * 4);
+    float* d_lat = ctx->stage_f32;
+    float* d_x = ctx->stage_f32 + nl;
+    if (nl + nx > ctx->stage_elems) return ctx->fail(CDC_ERR_SHAPE, "staging buffer too small");
+    CK(cudaMemcpyAsync(d_lat, ctx->pin_in, nl * 4, cudaMemcpyHostToDevice, S(s)));
+    CK(cudaMemcpyAsync(d_x, ctx->pin_x, nx * 4, cudaMemcpyHostToDevice, S(s)));
+    int r;
+    if ((r = cdc_set_latent(ctx, d_lat, s))) return r;
+    if ((r = cdc_set_x(ctx, d_x, s))) return r;
+    if ((r = cdc_decode(ctx, s))) return r;
+    if ((r = cdc_get_x(ctx, d_x, 1, s))) return r;
+    CK(cudaMemcpyAsync(ctx->pin_out, d_x, nx * 4, cudaMemcpyDeviceToHost, S(s)));
+    CK(cudaStreamSynchronize(S(s)));
+    memcpy(image_host, ctx->pin_out, nx * 4);
+    return CDC_OK;
+}
+
+int cdc_launches_per_step(cdc_ctx* ctx) { return ctx ? static_cast<int>(ctx->step_ops.size()) : 0; }
+int cdc_launches_context(cdc_ctx* ctx) { return ctx ? static_cast<int>(ctx->ctx_ops.size()) + 1 : 0; }
+
+double cdc_flops_per_step(cdc_ctx* ctx) {
+    if (!ctx) return 0;
+    double f = 0;
+    for (Op& op : ctx->step_ops) f += op.flops;
+    // time-embedding MLP + FiLM linears (precomputed per schedule; counted for parity with SURVEY 8d)
+    f += 2.0 * ctx->B * (64.0 * ctx->cfg.temb + static_cast<double>(ctx->cfg.temb) * ctx->cfg.temb);
+    f += 2.0 * ctx->B * ctx->cfg.temb * static_cast<double>(ctx->film_total);
+    return f;
+}
+
+int cdc_num_step_ops(cdc_ctx* ctx) { return ctx ? static_cast<int>(ctx->step_ops.size()) : 0; }
+const char* cdc_step_op_name(cdc_ctx* ctx, int i) {
+    return (ctx && i >= 0 && i < static_cast<int>(ctx->step_ops.size())) ? ctx->step_ops[i].name.c_str() : "";
+}
+double cdc_step_op_flops(cdc_ctx* ctx, int i) {
+    return (ctx && i >= 0 && i < static_cast<int>(ctx->step_ops.size())) ? ctx->step_ops[i].flops : 0;
+}
+double cdc_step_op_bytes(cdc_ctx* ctx, int i) {
+    return (ctx && i >= 0 && i < static_cast<int>(ctx->step_ops.size())) ? ctx->step_ops[i].bytes : 0;
+}
+int cdc_run_step_op(cdc_ctx* ctx, int i, int k, cdc_stream s) {
+    NEED_PLAN();
+    if (i < 0 || i >= static_cast<int>(ctx->step_ops.size()) || k < 0 || k >= ctx->K) return ctx->fail(CDC_ERR_SHAPE, "bad op/step index");
+    CK(ctx->step_ops[i].run(S(s), k));
+    return CDC_OK;
+}
+
+// ---- stateless integer path ----
+static int dev_sms() {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+}
+
+int cdc_quantize(const float* y, const float* mu, int32_t* q, float* y_hat, int64_t n, int64_t mu_inner, int64_t mu_mod,
+                 cdc_stream s) {
+    if (n < 0 || (n > 0 && (!y || !mu || !q))) return CDC_ERR_SHAPE;
+    if (mu_mod && mu_inner < 1) return CDC_ERR_SHAPE;
+    return launch_quantize(y, mu, q, y_hat, n, mu_inner, mu_mod, dev_sms(), S(s)) == cudaSuccess ? CDC_OK : CDC_ERR_CUDA;
+}
+
+int cdc_cdf_lookup(const int32_t* q, const float* sigma, const int32_t* cdf, const int32_t* row_start,
+                   const int32_t* cdf_length, const int32_t* offset, const float* scale_table, int rows, int64_t inner,
+                   int32_t* idx, int32_t* v, int32_t* lo, int32_t* hi, int32_t* raw, int64_t n, cdc_stream s) {
+    if (n < 0 || rows < 1 || rows > 256 || (!sigma && inner < 1)) return CDC_ERR_SHAPE;
+    CdfTables t{cdf, row_start, cdf_length, offset, scale_table, rows};
+    return launch_cdf_lookup(q, sigma, t, inner, idx, v, lo, hi, raw, n, dev_sms(), S(s)) == cudaSuccess ? CDC_OK
+                                                                                                        : CDC_ERR_CUDA;
+}
+
+// ---- single-op entry points for kernel-level parity tests ----
+int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1, int B, int H, int W,
+                  const float* w_oihw, const float* bias, int cout, int ksize, int mode, int force_bn,
+                  const void* residual, void* out, float* stats, int* pt_out, cdc_stream s) {
+    cdc_ctx tmp;
+    cdc_ctx* ctx = &tmp;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        g_create_err = "not an sm_100 device";
+        return CDC_ERR_ARCH;
+    }
+    Arena ar;
+    ConvW cw;
+    const int cin = c0 + c1;
+    int r = make_conv_w(ctx, ar, w_oihw, bias, cout, cin, ksize, cin, cin, false, &cw, S(s));
+    if (r) {
+        g_create_err = tmp.err;
+        ar.release();
+        return r;
+    }
+    ConvBuild cb;
+    cb.name = "test_conv";
+    Act a0;
+    a0.p = static_cast<__nv_bfloat16*>(const_cast<void*>(src0));
+    a0.C = c0;
+    a0.H = H;
+    a0.W = W;
+    cb.srcs.push_back(a0);
+    if (src1) {
+        Act a1 = a0;
+        a1.p = static_cast<__nv_bfloat16*>(const_cast<void*>(src1));
+        a1.C = c1;
+        cb.srcs.push_back(a1);
+    }
+    cb.w = &cw;
+    cb.mode = mode;
+    cb.ksize = ksize;
+    cb.out.p = static_cast<__nv_bfloat16*>(out);
+    cb.out.C = cw.n_pad;
+    cb.out.H = mode == MODE_S2 ? H / 2 : (mode == MODE_UP2 ? 2 * H : H);
+    cb.out.W = mode == MODE_S2 ? W / 2 : (mode == MODE_UP2 ? 2 * W : W);
+    cb.residual = static_cast<const __nv_bfloat16*>(residual);
+    cb.force_bn = force_bn;
+    if (stats) {
+        cb.epi = EPI_STATS;
+        cb.cpg = cout / 32;
+        cb.stats = stats;
+        if (pt_out) *pt_out = conv_num_partials(cb);
+    }
+    Op op;
+    std::string e;
+    r = build_conv(cb, B, prop.multiProcessorCount, &op, &e);
+    if (r) {
+        g_create_err = e;
+        ar.release();
+        return r;
+    }
+    cudaError_t ce = op.run(S(s), 0);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(S(s));
+    ar.release();
+    if (ce != cudaSuccess) {
+        g_create_err = std::string("test_conv: ") + cudaGetErrorString(ce);
+        return CDC_ERR_CUDA;
+    }
+    return CDC_OK;
+}
+
+int cdc_test_attention(const void* qkv, void* out, int B, int N, int heads, cdc_stream s) {
+    return launch_attention(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), B, N, heads, S(s)) ==
+                   cudaSuccess
+               ? CDC_OK
+               : CDC_ERR_CUDA;
+}
+
+int cdc_test_gn(const void* x, const void* r, void* y, const float* gamma, const float* beta, const float* film, int B,
+                int HW, int C, int silu, float eps, cdc_stream s) {
+    float* partials = nullptr;
+    float2* ab = nullptr;
+    const int PT = gn_stats_num_partials(HW);
+    if (cudaMalloc(&partials, static_cast<size_t>(B) * PT * 64 * 4) != cudaSuccess) return CDC_ERR_CUDA;
+    if (cudaMalloc(&ab, static_cast<size_t>(B) * C * sizeof(float2)) != cudaSuccess) {
+        cudaFree(partials);
+        return CDC_ERR_CUDA;
+    }
+    cudaError_t e = launch_gn_stats(static_cast<const __nv_bfloat16*>(x), partials, B, HW, C, nullptr, S(s));
+    if (e == cudaSuccess) e = launch_gn_finalize(partials, PT, gamma, beta, film, ab, B, C, HW, eps, S(s));
+    if (e == cudaSuccess)
+        e = launch_gn_apply(static_cast<const __nv_bfloat16*>(x), ab, static_cast<const __nv_bfloat16*>(r),
+                            static_cast<__nv_bfloat16*>(y), B, HW, C, silu, dev_sms(), S(s));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(S(s));
+    cudaFree(partials);
+    cudaFree(ab);
+    return e == cudaSuccess ? CDC_OK : CDC_ERR_CUDA;
+}
+
+}  // extern "C"

@@ -1,0 +1,121 @@
+/* cdc_b200 -- C ABI of the B200-native CDC decode hot path.
+ *
+ * Drop-in boundary.  The reference repository ships no code
+ * (/root/reference/README.md is 0 bytes, /root/reference/.gitignore:1-27 is a stock template), so
+ * there is no reference FFI to cite line by line; each entry point below names the ORACLE
+ * function it replaces (the parity source pinned by BASELINE.json `north_star`), which is what a
+ * maintainer of the reference would bind through ctypes.
+ *
+ * Conventions: plain pointers and sizes only; all tensor pointers are DEVICE pointers unless the
+ * name says `_host`; tensors cross the boundary as contiguous NCHW fp32 (the layout of the
+ * oracle's torch tensors) and are converted to the internal NHWC bf16 layout on the device.
+ * Every call returns 0 on success or a negative cdc_status; the message is available from
+ * cdc_last_error().  Nothing throws across the ABI.  There is NO CPU fallback: a device that is
+ * not sm_100 is CDC_ERR_ARCH.  One cdc_ctx per (process, device); not thread-safe; all work is
+ * enqueued on the caller's stream (pass 0 for the legacy default stream).
+ */
+#ifndef CDC_B200_H
+#define CDC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cdc_ctx cdc_ctx;
+typedef void* cdc_stream; /* cudaStream_t */
+
+typedef enum {
+    CDC_OK = 0,
+    CDC_ERR_SHAPE = -1,
+    CDC_ERR_ARCH = -2,
+    CDC_ERR_CUDA = -3,
+    CDC_ERR_UNIMPLEMENTED = -4,
+    CDC_ERR_STATE = -5,
+    CDC_ERR_WEIGHT = -6
+} cdc_status;
+
+/* oracle/config.py CDCConfig */
+typedef struct {
+    int32_t base;      /* 64 */
+    int32_t mults[4];  /* 1,2,3,4 */
+    int32_t groups;    /* 32 */
+    int32_t heads;     /* 4 */
+    int32_t head_dim;  /* 64 */
+    int32_t temb;      /* 256 */
+    int32_t T;         /* 1000 */
+    int32_t latent_ch; /* 256 */
+    float gn_eps;      /* 1e-5 */
+} cdc_config;
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+int cdc_create(const cdc_config* cfg, int device, cdc_ctx** out);
+void cdc_destroy(cdc_ctx* ctx);
+const char* cdc_last_error(cdc_ctx* ctx); /* ctx may be NULL: last error of a failed cdc_create */
+int cdc_abi_version(void);
+
+/* ---- weights: oracle/unet.py UNet.state_dict() (+ "context." + oracle/codec.py ContextNet) ----
+ * `name` is the state-dict key, `dev_ptr` a device fp32 tensor in PyTorch layout (conv OIHW,
+ * linear [out][in]).  The data is copied; the caller may free it after the call returns and the
+ * stream is synchronised.  cdc_finalize_weights() repacks conv weights to bf16 [C_out][kh][kw][C_in]
+ * and fails with CDC_ERR_WEIGHT naming the first missing tensor. */
+int cdc_load_weights(cdc_ctx* ctx, const char* name, const void* dev_ptr, const int64_t* shape, int ndim);
+int cdc_finalize_weights(cdc_ctx* ctx);
+int cdc_has_context_net(cdc_ctx* ctx);
+
+/* ---- oracle/sampler.py make_schedule / OracleDecoder.set_sample_schedule ---------------------- */
+int cdc_set_schedule(cdc_ctx* ctx, int steps);
+int cdc_schedule_index(cdc_ctx* ctx, int k);              /* training index idx_k, or <0 */
+int cdc_schedule_coeffs(cdc_ctx* ctx, int k, float* c0, float* c1);
+
+/* ---- shape binding: allocates the workspace arena, builds tensor maps and the launch plan ------ */
+int cdc_bind_io(cdc_ctx* ctx, int batch, int height, int width);
+int cdc_set_cond(cdc_ctx* ctx, const float* c0, const float* c1, const float* c2, const float* c3, cdc_stream s);
+int cdc_set_latent(cdc_ctx* ctx, const float* y_hat, cdc_stream s); /* runs the context net: cond = context_net(y_hat) */
+int cdc_set_x(cdc_ctx* ctx, const float* x_nchw, cdc_stream s);
+int cdc_get_x(cdc_ctx* ctx, float* x_nchw, int to_image01, cdc_stream s);
+int cdc_get_x0(cdc_ctx* ctx, float* x0_nchw, cdc_stream s); /* raw x0_hat of the last step (predict_x0) */
+
+/* ---- oracle/sampler.py OracleDecoder.denoise_step / decode ------------------------------------ */
+int cdc_denoise_step(cdc_ctx* ctx, int k, cdc_stream s); /* x <- c0_k*clamp(unet(x, idx_k, cond)) + c1_k*x */
+int cdc_decode(cdc_ctx* ctx, cdc_stream s);              /* all K steps: ONE cudaGraphLaunch */
+/* host-buffer convenience used for end-to-end timing: H2D(latent, x_T) -> context net -> decode ->
+ * D2H(image in [0,1]); synchronises the stream before returning. */
+int cdc_decode_host(cdc_ctx* ctx, const float* latent_host, const float* xT_host, float* image_host, cdc_stream s);
+int cdc_launches_per_step(cdc_ctx* ctx);
+int cdc_launches_context(cdc_ctx* ctx);
+double cdc_flops_per_step(cdc_ctx* ctx); /* algorithmic, SURVEY.md section 8d rule */
+
+/* ---- per-layer access for tests / profiling ---------------------------------------------------- */
+int cdc_num_step_ops(cdc_ctx* ctx);
+const char* cdc_step_op_name(cdc_ctx* ctx, int i);
+double cdc_step_op_flops(cdc_ctx* ctx, int i);
+double cdc_step_op_bytes(cdc_ctx* ctx, int i);
+int cdc_run_step_op(cdc_ctx* ctx, int i, int k, cdc_stream s);
+
+/* ---- oracle/entropy.py quantize_symbols / cdf_lookup (stateless) ------------------------------- */
+/* q = rint(y - mu) int32 (half-to-even), y_hat = q + mu.  mu_mod == 0: mu is elementwise;
+ * otherwise mu[(i / mu_inner) % mu_mod] (per-channel medians of the factorised prior). */
+int cdc_quantize(const float* y, const float* mu, int32_t* q, float* y_hat, int64_t n, int64_t mu_inner,
+                 int64_t mu_mod, cdc_stream s);
+/* sigma != NULL: idx from the 64-entry scale table; sigma == NULL: idx = (i / inner) % rows. */
+int cdc_cdf_lookup(const int32_t* q, const float* sigma, const int32_t* cdf, const int32_t* row_start,
+                   const int32_t* cdf_length, const int32_t* offset, const float* scale_table, int rows,
+                   int64_t inner, int32_t* idx, int32_t* v, int32_t* lo, int32_t* hi, int32_t* raw, int64_t n,
+                   cdc_stream s);
+
+/* ---- single-op entry points for kernel-level parity tests -------------------------------------- */
+/* conv: x NHWC bf16 sources (1 or 2), w OIHW fp32 (device), bias fp32; mode 0 = stride 1,
+ * 1 = stride 2, 2 = nearest-x2 input; out NHWC bf16; stats (optional) [B][PT][32][2]. */
+int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1, int B, int H, int W,
+                  const float* w_oihw, const float* bias, int cout, int ksize, int mode, int force_bn,
+                  const void* residual, void* out, float* stats, int* pt_out, cdc_stream s);
+int cdc_test_attention(const void* qkv, void* out, int B, int N, int heads, cdc_stream s);
+int cdc_test_gn(const void* x, const void* r, void* y, const float* gamma, const float* beta, const float* film,
+                int B, int HW, int C, int silu, float eps, cdc_stream s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CDC_B200_H */

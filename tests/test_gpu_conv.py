@@ -1,0 +1,134 @@
+"""K-conv (tcgen05 implicit GEMM) parity on a real B200, every call through the C ABI (include/cdc_b200.h).
+Checker: torch fp32 ops for the floating-point kernels, the CPU oracle for the integer path."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _lib():
+    from cdc_b200 import _ffi
+    return _ffi.lib()
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _nhwc_bf16(t):
+    return t.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def _run_conv(srcs, w, b, ksize, mode, force_bn=0, residual=None, stats=False):
+    """srcs: list of NCHW fp32 cuda tensors (bf16-exact).  Returns (out NCHW fp32, partials or None)."""
+    L = _lib()
+    B, _, H, W = srcs[0].shape
+    cout = w.shape[0]
+    n_pad = (cout + 63) // 64 * 64
+    OH, OW = (H // 2, W // 2) if mode == 1 else ((2 * H, 2 * W) if mode == 2 else (H, W))
+    s = [_nhwc_bf16(t) for t in srcs]
+    out = torch.full((B, OH, OW, n_pad), float("nan"), device=DEV, dtype=torch.bfloat16)
+    res = _nhwc_bf16(residual) if residual is not None else None
+    st = torch.zeros(B * (OH * OW // 64 + 64) * 64, device=DEV, dtype=torch.float32) if stats else None
+    pt = C.c_int(0)
+    rc = L.cdc_test_conv(0, _ptr(s[0]), s[0].shape[-1], _ptr(s[1]) if len(s) > 1 else C.c_void_p(0),
+                         s[1].shape[-1] if len(s) > 1 else 0, B, H, W, _ptr(w.contiguous()), _ptr(b.contiguous()),
+                         cout, ksize, mode, force_bn, _ptr(res), _ptr(out), _ptr(st), C.byref(pt), C.c_void_p(0))
+    assert rc == 0, L.cdc_last_error(None).decode()
+    torch.cuda.synchronize()
+    o = out[..., :cout].float().permute(0, 3, 1, 2).contiguous()
+    part = st[: B * pt.value * 64].reshape(B, pt.value, 32, 2) if stats else None
+    return o, part
+
+
+def _ref_conv(srcs, w, b, ksize, mode, residual=None):
+    x = torch.cat(srcs, dim=1)
+    if mode == 2:
+        x = F.interpolate(x, scale_factor=2, mode="nearest")
+    y = F.conv2d(x, w, b, stride=2 if mode == 1 else 1, padding=ksize // 2)
+    if residual is not None:
+        y = y + residual
+    return y
+
+
+def _mk(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (scale * torch.randn(*shape, generator=g)).bfloat16().float().to(DEV)
+
+
+def _check(o, ref, what):
+    err = (o - ref).abs()
+    tol = 8e-3 * ref.abs().clamp(min=1.0) + 2e-3
+    bad = (err > tol).float().mean().item()
+    assert torch.isfinite(o).all(), f"{what}: non-finite output"
+    assert bad == 0.0, f"{what}: {bad:.4%} elements off, max err {err.max().item():.4f}, ref max {ref.abs().max().item():.3f}"
+
+
+CONV_CASES = [
+    # name, B, H, W, cins, cout, ksize, mode, force_bn
+    ("3x3_c64_n64_row128", 1, 64, 128, [64], 64, 3, 0, 0),
+    ("3x3_c128_n128_2x64", 2, 32, 64, [128], 128, 3, 0, 0),
+    ("3x3_c192_n192", 1, 32, 32, [192], 192, 3, 0, 0),
+    ("3x3_c256_n256", 1, 16, 16, [256], 256, 3, 0, 256),
+    ("3x3_c256_n256_split64", 1, 16, 16, [256], 256, 3, 0, 64),
+    ("3x3_dual_64+128_n128", 1, 32, 64, [64, 128], 128, 3, 0, 0),
+    ("1x1_c256_n768", 1, 16, 16, [256], 768, 1, 0, 0),
+    ("1x1_c320_n192", 1, 32, 32, [128, 192], 192, 1, 0, 0),
+    ("s2_c64_n64", 1, 64, 128, [64], 64, 3, 1, 0),
+    ("s2_c192_n192", 2, 32, 32, [192], 192, 3, 1, 0),
+    ("up2_c128_n64", 1, 32, 64, [128], 64, 3, 2, 0),
+    ("up2_c256_n256", 1, 8, 8, [256], 256, 3, 2, 0),
+    ("ragged_48x24_c64_n64", 1, 24, 48, [64], 64, 3, 0, 0),
+    ("ragged_s2_24x40", 1, 24, 40, [64], 128, 3, 1, 0),
+    ("big_k4608_n256", 1, 16, 32, [256, 256], 256, 3, 0, 0),
+    ("multi_tile_persistent", 4, 64, 128, [64], 64, 3, 0, 0),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_matches_torch(case):
+    name, B, H, W, cins, cout, ks, mode, fbn = case
+    srcs = [_mk((B, c, H, W), 10 + i) for i, c in enumerate(cins)]
+    K = sum(cins) * ks * ks
+    w = _mk((cout, sum(cins), ks, ks), 20, scale=1.0 / np.sqrt(K))
+    b = _mk((cout,), 21, scale=0.5)
+    o, _ = _run_conv(srcs, w, b, ks, mode, fbn)
+    _check(o, _ref_conv(srcs, w, b, ks, mode), name)
+
+
+def test_conv_residual_epilogue():
+    srcs = [_mk((1, 256, 16, 16), 1)]
+    w = _mk((256, 256, 1, 1), 2, scale=1 / 16.0)
+    b = _mk((256,), 3)
+    r = _mk((1, 256, 16, 16), 4)
+    o, _ = _run_conv(srcs, w, b, 1, 0, 0, residual=r)
+    _check(o, _ref_conv(srcs, w, b, 1, 0, residual=r), "residual")
+
+
+@pytest.mark.parametrize("cfg", [(64, 1, 64, 128, 0), (128, 2, 32, 64, 0), (128, 1, 16, 16, 64), (192, 1, 32, 32, 0),
+                                 (256, 1, 16, 32, 256), (256, 1, 16, 16, 128), (256, 1, 16, 16, 64),
+                                 (64, 1, 24, 48, 0)])
+def test_conv_groupnorm_partials(cfg):
+    cout, B, H, W, fbn = cfg
+    srcs = [_mk((B, 64, H, W), 5)]
+    w = _mk((cout, 64, 3, 3), 6, scale=1 / 24.0)
+    b = _mk((cout,), 7)
+    o, part = _run_conv(srcs, w, b, 3, 0, fbn, stats=True)
+    ref = _ref_conv(srcs, w, b, 3, 0)
+    _check(o, ref, "stats-conv output")
+    got = part.double().sum(dim=1)  # [B, 32, 2]
+    rg = ref.double().reshape(B, 32, -1)
+    want = torch.stack([rg.sum(-1), (rg * rg).sum(-1)], dim=-1)
+    rel = (got - want).abs() / want.abs().clamp(min=1.0)
+    assert rel.max().item() < 2e-3, f"GN partials off: {rel.max().item()}"
+    # bitwise reproducible (fixed-order reduction)
+    o2, part2 = _run_conv(srcs, w, b, 3, 0, fbn, stats=True)
+    assert torch.equal(part, part2) and torch.equal(o, o2)
+
+

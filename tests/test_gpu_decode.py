@@ -1,0 +1,129 @@
+"""Step- and decode-level parity of the CUDA path against the CPU oracle on a real B200
+(teacher-forced per-step max-abs <= 1e-2; graph replay == eager launches)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-2  # BASELINE.json north_star: reconstructions within 1e-2 max-abs of the fp32 oracle per step
+
+_cache = {}
+
+
+def _setup(with_context=False):
+    key = ("ctx" if with_context else "unet")
+    if key in _cache:
+        return _cache[key]
+    from cdc_b200 import CDCConfig, Decoder
+    from oracle.config import CDCConfig as OCfg
+    from oracle.sampler import OracleDecoder
+    from oracle.weights import build_codec, build_unet
+    ocfg = OCfg()
+    net = build_unet(ocfg, seed=0)
+    weights = dict(net.state_dict())
+    codec = None
+    if with_context:
+        codec = build_codec(ocfg, seed=1)
+        weights.update({"context." + k: v for k, v in codec.context.state_dict().items()})
+    dec = Decoder(CDCConfig(), weights, device=DEV)
+    orc = OracleDecoder(ocfg, net, context_net=codec.context if codec else None)
+    _cache[key] = (dec, orc, ocfg)
+    return _cache[key]
+
+
+@pytest.mark.parametrize("shape", [(1, 256, 256), (2, 128, 192)])
+def test_teacher_forced_step_parity(shape):
+    from oracle.weights import synthetic_cond, synthetic_init
+    dec, orc, ocfg = _setup()
+    B, H, W = shape
+    dec.set_sample_schedule(17)
+    orc.set_sample_schedule(17)
+    assert dec.idx == orc.sched.idx
+    for k in range(17):
+        c0, c1 = dec.coeffs(k)
+        assert c0 == float(orc.sched.c0[k]) and c1 == float(orc.sched.c1[k])
+    cond = synthetic_cond(ocfg, B, H, W)
+    x = synthetic_init(B, H, W)
+    worst = 0.0
+    for t in (999, 500, 0):
+        x0_ref = orc.predict_x0(x, t, cond)
+        xp_ref = orc.denoise_step(x, t, cond)
+        xp = dec.denoise_step(x, t, cond).cpu()
+        x0 = dec._get_x0().cpu()
+        e0 = (x0 - x0_ref).abs().max().item()
+        e1 = (xp - xp_ref).abs().max().item()
+        print(f"shape {shape} t={t}: max|x0-x0_ref|={e0:.5f} max|xprev-ref|={e1:.5f}")
+        worst = max(worst, e1)
+        assert torch.isfinite(xp).all()
+        assert e1 <= TOL, f"t={t}: x_prev max-abs {e1}"
+        assert e0 <= 3 * TOL, f"t={t}: x0_hat max-abs {e0}"
+    try:
+        dec.denoise_step(x, 998, cond)
+        assert False, "t outside the schedule must raise"
+    except ValueError:
+        pass
+
+
+def test_full_trajectory_teacher_forced_and_graph_equals_eager():
+    from oracle.weights import synthetic_cond, synthetic_init
+    dec, orc, ocfg = _setup()
+    B, H, W, K = 1, 128, 128, 5
+    cond = synthetic_cond(ocfg, B, H, W, index=3)
+    x = synthetic_init(B, H, W, index=3)
+    traj = []
+    img_ref = orc.decode(torch.zeros(B, 256, H // 16, W // 16), K, init=x, cond=cond, trajectory=traj)
+    dec.set_sample_schedule(K)
+    for k in range(K):  # teacher forcing: feed the oracle's x_t
+        xp = dec.denoise_step(traj[k], orc.sched.idx[k], cond).cpu()
+        ref = traj[k + 1] if k + 1 < K else (img_ref * 2 - 1)
+        if k + 1 == K:
+            xp = xp.clamp(-1, 1)
+        e = (xp - ref).abs().max().item()
+        print(f"k={k}: {e:.5f}")
+        assert e <= TOL
+    # eager free-running vs one graph launch: bitwise identical
+    xe = x.clone()
+    for k in range(K):
+        xe = dec.denoise_step(xe, orc.sched.idx[k])
+    img_e = ((xe.clamp(-1, 1) + 1) / 2).cpu()
+    img_g = dec.decode(torch.zeros(B, 256, H // 16, W // 16), K, init=x.to(DEV), cond=cond).cpu()
+    assert torch.equal(img_e, img_g)
+    img_g2 = dec.decode(torch.zeros(B, 256, H // 16, W // 16), K, init=x.to(DEV), cond=cond).cpu()
+    assert torch.equal(img_g, img_g2)
+    fr = (img_g - img_ref).abs().max().item()
+    print(f"free-running decode max-abs vs oracle: {fr:.5f}")
+    assert fr < 0.1
+
+
+def test_context_net_and_host_decode():
+    from oracle.weights import synthetic_init, synthetic_latent
+    dec, orc, ocfg = _setup(with_context=True)
+    B, H, W, K = 1, 128, 192, 3
+    lat = synthetic_latent(B, H, W)
+    x = synthetic_init(B, H, W)
+    with torch.no_grad():
+        cond_ref = orc.context_net(lat)
+    img_ref = orc.decode(lat, K, init=x, cond=cond_ref)
+    img = dec.decode(lat, K, init=x)  # host tensors -> cdc_decode_host
+    assert img.device.type == "cpu" and img.shape == (B, 3, H, W)
+    e = (img - img_ref).abs().max().item()
+    print(f"host decode (context net on GPU) max-abs vs oracle: {e:.5f}")
+    assert e < 0.1
+    img2 = dec.decode(lat.to(DEV), K, init=x.to(DEV)).cpu()
+    assert torch.equal(img, img2)
+
+
+def test_flops_and_launch_accounting():
+    from oracle.unet import unet_flops
+    dec, orc, ocfg = _setup()
+    dec.set_sample_schedule(17)
+    dec.bind(1, 256, 256)
+    assert abs(dec.flops_per_step() / unet_flops(ocfg, 1, 256, 256) - 1.0) < 1e-6
+    assert dec.launches_per_step() == len(dec.step_ops()) > 100
+
+
+def test_wrong_shapes_fail_loudly():
+    dec, _, _ = _setup()
+    with pytest.raises(RuntimeError):
+        dec.bind(1, 100, 256)
