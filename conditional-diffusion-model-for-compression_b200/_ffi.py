@@ -8,7 +8,7 @@ LIB_PATH = os.path.join(_HERE, "libcdc_b200.so")
 
 # every symbol include/cdc_b200.h declares
 SYMBOLS = [
-    "cdc_create", "cdc_destroy", "cdc_last_error", "cdc_abi_version", "cdc_load_weights", "cdc_finalize_weights",
+    "cdc_create", "cdc_destroy", "cdc_last_error", "cdc_abi_version", "cdc_act_dtype", "cdc_load_weights", "cdc_finalize_weights",
     "cdc_has_context_net", "cdc_set_schedule", "cdc_schedule_index", "cdc_schedule_coeffs", "cdc_bind_io",
     "cdc_set_cond", "cdc_set_latent", "cdc_set_x", "cdc_get_x", "cdc_get_x0", "cdc_denoise_step", "cdc_decode",
     "cdc_decode_host", "cdc_launches_per_step", "cdc_launches_context", "cdc_flops_per_step", "cdc_num_step_ops",

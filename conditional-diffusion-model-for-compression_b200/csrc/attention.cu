@@ -18,9 +18,9 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        "mma.sync.aligned.m16n8k16.row.col.f32." CDC_MMA_SYNC_T "." CDC_MMA_SYNC_T ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -28,21 +28,21 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, ui
     asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
 }
 
-__global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                        __nv_bfloat16* __restrict__ out, int N, int heads) {
-    __shared__ __align__(16) __nv_bfloat16 Qs[kAttBQ][kAttPitch];
-    __shared__ __align__(16) __nv_bfloat16 Ks[2][kAttBK][kAttPitch];
-    __shared__ __align__(16) __nv_bfloat16 Vs[2][kAttBK][kAttPitch];
+__global__ void __launch_bounds__(128) attention_kernel(const act_t* __restrict__ qkv,
+                                                        act_t* __restrict__ out, int N, int heads) {
+    __shared__ __align__(16) act_t Qs[kAttBQ][kAttPitch];
+    __shared__ __align__(16) act_t Ks[2][kAttBK][kAttPitch];
+    __shared__ __align__(16) act_t Vs[2][kAttBK][kAttPitch];
     const int C = heads * kAttD, ld = 3 * C;
     const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kAttBQ;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * N * ld + h * kAttD;
+    const act_t* base = qkv + static_cast<size_t>(b) * N * ld + h * kAttD;
 
-    auto load_tile = [&](__nv_bfloat16 (*dst)[kAttPitch], const __nv_bfloat16* src, int row0) {
+    auto load_tile = [&](act_t (*dst)[kAttPitch], const act_t* src, int row0) {
         for (int i = tid; i < 64 * 8; i += 128) {
             const int r = i >> 3, c = i & 7;
             const bool ok = row0 + r < N;
-            const __nv_bfloat16* sp = src + static_cast<size_t>(ok ? row0 + r : 0) * ld + c * 8;
+            const act_t* sp = src + static_cast<size_t>(ok ? row0 + r : 0) * ld + c * 8;
             cp_async16(smem_u32(&dst[r][c * 8]), sp, ok);
         }
     };
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __r
             for (int kk = 0; kk < 4; ++kk) {
                 const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Ks[buf][n * 8 + g][kk * 16 + 2 * t]);
                 const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Ks[buf][n * 8 + g][kk * 16 + 8 + 2 * t]);
-                mma_bf16_16816(s[n], qf[kk], b0, b1);
+                mma_16816(s[n], qf[kk], b0, b1);
             }
         }
         // scale to log2 domain, mask the key tail
@@ -121,8 +121,8 @@ __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __r
             const float p2 = exp2f(s[n][2] - mn1), p3 = exp2f(s[n][3] - mn1);
             rs0 += p0 + p1;
             rs1 += p2 + p3;
-            pf[n >> 1][(n & 1) * 2 + 0] = pack_bf16x2(p0, p1);
-            pf[n >> 1][(n & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+            pf[n >> 1][(n & 1) * 2 + 0] = pack_act2(p0, p1);
+            pf[n >> 1][(n & 1) * 2 + 1] = pack_act2(p2, p3);
         }
         rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1);
         rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __r
                 uint32_t b0, b1;
                 const int r = kk * 16 + (lane & 15);
                 ldmatrix_x2_trans(b0, b1, smem_u32(&Vs[buf][r][n * 8]));
-                mma_bf16_16816(o[n], pf[kk], b0, b1);
+                mma_16816(o[n], pf[kk], b0, b1);
             }
         }
         __syncthreads();
@@ -157,14 +157,14 @@ __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __r
         const int d = n * 8 + 2 * t;
         if (r0 < N)
             *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * N + r0) * C + h * kAttD + d) =
-                pack_bf16x2(o[n][0] * inv0, o[n][1] * inv0);
+                pack_act2(o[n][0] * inv0, o[n][1] * inv0);
         if (r1 < N)
             *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * N + r1) * C + h * kAttD + d) =
-                pack_bf16x2(o[n][2] * inv1, o[n][3] * inv1);
+                pack_act2(o[n][2] * inv1, o[n][3] * inv1);
     }
 }
 
-cudaError_t launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* o, int B, int N, int heads, cudaStream_t s) {
+cudaError_t launch_attention(const act_t* qkv, act_t* o, int B, int N, int heads, cudaStream_t s) {
     dim3 grid((N + kAttBQ - 1) / kAttBQ, heads, B);
     attention_kernel<<<grid, 128, 0, s>>>(qkv, o, N, heads);
     return cudaGetLastError();

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
     } else if (warp == 1) {
         if (lane == 0) {
             // ------------------------------------------------------------ MMA issuer
-            constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+            constexpr uint32_t idesc = make_idesc_f16(128, BN);
             uint32_t stage = 0, phase = 0, it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const uint32_t as = it & 1, aphase = (it >> 1) & 1;
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
                     const uint64_t bdesc = make_sw128_desc(sa + Cfg::A_BYTES);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)  // 4 x (K = 16): +32 B inside the 128 B swizzle row
-                        umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0);
+                        umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0);
                     umma_commit(bar_empty + 8 * stage);  // frees the smem slot once these MMAs retire
                     if (++stage == NS) {
                         stage = 0;
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
                         const float xt = p.x[pix * 3 + c];
                         const float xn = p.c0 * fminf(fmaxf(x0, -1.0f), 1.0f) + p.c1 * xt;
                         p.x[pix * 3 + c] = xn;
-                        p.xpad[pix * 64 + c] = __float2bfloat16_rn(xn);
+                        p.xpad[pix * 64 + c] = to_act(xn);
                         if (p.x0_out) p.x0_out[pix * 3 + c] = x0;
                     }
                 }
@@ -214,8 +214,8 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
                 float gs[G], gq[G];
 #pragma unroll
                 for (int g = 0; g < G; ++g) gs[g] = gq[g] = 0.0f;
-                __nv_bfloat16* orow = p.out + pix * p.ldc + nt * BN;
-                const __nv_bfloat16* rrow = p.residual ? p.residual + pix * p.ldc + nt * BN : nullptr;
+                act_t* orow = p.out + pix * p.ldc + nt * BN;
+                const act_t* rrow = p.residual ? p.residual + pix * p.ldc + nt * BN : nullptr;
                 const float* bs = bias_s + nt * BN;
 #pragma unroll
                 for (int ch = 0; ch < BN / 32; ++ch) {
@@ -245,20 +245,20 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
                         for (int s4 = 0; s4 < 4; ++s4) {
                             if (rrow) {
                                 const uint4 r = *reinterpret_cast<const uint4*>(rrow + ch * 32 + s4 * 8);
-                                f[s4 * 8 + 0] += bf16_lo(r.x);
-                                f[s4 * 8 + 1] += bf16_hi(r.x);
-                                f[s4 * 8 + 2] += bf16_lo(r.y);
-                                f[s4 * 8 + 3] += bf16_hi(r.y);
-                                f[s4 * 8 + 4] += bf16_lo(r.z);
-                                f[s4 * 8 + 5] += bf16_hi(r.z);
-                                f[s4 * 8 + 6] += bf16_lo(r.w);
-                                f[s4 * 8 + 7] += bf16_hi(r.w);
+                                f[s4 * 8 + 0] += act_lo(r.x);
+                                f[s4 * 8 + 1] += act_hi(r.x);
+                                f[s4 * 8 + 2] += act_lo(r.y);
+                                f[s4 * 8 + 3] += act_hi(r.y);
+                                f[s4 * 8 + 4] += act_lo(r.z);
+                                f[s4 * 8 + 5] += act_hi(r.z);
+                                f[s4 * 8 + 6] += act_lo(r.w);
+                                f[s4 * 8 + 7] += act_hi(r.w);
                             }
                             uint4 o;
-                            o.x = pack_bf16x2(f[s4 * 8 + 0], f[s4 * 8 + 1]);
-                            o.y = pack_bf16x2(f[s4 * 8 + 2], f[s4 * 8 + 3]);
-                            o.z = pack_bf16x2(f[s4 * 8 + 4], f[s4 * 8 + 5]);
-                            o.w = pack_bf16x2(f[s4 * 8 + 6], f[s4 * 8 + 7]);
+                            o.x = pack_act2(f[s4 * 8 + 0], f[s4 * 8 + 1]);
+                            o.y = pack_act2(f[s4 * 8 + 2], f[s4 * 8 + 3]);
+                            o.z = pack_act2(f[s4 * 8 + 4], f[s4 * 8 + 5]);
+                            o.w = pack_act2(f[s4 * 8 + 6], f[s4 * 8 + 7]);
                             dst[s4] = o;
                         }
                     }

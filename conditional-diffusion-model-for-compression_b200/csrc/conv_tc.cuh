@@ -5,7 +5,7 @@
 // matching 64-wide slice of the [C_out][K] weight matrix.
 #pragma once
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include "act.cuh"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -24,9 +24,9 @@ struct KBlock {
 };
 
 enum ConvEpilogue : int {
-    EPI_STORE = 0,  // +bias (+bf16 residual) -> bf16 NHWC
+    EPI_STORE = 0,  // +bias (+bf16 residual) -> act_t NHWC
     EPI_STATS = 1,  // EPI_STORE and per-(tile, group) sum / sum-of-squares partials for GroupNorm
-    EPI_DDIM = 2,   // final conv: x0 = acc+bias; x_prev = c0*clamp(x0) + c1*x_t (fp32), bf16 copy for the stem
+    EPI_DDIM = 2,   // final conv: x0 = acc+bias; x_prev = c0*clamp(x0) + c1*x_t (fp32), act_t copy for the stem
 };
 
 struct alignas(64) ConvParams {
@@ -43,13 +43,13 @@ struct alignas(64) ConvParams {
     int ldc;        // channels of the output tensor (row pitch in elements)
     int n_total;    // true C_out rounded up to the N tile
     int n_tiles;    // n_total / BN
-    __nv_bfloat16* out;
+    act_t* out;
     const float* bias;                 // [n_total]
-    const __nv_bfloat16* residual;     // optional, same layout as out
+    const act_t* residual;     // optional, same layout as out
     float* stats;                      // EPI_STATS: [batch][PT][32][2]
     // EPI_DDIM
     float* x;                          // [B*H*W][3] fp32, updated in place
-    __nv_bfloat16* xpad;               // [B*H*W][64] bf16, channels 0..2 rewritten
+    act_t* xpad;               // [B*H*W][64] bf16, channels 0..2 rewritten
     float* x0_out;                     // optional [B*H*W][3] raw x0_hat
     float c0, c1;
 };

@@ -13,12 +13,12 @@ constexpr int kStatsPix = 64;
 
 int gn_stats_num_partials(int HW) { return (HW + kStatsPix - 1) / kStatsPix; }
 
-__global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partials,
+__global__ void __launch_bounds__(256) gn_stats_kernel(const act_t* __restrict__ x, float* __restrict__ partials,
                                                        int HW, int C, int PT) {
     __shared__ float s_sum[8][512], s_sq[8][512];  // [row-in-pass][channel] (C <= 512)
     const int b = blockIdx.y, pt = blockIdx.x;
     const int vecs = C / 8;                 // uint4 per pixel
-    const int rows = 256 / vecs;            // pixels per pass
+    const int rows = (256 / vecs) < 8 ? (256 / vecs) : 8;  // pixels per pass (smem rows)
     const int t = threadIdx.x, cv = t % vecs, pr = t / vecs;
     float s[8], q[8];
 #pragma unroll
@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __re
             const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float a = bf16_lo(w[j]), c = bf16_hi(w[j]);
+                const float a = act_lo(w[j]), c = act_hi(w[j]);
                 s[2 * j] += a;
                 q[2 * j] += a * a;
                 s[2 * j + 1] += c;
@@ -69,9 +69,9 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __re
     }
 }
 
-cudaError_t launch_gn_stats(const __nv_bfloat16* x, float* partials, int B, int HW, int C, int* PT_out,
+cudaError_t launch_gn_stats(const act_t* x, float* partials, int B, int HW, int C, int* PT_out,
                             cudaStream_t s) {
-    if (C % 32 != 0 || C > 512 || (256 % (C / 8)) != 0 || 256 / (C / 8) > 8) return cudaErrorInvalidValue;
+    if (C % 32 != 0 || C > 512 || C < 32) return cudaErrorInvalidValue;
     const int PT = gn_stats_num_partials(HW);
     if (PT_out) *PT_out = PT;
     gn_stats_kernel<<<dim3(PT, B), 256, 0, s>>>(x, partials, HW, C, PT);
@@ -149,23 +149,23 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* __restrict__
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float4 c = abp[j];  // (a0, b0, a1, b1)
-            float v0 = c.x * bf16_lo(w[j]) + c.y;
-            float v1 = c.z * bf16_hi(w[j]) + c.w;
+            float v0 = c.x * act_lo(w[j]) + c.y;
+            float v1 = c.z * act_hi(w[j]) + c.w;
             if (SILU) {
                 v0 = silu_f(v0);
                 v1 = silu_f(v1);
             }
             if (RES) {
-                v0 += bf16_lo(rw[j]);
-                v1 += bf16_hi(rw[j]);
+                v0 += act_lo(rw[j]);
+                v1 += act_hi(rw[j]);
             }
-            o[j] = pack_bf16x2(v0, v1);
+            o[j] = pack_act2(v0, v1);
         }
         y[i] = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
 
-cudaError_t launch_gn_apply(const __nv_bfloat16* x, const float2* ab, const __nv_bfloat16* r, __nv_bfloat16* y, int B,
+cudaError_t launch_gn_apply(const act_t* x, const float2* ab, const act_t* r, act_t* y, int B,
                             int HW, int C, int silu, int num_sms, cudaStream_t s) {
     const long long nvec = static_cast<long long>(B) * HW * C / 8;
     const int vpp = C / 8;
@@ -229,8 +229,8 @@ cudaError_t launch_temb_film(const FilmParams& p, int K, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Layout conversion (API boundary: NCHW fp32 tensors <-> device NHWC bf16 / fp32).
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C, int HW,
+// Layout conversion (API boundary: NCHW fp32 tensors <-> device NHWC act_t / fp32).
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, act_t* __restrict__ dst, int C, int HW,
                                     int ldc) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
@@ -241,22 +241,22 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16
     __syncthreads();
     for (int j = threadIdx.y; j < 32; j += 8) {
         const int p = p0 + j, c = c0 + threadIdx.x;
-        if (p < HW && c < C) dst[(static_cast<size_t>(b) * HW + p) * ldc + c] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+        if (p < HW && c < C) dst[(static_cast<size_t>(b) * HW + p) * ldc + c] = to_act(tile[threadIdx.x][j]);
     }
 }
-cudaError_t launch_nchw_f32_to_nhwc_bf16(const float* src, __nv_bfloat16* dst, int B, int C, int HW, int ldc,
+cudaError_t launch_nchw_f32_to_nhwc_act(const float* src, act_t* dst, int B, int C, int HW, int ldc,
                                          cudaStream_t s) {
     dim3 grid((HW + 31) / 32, (C + 31) / 32, B);
     nchw_to_nhwc_kernel<<<grid, dim3(32, 8), 0, s>>>(src, dst, C, HW, ldc);
     return cudaGetLastError();
 }
 
-__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+__global__ void nhwc_to_nchw_kernel(const act_t* __restrict__ src, float* __restrict__ dst, int C, int HW) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
     for (int j = threadIdx.y; j < 32; j += 8) {
         const int p = p0 + j, c = c0 + threadIdx.x;
-        tile[j][threadIdx.x] = (c < C && p < HW) ? __bfloat162float(src[(static_cast<size_t>(b) * HW + p) * C + c]) : 0.f;
+        tile[j][threadIdx.x] = (c < C && p < HW) ? from_act(src[(static_cast<size_t>(b) * HW + p) * C + c]) : 0.f;
     }
     __syncthreads();
     for (int j = threadIdx.y; j < 32; j += 8) {
@@ -264,13 +264,13 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float
         if (p < HW && c < C) dst[(static_cast<size_t>(b) * C + c) * HW + p] = tile[threadIdx.x][j];
     }
 }
-cudaError_t launch_nhwc_bf16_to_nchw_f32(const __nv_bfloat16* src, float* dst, int B, int C, int HW, cudaStream_t s) {
+cudaError_t launch_nhwc_act_to_nchw_f32(const act_t* src, float* dst, int B, int C, int HW, cudaStream_t s) {
     dim3 grid((HW + 31) / 32, (C + 31) / 32, B);
     nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, s>>>(src, dst, C, HW);
     return cudaGetLastError();
 }
 
-__global__ void x_in_kernel(const float* __restrict__ x, float* __restrict__ xs, __nv_bfloat16* __restrict__ xpad,
+__global__ void x_in_kernel(const float* __restrict__ x, float* __restrict__ xs, act_t* __restrict__ xpad,
                             long long n, int HW) {
     for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
         const long long b = i / HW, p = i % HW;
@@ -278,11 +278,11 @@ __global__ void x_in_kernel(const float* __restrict__ x, float* __restrict__ xs,
         for (int c = 0; c < 3; ++c) {
             const float v = x[(b * 3 + c) * HW + p];
             xs[i * 3 + c] = v;
-            xpad[i * 64 + c] = __float2bfloat16_rn(v);
+            xpad[i * 64 + c] = to_act(v);
         }
     }
 }
-cudaError_t launch_x_in(const float* x_nchw, float* xs, __nv_bfloat16* xpad, int B, int HW, cudaStream_t s) {
+cudaError_t launch_x_in(const float* x_nchw, float* xs, act_t* xpad, int B, int HW, cudaStream_t s) {
     const long long n = static_cast<long long>(B) * HW;
     x_in_kernel<<<static_cast<int>((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096), 256, 0, s>>>(x_nchw, xs, xpad, n, HW);
     return cudaGetLastError();
@@ -308,7 +308,7 @@ cudaError_t launch_x_out(const float* xs, float* x_nchw, int B, int HW, int to_i
 
 // OIHW fp32 -> [O_pad][taps][I_pad] bf16; input channel i < split keeps slot i, i >= split moves to
 // split_pad + (i - split); everything else is zero.
-__global__ void repack_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int O, int I,
+__global__ void repack_weight_kernel(const float* __restrict__ src, act_t* __restrict__ dst, int O, int I,
                                      int taps, int O_pad, int I_pad, int split, int split_pad) {
     const long long n = static_cast<long long>(O_pad) * taps * I_pad;
     for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < n; idx += gridDim.x * 256LL) {
@@ -320,10 +320,10 @@ __global__ void repack_weight_kernel(const float* __restrict__ src, __nv_bfloat1
         else if (slot >= split_pad && slot - split_pad + split < I) i = slot - split_pad + split;
         float v = 0.f;
         if (o < O && i >= 0 && i < I) v = src[(static_cast<size_t>(o) * I + i) * taps + tap];
-        dst[idx] = __float2bfloat16_rn(v);
+        dst[idx] = to_act(v);
     }
 }
-cudaError_t launch_repack_weight(const float* src, __nv_bfloat16* dst, int O, int I, int taps, int O_pad, int I_pad,
+cudaError_t launch_repack_weight(const float* src, act_t* dst, int O, int I, int taps, int O_pad, int I_pad,
                                  int split, int split_pad, cudaStream_t s) {
     const long long n = static_cast<long long>(O_pad) * taps * I_pad;
     repack_weight_kernel<<<static_cast<int>((n + 255) / 256 < 2048 ? (n + 255) / 256 : 2048), 256, 0, s>>>(

@@ -1,6 +1,6 @@
 // Launchers of the non-GEMM kernels of the decode hot path (all HBM- or latency-bound).
 #pragma once
-#include <cuda_bf16.h>
+#include "act.cuh"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -9,14 +9,14 @@ namespace cdc {
 // ---- GroupNorm (oracle/unet.py RB / Attn) -------------------------------
 // partials: [B][PT][32][2] (sum, sum of squares) per tile and group.
 // ab:       [B][C] float2 = (a, b) with y = a*x + b  (GN affine and FiLM folded).
-cudaError_t launch_gn_stats(const __nv_bfloat16* x, float* partials, int B, int HW, int C, int* PT_out,
+cudaError_t launch_gn_stats(const act_t* x, float* partials, int B, int HW, int C, int* PT_out,
                             cudaStream_t s);
 int gn_stats_num_partials(int HW);
 cudaError_t launch_gn_finalize(const float* partials, int PT, const float* gamma, const float* beta,
                                const float* film /* [2C] scale|shift or null */, float2* ab, int B, int C, int HW,
                                float eps, cudaStream_t s);
 // y = act(a*x+b) (+ r); act = SiLU if silu != 0.  In place allowed (y == x).
-cudaError_t launch_gn_apply(const __nv_bfloat16* x, const float2* ab, const __nv_bfloat16* r, __nv_bfloat16* y,
+cudaError_t launch_gn_apply(const act_t* x, const float2* ab, const act_t* r, act_t* y,
                             int B, int HW, int C, int silu, int num_sms, cudaStream_t s);
 
 // ---- time embedding + FiLM (C8; oracle/unet.py TimeEmbed, RB.film) ----------------------------
@@ -37,20 +37,20 @@ struct FilmParams {
 cudaError_t launch_temb_film(const FilmParams& p, int K, cudaStream_t s);
 
 // ---- layout conversion at the API boundary -----------------------------------------------------
-cudaError_t launch_nchw_f32_to_nhwc_bf16(const float* src, __nv_bfloat16* dst, int B, int C, int HW, int ldc,
+cudaError_t launch_nchw_f32_to_nhwc_act(const float* src, act_t* dst, int B, int C, int HW, int ldc,
                                          cudaStream_t s);
-cudaError_t launch_nhwc_bf16_to_nchw_f32(const __nv_bfloat16* src, float* dst, int B, int C, int HW, cudaStream_t s);
-// x NCHW fp32 [B,3,H,W] -> xs NHWC fp32 [B*HW][3] and xpad bf16 [B*HW][64] (channels 0..2; rest untouched)
-cudaError_t launch_x_in(const float* x_nchw, float* xs, __nv_bfloat16* xpad, int B, int HW, cudaStream_t s);
+cudaError_t launch_nhwc_act_to_nchw_f32(const act_t* src, float* dst, int B, int C, int HW, cudaStream_t s);
+// x NCHW fp32 [B,3,H,W] -> xs NHWC fp32 [B*HW][3] and xpad act_t [B*HW][64] (channels 0..2; rest untouched)
+cudaError_t launch_x_in(const float* x_nchw, float* xs, act_t* xpad, int B, int HW, cudaStream_t s);
 // xs NHWC fp32 -> NCHW fp32, optionally mapped to [0,1]: (clamp(x,-1,1)+1)/2
 cudaError_t launch_x_out(const float* xs, float* x_nchw, int B, int HW, int to_image, cudaStream_t s);
-// conv weight repack: OIHW fp32 -> [O_pad][taps][I_pad] bf16 with input channels >= split moved to split_pad
-cudaError_t launch_repack_weight(const float* src, __nv_bfloat16* dst, int O, int I, int taps, int O_pad, int I_pad,
+// conv weight repack: OIHW fp32 -> [O_pad][taps][I_pad] act_t with input channels >= split moved to split_pad
+cudaError_t launch_repack_weight(const float* src, act_t* dst, int O, int I, int taps, int O_pad, int I_pad,
                                  int split, int split_pad, cudaStream_t s);
 
 // ---- attention (C7; oracle/unet.py Attn) --------------------------------------------------------
-// qkv [B*N][768] bf16 (q | k | v, head h = channels 64h..64h+63) -> o [B*N][256] bf16
-cudaError_t launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* o, int B, int N, int heads, cudaStream_t s);
+// qkv [B*N][768] act_t (q | k | v, head h = channels 64h..64h+63) -> o [B*N][256] bf16
+cudaError_t launch_attention(const act_t* qkv, act_t* o, int B, int N, int heads, cudaStream_t s);
 
 // ---- integer path (C10; oracle/entropy.py) ------------------------------------------------------
 cudaError_t launch_quantize(const float* y, const float* mu, int32_t* q, float* yhat, int64_t n, int64_t mu_inner,

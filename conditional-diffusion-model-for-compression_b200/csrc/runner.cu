@@ -41,13 +41,13 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-struct Act {  // NHWC bf16 activation, batch implied by the plan
-    __nv_bfloat16* p = nullptr;
+struct Act {  // NHWC act_t activation, batch implied by the plan
+    act_t* p = nullptr;
     int C = 0, H = 0, W = 0;
 };
 
-struct ConvW {  // repacked conv weights: bf16 [n_pad][taps][c_pad], fp32 bias [n_pad]
-    __nv_bfloat16* w = nullptr;
+struct ConvW {  // repacked conv weights: act_t [n_pad][taps][c_pad], fp32 bias [n_pad]
+    act_t* w = nullptr;
     float* bias = nullptr;
     int n_true = 0, n_pad = 0, taps = 0, c_pad = 0, c_true = 0;
 };
@@ -94,17 +94,17 @@ struct ConvBuild {
     int epi = EPI_STORE;
     int cpg = 1;
     float* stats = nullptr;
-    const __nv_bfloat16* residual = nullptr;
+    const act_t* residual = nullptr;
     int force_bn = 0;
     // DDIM
     float* x = nullptr;
-    __nv_bfloat16* xpad = nullptr;
+    act_t* xpad = nullptr;
     float* x0_out = nullptr;
     const std::vector<float>* c0 = nullptr;  // per-step sampler coefficients (host)
     const std::vector<float>* c1 = nullptr;
 };
 
-static int encode_act_map(CUtensorMap* m, const __nv_bfloat16* base, int C, int Wd, int Hd, int B, size_t sW, size_t sH,
+static int encode_act_map(CUtensorMap* m, const act_t* base, int C, int Wd, int Hd, int B, size_t sW, size_t sH,
                           size_t sB, int BW, int BH) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return -1;
@@ -113,20 +113,20 @@ static int encode_act_map(CUtensorMap* m, const __nv_bfloat16* base, int C, int 
     cuuint64_t strides[3] = {sW * 2, sH * 2, sB * 2};
     cuuint32_t box[4] = {64, static_cast<cuuint32_t>(BW), static_cast<cuuint32_t>(BH), 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(base), dims, strides, box, es,
+    CUresult r = enc(m, CDC_TMA_DTYPE, 4, const_cast<act_t*>(base), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
 }
 
-static int encode_w_map(CUtensorMap* m, const __nv_bfloat16* w, int K, int N, int BN) {
+static int encode_w_map(CUtensorMap* m, const act_t* w, int K, int N, int BN) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return -1;
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(N)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(K) * 2};
     cuuint32_t box[2] = {64, static_cast<cuuint32_t>(BN)};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(w), dims, strides, box, es,
+    CUresult r = enc(m, CDC_TMA_DTYPE, 2, const_cast<act_t*>(w), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
@@ -218,7 +218,7 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
         if (cb.mode == MODE_S2) {
             for (int py = 0; py < 2; ++py)
                 for (int px = 0; px < 2; ++px) {
-                    const __nv_bfloat16* base = a.p + (static_cast<size_t>(py) * a.W + px) * a.C;
+                    const act_t* base = a.p + (static_cast<size_t>(py) * a.W + px) * a.C;
                     if (encode_act_map(&cp->amap[nmaps++], base, a.C, a.W / 2, a.H / 2, B, 2 * static_cast<size_t>(a.C),
                                        2 * static_cast<size_t>(a.W) * a.C, static_cast<size_t>(a.H) * a.W * a.C, BW, BH))
                         return fail("cuTensorMapEncodeTiled (stride-2 view) failed");
@@ -500,7 +500,7 @@ struct PlanB {
         ops->push_back(op);
     }
     // GN finalize (+FiLM of step k) and apply
-    void gn(const std::string& name, const std::string& gnp, int film_idx, int PT, Act x, const __nv_bfloat16* res, Act y,
+    void gn(const std::string& name, const std::string& gnp, int film_idx, int PT, Act x, const act_t* res, Act y,
             bool silu) {
         if (rc) return;
         cdc_ctx* c = ctx;
@@ -519,8 +519,8 @@ struct PlanB {
         Op a;
         a.name = name + (silu ? ".apply_silu" : ".apply") + (res ? "_res" : "");
         a.bytes = static_cast<double>(B) * HW * Cc * 2 * (res ? 3 : 2);
-        const __nv_bfloat16 *xp = x.p, *rp = res;
-        __nv_bfloat16* yp = y.p;
+        const act_t *xp = x.p, *rp = res;
+        act_t* yp = y.p;
         const int si = silu ? 1 : 0;
         a.run = [c, xp, rp, yp, B, HW, Cc, si](cudaStream_t s, int) {
             return launch_gn_apply(xp, c->ab, rp, yp, B, HW, Cc, si, c->num_sms, s);
@@ -553,7 +553,7 @@ struct PlanB {
         c2.cpg = cpg;
         c2.stats = ctx->partials;
         conv(c2);
-        const __nv_bfloat16* resp = in[0].p;
+        const act_t* resp = in[0].p;
         if (cin != cout) {
             Act r = shared("res", cout, H, W);
             ConvBuild cr;
@@ -638,7 +638,7 @@ static int build_plans(cdc_ctx* ctx) {
         Op st;
         st.name = "mid.attn.gn.stats";
         st.bytes = static_cast<double>(B) * HW * Cm * 2;
-        const __nv_bfloat16* m1p = m1.p;
+        const act_t* m1p = m1.p;
         st.run = [c, m1p, B, HW, Cm](cudaStream_t s, int) { return launch_gn_stats(m1p, c->partials, B, HW, Cm, nullptr, s); };
         ctx->step_ops.push_back(st);
         pb.gn("mid.attn.gn", "mid.attn.gn", -1, gn_stats_num_partials(HW), m1, nullptr, n, false);
@@ -653,8 +653,8 @@ static int build_plans(cdc_ctx* ctx) {
         at.name = "mid.attn.sdpa";
         at.flops = static_cast<double>(B) * ctx->cfg.heads * 4.0 * HW * HW * ctx->cfg.head_dim;
         at.bytes = static_cast<double>(B) * HW * Cm * 2 * 4;
-        const __nv_bfloat16* qp = qkv.p;
-        __nv_bfloat16* op_ = o.p;
+        const act_t* qp = qkv.p;
+        act_t* op_ = o.p;
         const int heads = ctx->cfg.heads;
         at.run = [qp, op_, B, HW, heads](cudaStream_t s, int) { return launch_attention(qp, op_, B, HW, heads, s); };
         ctx->step_ops.push_back(at);
@@ -763,6 +763,8 @@ static int capture_graph(cdc_ctx* ctx) {
 extern "C" {
 
 int cdc_abi_version(void) { return 1; }
+
+int cdc_act_dtype(void) { return CDC_ACT_FP16 ? 1 : 0; }
 
 const char* cdc_last_error(cdc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
@@ -1014,7 +1016,7 @@ int cdc_set_cond(cdc_ctx* ctx, const float* c0, const float* c1, const float* c2
     const float* src[4] = {c0, c1, c2, c3};
     for (int i = 0; i < 4; ++i) {
         const Act& a = ctx->cond[i];
-        CK(launch_nchw_f32_to_nhwc_bf16(src[i], a.p, ctx->B, a.C, a.H * a.W, a.C, S(s)));
+        CK(launch_nchw_f32_to_nhwc_act(src[i], a.p, ctx->B, a.C, a.H * a.W, a.C, S(s)));
     }
     return CDC_OK;
 }
@@ -1023,7 +1025,7 @@ int cdc_set_latent(cdc_ctx* ctx, const float* y_hat, cdc_stream s) {
     NEED_PLAN();
     if (!ctx->has_ctx) return ctx->fail(CDC_ERR_WEIGHT, "context-net weights (context.*) were not loaded");
     const Act& a = ctx->latent;
-    CK(launch_nchw_f32_to_nhwc_bf16(y_hat, a.p, ctx->B, a.C, a.H * a.W, a.C, S(s)));
+    CK(launch_nchw_f32_to_nhwc_act(y_hat, a.p, ctx->B, a.C, a.H * a.W, a.C, S(s)));
     for (Op& op : ctx->ctx_ops) {
         cudaError_t e = op.run(S(s), 0);
         if (e != cudaSuccess) return ctx->fail(CDC_ERR_CUDA, "%s: %s", op.name.c_str(), cudaGetErrorString(e));
@@ -1162,6 +1164,10 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
         g_create_err = "not an sm_100 device";
         return CDC_ERR_ARCH;
     }
+    if (configure_conv_kernels() != cudaSuccess) {
+        g_create_err = "cudaFuncSetAttribute(conv_tc_kernel) failed";
+        return CDC_ERR_CUDA;
+    }
     Arena ar;
     ConvW cw;
     const int cin = c0 + c1;
@@ -1174,25 +1180,25 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
     ConvBuild cb;
     cb.name = "test_conv";
     Act a0;
-    a0.p = static_cast<__nv_bfloat16*>(const_cast<void*>(src0));
+    a0.p = static_cast<act_t*>(const_cast<void*>(src0));
     a0.C = c0;
     a0.H = H;
     a0.W = W;
     cb.srcs.push_back(a0);
     if (src1) {
         Act a1 = a0;
-        a1.p = static_cast<__nv_bfloat16*>(const_cast<void*>(src1));
+        a1.p = static_cast<act_t*>(const_cast<void*>(src1));
         a1.C = c1;
         cb.srcs.push_back(a1);
     }
     cb.w = &cw;
     cb.mode = mode;
     cb.ksize = ksize;
-    cb.out.p = static_cast<__nv_bfloat16*>(out);
+    cb.out.p = static_cast<act_t*>(out);
     cb.out.C = cw.n_pad;
     cb.out.H = mode == MODE_S2 ? H / 2 : (mode == MODE_UP2 ? 2 * H : H);
     cb.out.W = mode == MODE_S2 ? W / 2 : (mode == MODE_UP2 ? 2 * W : W);
-    cb.residual = static_cast<const __nv_bfloat16*>(residual);
+    cb.residual = static_cast<const act_t*>(residual);
     cb.force_bn = force_bn;
     if (stats) {
         cb.epi = EPI_STATS;
@@ -1219,7 +1225,7 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
 }
 
 int cdc_test_attention(const void* qkv, void* out, int B, int N, int heads, cdc_stream s) {
-    return launch_attention(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), B, N, heads, S(s)) ==
+    return launch_attention(static_cast<const act_t*>(qkv), static_cast<act_t*>(out), B, N, heads, S(s)) ==
                    cudaSuccess
                ? CDC_OK
                : CDC_ERR_CUDA;
@@ -1235,11 +1241,11 @@ int cdc_test_gn(const void* x, const void* r, void* y, const float* gamma, const
         cudaFree(partials);
         return CDC_ERR_CUDA;
     }
-    cudaError_t e = launch_gn_stats(static_cast<const __nv_bfloat16*>(x), partials, B, HW, C, nullptr, S(s));
+    cudaError_t e = launch_gn_stats(static_cast<const act_t*>(x), partials, B, HW, C, nullptr, S(s));
     if (e == cudaSuccess) e = launch_gn_finalize(partials, PT, gamma, beta, film, ab, B, C, HW, eps, S(s));
     if (e == cudaSuccess)
-        e = launch_gn_apply(static_cast<const __nv_bfloat16*>(x), ab, static_cast<const __nv_bfloat16*>(r),
-                            static_cast<__nv_bfloat16*>(y), B, HW, C, silu, dev_sms(), S(s));
+        e = launch_gn_apply(static_cast<const act_t*>(x), ab, static_cast<const act_t*>(r),
+                            static_cast<act_t*>(y), B, HW, C, silu, dev_sms(), S(s));
     if (e == cudaSuccess) e = cudaStreamSynchronize(S(s));
     cudaFree(partials);
     cudaFree(ab);

@@ -8,7 +8,7 @@
  *
  * Conventions: plain pointers and sizes only; all tensor pointers are DEVICE pointers unless the
  * name says `_host`; tensors cross the boundary as contiguous NCHW fp32 (the layout of the
- * oracle's torch tensors) and are converted to the internal NHWC bf16 layout on the device.
+ * oracle's torch tensors) and are converted to the internal NHWC 16-bit layout (fp16 by default, see csrc/act.cuh) on the device.
  * Every call returns 0 on success or a negative cdc_status; the message is available from
  * cdc_last_error().  Nothing throws across the ABI.  There is NO CPU fallback: a device that is
  * not sm_100 is CDC_ERR_ARCH.  One cdc_ctx per (process, device); not thread-safe; all work is
@@ -54,11 +54,12 @@ int cdc_create(const cdc_config* cfg, int device, cdc_ctx** out);
 void cdc_destroy(cdc_ctx* ctx);
 const char* cdc_last_error(cdc_ctx* ctx); /* ctx may be NULL: last error of a failed cdc_create */
 int cdc_abi_version(void);
+int cdc_act_dtype(void); /* storage / MMA operand type of activations: 1 = fp16 (default build), 0 = bf16 */
 
 /* ---- weights: oracle/unet.py UNet.state_dict() (+ "context." + oracle/codec.py ContextNet) ----
  * `name` is the state-dict key, `dev_ptr` a device fp32 tensor in PyTorch layout (conv OIHW,
  * linear [out][in]).  The data is copied; the caller may free it after the call returns and the
- * stream is synchronised.  cdc_finalize_weights() repacks conv weights to bf16 [C_out][kh][kw][C_in]
+ * stream is synchronised.  cdc_finalize_weights() repacks conv weights to 16-bit [C_out][kh][kw][C_in]
  * and fails with CDC_ERR_WEIGHT naming the first missing tensor. */
 int cdc_load_weights(cdc_ctx* ctx, const char* name, const void* dev_ptr, const int64_t* shape, int ndim);
 int cdc_finalize_weights(cdc_ctx* ctx);
@@ -106,8 +107,8 @@ int cdc_cdf_lookup(const int32_t* q, const float* sigma, const int32_t* cdf, con
                    cdc_stream s);
 
 /* ---- single-op entry points for kernel-level parity tests -------------------------------------- */
-/* conv: x NHWC bf16 sources (1 or 2), w OIHW fp32 (device), bias fp32; mode 0 = stride 1,
- * 1 = stride 2, 2 = nearest-x2 input; out NHWC bf16; stats (optional) [B][PT][32][2]. */
+/* conv: x NHWC 16-bit (cdc_act_dtype) sources (1 or 2), w OIHW fp32 (device), bias fp32; mode 0 = stride 1,
+ * 1 = stride 2, 2 = nearest-x2 input; out NHWC 16-bit; stats (optional) [B][PT][32][2]. */
 int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1, int B, int H, int W,
                   const float* w_oihw, const float* bias, int cout, int ksize, int mode, int force_bn,
                   const void* residual, void* out, float* stats, int* pt_out, cdc_stream s);

@@ -5,6 +5,8 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
+torch.backends.cudnn.allow_tf32 = False  # the torch checker must be true fp32
+torch.backends.cuda.matmul.allow_tf32 = False
 DEV = "cuda:0"
 TOL = 1e-2  # BASELINE.json north_star: reconstructions within 1e-2 max-abs of the fp32 oracle per step
 

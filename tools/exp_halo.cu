@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(128, 1) exp_kernel(const __grid_constant__ Par
         if (threadIdx.x == 0) {
             const uint64_t ad = make_sw128_desc(sA + p.cfg[c].s * 128, p.cfg[c].bo);
             const uint64_t bd = make_sw128_desc(sB);
-            for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem, ad + 2 * k, bd + 2 * k, make_idesc_bf16(128, 64), k != 0);
+            for (int k = 0; k < 4; ++k) umma_f16_ss(tmem, ad + 2 * k, bd + 2 * k, ((1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24)), k != 0);
             umma_commit(bars + 8);
         }
         mbar_wait(bars + 8, ph);
