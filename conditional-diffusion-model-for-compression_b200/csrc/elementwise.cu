@@ -79,40 +79,43 @@ cudaError_t launch_gn_stats(const act_t* x, float* partials, int B, int HW, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Finalize: one CTA per image, one warp per group.  Lane l sums partials l, l+32, ... in order,
-// then a fixed shuffle tree; double accumulation for the final mean / variance.
-__global__ void __launch_bounds__(1024) gn_finalize_kernel(const float* __restrict__ partials, int PT,
-                                                           const float* __restrict__ gamma,
-                                                           const float* __restrict__ beta,
-                                                           const float* __restrict__ film, float2* __restrict__ ab,
-                                                           int C, int HW, float eps) {
-    __shared__ float s_mean[32], s_rstd[32];
-    const int b = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// Finalize: one CTA per (group, image).  Thread t sums partials t, t+256, ... in order, then a fixed
+// shared-memory tree; double accumulation.  The CTA then writes (a, b) for its C/32 channels.
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restrict__ partials, int PT,
+                                                          const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta,
+                                                          const float* __restrict__ film, float2* __restrict__ ab,
+                                                          int C, int HW, float eps) {
+    __shared__ double s_s[256], s_q[256];
+    const int g = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
     const float2* src = reinterpret_cast<const float2*>(partials) + static_cast<size_t>(b) * PT * 32 + g;
     double s = 0.0, q = 0.0;
-    for (int pt = lane; pt < PT; pt += 32) {
+    for (int pt = t; pt < PT; pt += 256) {
         const float2 v = src[static_cast<size_t>(pt) * 32];
         s += v.x;
         q += v.y;
     }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, m);
-        q += __shfl_xor_sync(0xffffffffu, q, m);
-    }
-    if (lane == 0) {
-        const double n = static_cast<double>(C / 32) * HW;
-        const double mean = s / n;
-        double var = q / n - mean * mean;
-        if (var < 0.0) var = 0.0;
-        s_mean[g] = static_cast<float>(mean);
-        s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    }
+    s_s[t] = s;
+    s_q[t] = q;
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += 1024) {
-        const int gg = c / (C / 32);
-        float a = gamma[c] * s_rstd[gg];
-        float bb = beta[c] - s_mean[gg] * a;
+#pragma unroll
+    for (int m = 128; m >= 1; m >>= 1) {
+        if (t < m) {
+            s_s[t] += s_s[t + m];
+            s_q[t] += s_q[t + m];
+        }
+        __syncthreads();
+    }
+    const int cpg = C / 32;
+    if (t < cpg) {
+        const double n = static_cast<double>(cpg) * HW;
+        const double mean = s_s[0] / n;
+        double var = s_q[0] / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+        const int c = g * cpg + t;
+        float a = gamma[c] * rstd;
+        float bb = beta[c] - static_cast<float>(mean) * a;
         if (film) {
             const float sc = 1.0f + film[c], sh = film[C + c];
             a *= sc;
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(1024) gn_finalize_kernel(const float* __restri
 
 cudaError_t launch_gn_finalize(const float* partials, int PT, const float* gamma, const float* beta, const float* film,
                                float2* ab, int B, int C, int HW, float eps, cudaStream_t s) {
-    gn_finalize_kernel<<<B, 1024, 0, s>>>(partials, PT, gamma, beta, film, ab, C, HW, eps);
+    gn_finalize_kernel<<<dim3(32, B), 256, 0, s>>>(partials, PT, gamma, beta, film, ab, C, HW, eps);
     return cudaGetLastError();
 }
 
@@ -133,35 +136,66 @@ cudaError_t launch_gn_finalize(const float* partials, int PT, const float* gamma
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
 
 template <bool SILU, bool RES>
+__device__ __forceinline__ uint4 gn_apply_vec(const uint4 u, const uint4 rr, const float4 (&c)[4]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float v0 = c[j].x * act_lo(w[j]) + c[j].y;  // c = (a0, b0, a1, b1)
+        float v1 = c[j].z * act_hi(w[j]) + c[j].w;
+        if (SILU) {
+            v0 = silu_f(v0);
+            v1 = silu_f(v1);
+        }
+        if (RES) {
+            v0 += act_lo(rw[j]);
+            v1 += act_hi(rw[j]);
+        }
+        o[j] = pack_act2(v0, v1);
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// The grid stride is a multiple of the vectors per pixel, so a thread always owns the same 8 channels:
+// its (a, b) pairs live in registers and are reloaded only when the image index changes.
+template <bool SILU, bool RES>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* __restrict__ x, const float2* __restrict__ ab,
                                                        const uint4* __restrict__ r, uint4* __restrict__ y,
                                                        long long nvec, int vecs_per_pix, long long vecs_per_img) {
-    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < nvec; i += gridDim.x * 256LL) {
-        const int cv = static_cast<int>(i % vecs_per_pix);
-        const int b = static_cast<int>(i / vecs_per_img);
-        const float4* abp = reinterpret_cast<const float4*>(ab + (static_cast<size_t>(b) * vecs_per_pix + cv) * 8);
-        const uint4 u = x[i];
-        uint4 rr = make_uint4(0, 0, 0, 0);
-        if (RES) rr = r[i];
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-        const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
-        uint32_t o[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4 c = abp[j];  // (a0, b0, a1, b1)
-            float v0 = c.x * act_lo(w[j]) + c.y;
-            float v1 = c.z * act_hi(w[j]) + c.w;
-            if (SILU) {
-                v0 = silu_f(v0);
-                v1 = silu_f(v1);
-            }
-            if (RES) {
-                v0 += act_lo(rw[j]);
-                v1 += act_hi(rw[j]);
-            }
-            o[j] = pack_act2(v0, v1);
+    const long long stride = gridDim.x * 256LL;
+    long long i = blockIdx.x * 256LL + threadIdx.x;
+    const int cv = static_cast<int>(i % vecs_per_pix);
+    int cur_b = -1;
+    float4 c[4];
+    for (; i < nvec; i += 2 * stride) {
+        const long long i2 = i + stride;
+        const bool has2 = i2 < nvec;
+        const uint4 u0 = x[i];
+        uint4 u1 = make_uint4(0, 0, 0, 0), r0 = u1, r1 = u1;
+        if (has2) u1 = x[i2];
+        if (RES) {
+            r0 = r[i];
+            if (has2) r1 = r[i2];
         }
-        y[i] = make_uint4(o[0], o[1], o[2], o[3]);
+        int b = static_cast<int>(i / vecs_per_img);
+        if (b != cur_b) {
+            const float4* abp = reinterpret_cast<const float4*>(ab + (static_cast<size_t>(b) * vecs_per_pix + cv) * 8);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c[j] = abp[j];
+            cur_b = b;
+        }
+        y[i] = gn_apply_vec<SILU, RES>(u0, r0, c);
+        if (has2) {
+            b = static_cast<int>(i2 / vecs_per_img);
+            if (b != cur_b) {
+                const float4* abp = reinterpret_cast<const float4*>(ab + (static_cast<size_t>(b) * vecs_per_pix + cv) * 8);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) c[j] = abp[j];
+                cur_b = b;
+            }
+            y[i2] = gn_apply_vec<SILU, RES>(u1, r1, c);
+        }
     }
 }
 
@@ -170,20 +204,25 @@ cudaError_t launch_gn_apply(const act_t* x, const float2* ab, const act_t* r, ac
     const long long nvec = static_cast<long long>(B) * HW * C / 8;
     const int vpp = C / 8;
     const long long vpi = static_cast<long long>(HW) * vpp;
-    long long want = (nvec + 255) / 256;
-    const long long cap = static_cast<long long>(num_sms) * 16;
-    const int grid = static_cast<int>(want < cap ? want : cap);
+    long long want = (nvec + 511) / 512;
+    const long long cap = static_cast<long long>(num_sms) * 8;
+    long long grid = want < cap ? want : cap;
+    // (grid * 256) % vpp == 0  <=>  the per-thread channel vector is loop-invariant
+    const int need = vpp % 3 == 0 ? 3 : 1;  // 256 covers the power-of-two part of vpp (8, 16, 32, 64)
+    grid = (grid + need - 1) / need * need;
+    if ((grid * 256) % vpp != 0) return cudaErrorInvalidValue;
     const uint4* xv = reinterpret_cast<const uint4*>(x);
     const uint4* rv = reinterpret_cast<const uint4*>(r);
     uint4* yv = reinterpret_cast<uint4*>(y);
+    const int g = static_cast<int>(grid);
     if (silu && r)
-        gn_apply_kernel<true, true><<<grid, 256, 0, s>>>(xv, ab, rv, yv, nvec, vpp, vpi);
+        gn_apply_kernel<true, true><<<g, 256, 0, s>>>(xv, ab, rv, yv, nvec, vpp, vpi);
     else if (silu)
-        gn_apply_kernel<true, false><<<grid, 256, 0, s>>>(xv, ab, rv, yv, nvec, vpp, vpi);
+        gn_apply_kernel<true, false><<<g, 256, 0, s>>>(xv, ab, rv, yv, nvec, vpp, vpi);
     else if (r)
-        gn_apply_kernel<false, true><<<grid, 256, 0, s>>>(xv, ab, rv, yv, nvec, vpp, vpi);
+        gn_apply_kernel<false, true><<<g, 256, 0, s>>>(xv, ab, rv, yv, nvec, vpp, vpi);
     else
-        gn_apply_kernel<false, false><<<grid, 256, 0, s>>>(xv, ab, rv, yv, nvec, vpp, vpi);
+        gn_apply_kernel<false, false><<<g, 256, 0, s>>>(xv, ab, rv, yv, nvec, vpp, vpi);
     return cudaGetLastError();
 }
 

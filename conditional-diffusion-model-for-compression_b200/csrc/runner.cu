@@ -198,15 +198,22 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
     } else if (cb.force_bn) {
         bn = cb.force_bn;
     } else {
+        // Cost model from the round-1 per-layer measurements: a CTA ingests ~33 B/cycle from L2 through
+        // TMA when all SMs stream, a K-block costs max(MMA cycles, bytes / 33), and whole waves count.
         const int cands[4] = {256, 192, 128, 64};
-        int smallest = 0;
+        double best = 0;
         for (int c : cands) {
             if (w.n_pad % c) continue;
             if (cb.epi == EPI_STATS && !stats_inst_ok(c, cb.cpg)) continue;
-            smallest = c;
-            if (!bn && m_tiles * (w.n_pad / c) >= num_sms) bn = c;
+            const long tiles = m_tiles * (w.n_pad / c);
+            const long waves = (tiles + num_sms - 1) / num_sms;
+            const double mma = 4.0 * (c / 2.0), mem = (16384.0 + c * 128.0) / 33.0;
+            const double cost = static_cast<double>(waves) * (mma > mem ? mma : mem);
+            if (!bn || cost < best) {
+                bn = c;
+                best = cost;
+            }
         }
-        if (!bn) bn = smallest;
     }
     if (!bn || w.n_pad % bn) return fail("no N tile for C_out");
     if (cb.epi == EPI_STATS && !stats_inst_ok(bn, cb.cpg)) return fail("no stats instantiation for (BN, cpg)");
