@@ -27,6 +27,10 @@ __device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
     __half2 h = __floats2half2_rn(sat_act(lo), sat_act(hi));
     return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ uint32_t pack_act2_nosat(float lo, float hi) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
 __device__ __forceinline__ float act_lo(uint32_t u) { return __half2float(__ushort_as_half(static_cast<unsigned short>(u & 0xFFFFu))); }
 __device__ __forceinline__ float act_hi(uint32_t u) { return __half2float(__ushort_as_half(static_cast<unsigned short>(u >> 16))); }
 __device__ __forceinline__ act_t to_act(float v) { return __float2half_rn(sat_act(v)); }
@@ -40,6 +44,7 @@ __device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ uint32_t pack_act2_nosat(float lo, float hi) { return pack_act2(lo, hi); }
 __device__ __forceinline__ float act_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float act_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 __device__ __forceinline__ act_t to_act(float v) { return __float2bfloat16_rn(v); }

@@ -1,0 +1,149 @@
+// Shared epilogue of the tcgen05 conv kernels: one 128-pixel x BN accumulator tile
+// TMEM -> registers -> (+bias, GroupNorm partials, residual, DDIM update) -> global.
+// Called by the 4 epilogue warps (128 threads); thread = TMEM lane = output pixel.
+#pragma once
+#include "conv_tc.cuh"
+#include "ptx.cuh"
+
+namespace cdc {
+
+struct EpiArgs {
+    act_t* out;
+    const act_t* residual;
+    int ldc;
+    // EPI_DDIM
+    float* x;
+    act_t* xpad;
+    float* x0_out;
+    float c0, c1;
+};
+
+template <int G>
+__device__ __forceinline__ float warp_group_reduce(float (&s)[G], int lane) {
+    // Butterfly reduce-scatter over the warp: on return lane L holds the warp total of group
+    // L >> (5 - log2 G).  Fixed shuffle order => bitwise reproducible.
+    constexpr int LOG2G = (G == 32) ? 5 : (G == 16) ? 4 : (G == 8) ? 3 : (G == 4) ? 2 : (G == 2) ? 1 : 0;
+    static_assert((1 << LOG2G) == G, "G must be a power of two <= 32");
+#pragma unroll
+    for (int step = 0; step < LOG2G; ++step) {
+        const int m = 16 >> step;
+        const int half = G >> (step + 1);
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < G / 2; ++i) {
+            if (i < half) {
+                const float send = up ? s[i] : s[i + half];
+                const float keep = up ? s[i + half] : s[i];
+                s[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+            }
+        }
+    }
+    float r = s[0];
+#pragma unroll
+    for (int m = (16 >> LOG2G); m >= 1; m >>= 1) r += __shfl_xor_sync(0xffffffffu, r, m);
+    return r;
+}
+
+// taddr: TMEM address of this warp's 32 lanes of the accumulator; bar_tempty: mbarrier (128 arrivals)
+// that hands the accumulator back to the MMA warp; bs: bias of this N tile (shared memory);
+// red: 4*32*2 floats of shared scratch (alternate between consecutive tiles);
+// stats_dst: this tile's first group slot in the partials buffer ([.. 32 groups ..][2]) or unused.
+template <int BN, int CPG, int EPI>
+__device__ __forceinline__ void conv_epilogue_tile(const EpiArgs& e, uint32_t taddr, uint32_t bar_tempty,
+                                                   const float* bs, float* red, int q, int lane, bool valid,
+                                                   size_t pix, int n0, float* stats_dst) {
+    constexpr int G = (EPI == EPI_STATS) ? BN / CPG : 1;
+    const int row = q * 32 + lane;
+    if constexpr (EPI == EPI_DDIM) {
+        uint32_t v[16];
+        tmem_ld16(taddr, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(bar_tempty);
+        if (valid) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float x0 = __uint_as_float(v[c]) + bs[c];
+                const float xt = e.x[pix * 3 + c];
+                const float xn = e.c0 * fminf(fmaxf(x0, -1.0f), 1.0f) + e.c1 * xt;
+                e.x[pix * 3 + c] = xn;
+                e.xpad[pix * 64 + c] = to_act(xn);
+                if (e.x0_out) e.x0_out[pix * 3 + c] = x0;
+            }
+        }
+    } else {
+        float gs[G], gq[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) gs[g] = gq[g] = 0.0f;
+        act_t* orow = e.out + pix * e.ldc + n0;
+        const act_t* rrow = e.residual ? e.residual + pix * e.ldc + n0 : nullptr;
+#pragma unroll
+        for (int ch = 0; ch < BN / 32; ++ch) {
+            uint32_t v[32];
+            tmem_ld32(taddr + ch * 32, v);
+            tmem_ld_wait();
+            if (ch == BN / 32 - 1) {  // accumulator drained: hand the TMEM stage back early
+                tc_fence_before();
+                mbar_arrive(bar_tempty);
+            }
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bs[ch * 32 + j];
+            if constexpr (EPI == EPI_STATS) {
+                const float msk = valid ? 1.0f : 0.0f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int g = (ch * 32 + j) / CPG;
+                    const float x = f[j] * msk;
+                    gs[g] += x;
+                    gq[g] += x * x;
+                }
+            }
+            if (valid) {
+                uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
+#pragma unroll
+                for (int s4 = 0; s4 < 4; ++s4) {
+                    if (rrow) {
+                        const uint4 r = *reinterpret_cast<const uint4*>(rrow + ch * 32 + s4 * 8);
+                        f[s4 * 8 + 0] += act_lo(r.x);
+                        f[s4 * 8 + 1] += act_hi(r.x);
+                        f[s4 * 8 + 2] += act_lo(r.y);
+                        f[s4 * 8 + 3] += act_hi(r.y);
+                        f[s4 * 8 + 4] += act_lo(r.z);
+                        f[s4 * 8 + 5] += act_hi(r.z);
+                        f[s4 * 8 + 6] += act_lo(r.w);
+                        f[s4 * 8 + 7] += act_hi(r.w);
+                    }
+                    uint4 o;
+                    o.x = pack_act2(f[s4 * 8 + 0], f[s4 * 8 + 1]);
+                    o.y = pack_act2(f[s4 * 8 + 2], f[s4 * 8 + 3]);
+                    o.z = pack_act2(f[s4 * 8 + 4], f[s4 * 8 + 5]);
+                    o.w = pack_act2(f[s4 * 8 + 6], f[s4 * 8 + 7]);
+                    dst[s4] = o;
+                }
+            }
+        }
+        if constexpr (EPI == EPI_STATS) {
+            // warp butterfly -> 4 warps through smem -> one fixed-order partial per (tile, group)
+            const float ws = warp_group_reduce<G>(gs, lane);
+            const float wq = warp_group_reduce<G>(gq, lane);
+            constexpr int REP = 32 / G;
+            if ((lane & (REP - 1)) == 0) {
+                const int g = lane / REP;
+                red[(q * 32 + g) * 2 + 0] = ws;
+                red[(q * 32 + g) * 2 + 1] = wq;
+            }
+            named_bar_sync(1, 128);
+            if (row < G) {
+                const float s = ((red[(0 * 32 + row) * 2] + red[(1 * 32 + row) * 2]) + red[(2 * 32 + row) * 2]) +
+                                red[(3 * 32 + row) * 2];
+                const float s2 = ((red[(0 * 32 + row) * 2 + 1] + red[(1 * 32 + row) * 2 + 1]) +
+                                  red[(2 * 32 + row) * 2 + 1]) + red[(3 * 32 + row) * 2 + 1];
+                stats_dst[row * 2 + 0] = s;
+                stats_dst[row * 2 + 1] = s2;
+            }
+        }
+    }
+}
+
+}  // namespace cdc

@@ -15,6 +15,7 @@
 // Oracle counterpart: oracle/unet.py `conv`, `Up`, `RB` (the reference ships no code).
 #include <stdio.h>
 
+#include "conv_epilogue.cuh"
 #include "conv_tc.cuh"
 #include "ptx.cuh"
 
@@ -39,38 +40,10 @@ struct ConvCfg {
     static constexpr int SMEM_BYTES = 1024 + NS * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + RED_BYTES;
 };
 
-template <int G>
-__device__ __forceinline__ float warp_group_reduce(float (&s)[G], int lane) {
-    // Butterfly reduce-scatter over the warp: on return lane L holds the warp total of group
-    // L >> (5 - log2 G).  Fixed shuffle order => bitwise reproducible.
-    constexpr int LOG2G = (G == 32) ? 5 : (G == 16) ? 4 : (G == 8) ? 3 : (G == 4) ? 2 : (G == 2) ? 1 : 0;
-    static_assert((1 << LOG2G) == G, "G must be a power of two <= 32");
-#pragma unroll
-    for (int step = 0; step < LOG2G; ++step) {
-        const int m = 16 >> step;
-        const int half = G >> (step + 1);
-        const bool up = (lane & m) != 0;
-#pragma unroll
-        for (int i = 0; i < G / 2; ++i) {
-            if (i < half) {
-                const float send = up ? s[i] : s[i + half];
-                const float keep = up ? s[i + half] : s[i];
-                s[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
-            }
-        }
-    }
-    float r = s[0];
-#pragma unroll
-    for (int m = (16 >> LOG2G); m >= 1; m >>= 1) r += __shfl_xor_sync(0xffffffffu, r, m);
-    return r;
-}
-
 template <int BN, int CPG, int EPI>
 __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
     using Cfg = ConvCfg<BN>;
     constexpr int NS = Cfg::NS;
-    constexpr int G = (EPI == EPI_STATS) ? BN / CPG : 1;
-
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
     const uint32_t base = (raw_u32 + 1023u) & ~1023u;  // 128B-swizzle atoms need 1024 B alignment
@@ -179,6 +152,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
         const int q = warp & 3;  // TMEM sub-partition: lanes 32q .. 32q+31
         const int row = q * 32 + lane;
         const int ty = row >> BWl, tx = row & (BW - 1);
+        const EpiArgs ea{p.out, p.residual, p.ldc, p.x, p.xpad, p.x0_out, p.c0, p.c1};
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             int nt, ph, b, th, tw;
@@ -193,101 +167,13 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE;
 
-            if constexpr (EPI == EPI_DDIM) {
-                uint32_t v[16];
-                tmem_ld16(taddr, v);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(bar_tempty + 8 * as);
-                if (valid) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const float x0 = __uint_as_float(v[c]) + bias_s[c];
-                        const float xt = p.x[pix * 3 + c];
-                        const float xn = p.c0 * fminf(fmaxf(x0, -1.0f), 1.0f) + p.c1 * xt;
-                        p.x[pix * 3 + c] = xn;
-                        p.xpad[pix * 64 + c] = to_act(xn);
-                        if (p.x0_out) p.x0_out[pix * 3 + c] = x0;
-                    }
-                }
-            } else {
-                float gs[G], gq[G];
-#pragma unroll
-                for (int g = 0; g < G; ++g) gs[g] = gq[g] = 0.0f;
-                act_t* orow = p.out + pix * p.ldc + nt * BN;
-                const act_t* rrow = p.residual ? p.residual + pix * p.ldc + nt * BN : nullptr;
-                const float* bs = bias_s + nt * BN;
-#pragma unroll
-                for (int ch = 0; ch < BN / 32; ++ch) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + ch * 32, v);
-                    tmem_ld_wait();
-                    if (ch == BN / 32 - 1) {  // accumulator drained: hand the TMEM stage back early
-                        tc_fence_before();
-                        mbar_arrive(bar_tempty + 8 * as);
-                    }
-                    float f[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bs[ch * 32 + j];
-                    if constexpr (EPI == EPI_STATS) {
-                        const float msk = valid ? 1.0f : 0.0f;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int g = (ch * 32 + j) / CPG;
-                            const float x = f[j] * msk;
-                            gs[g] += x;
-                            gq[g] += x * x;
-                        }
-                    }
-                    if (valid) {
-                        uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
-#pragma unroll
-                        for (int s4 = 0; s4 < 4; ++s4) {
-                            if (rrow) {
-                                const uint4 r = *reinterpret_cast<const uint4*>(rrow + ch * 32 + s4 * 8);
-                                f[s4 * 8 + 0] += act_lo(r.x);
-                                f[s4 * 8 + 1] += act_hi(r.x);
-                                f[s4 * 8 + 2] += act_lo(r.y);
-                                f[s4 * 8 + 3] += act_hi(r.y);
-                                f[s4 * 8 + 4] += act_lo(r.z);
-                                f[s4 * 8 + 5] += act_hi(r.z);
-                                f[s4 * 8 + 6] += act_lo(r.w);
-                                f[s4 * 8 + 7] += act_hi(r.w);
-                            }
-                            uint4 o;
-                            o.x = pack_act2(f[s4 * 8 + 0], f[s4 * 8 + 1]);
-                            o.y = pack_act2(f[s4 * 8 + 2], f[s4 * 8 + 3]);
-                            o.z = pack_act2(f[s4 * 8 + 4], f[s4 * 8 + 5]);
-                            o.w = pack_act2(f[s4 * 8 + 6], f[s4 * 8 + 7]);
-                            dst[s4] = o;
-                        }
-                    }
-                }
-                if constexpr (EPI == EPI_STATS) {
-                    // warp butterfly -> 4 warps through smem -> one fixed-order partial per (tile, group)
-                    const float ws = warp_group_reduce<G>(gs, lane);
-                    const float wq = warp_group_reduce<G>(gq, lane);
-                    constexpr int REP = 32 / G;
-                    float* red = red_s + (it & 1) * (4 * 32 * 2);
-                    if ((lane & (REP - 1)) == 0) {
-                        const int g = lane / REP;
-                        red[(q * 32 + g) * 2 + 0] = ws;
-                        red[(q * 32 + g) * 2 + 1] = wq;
-                    }
-                    named_bar_sync(1, 128);
-                    if (row < G) {
-                        const float s = ((red[(0 * 32 + row) * 2] + red[(1 * 32 + row) * 2]) +
-                                         red[(2 * 32 + row) * 2]) + red[(3 * 32 + row) * 2];
-                        const float s2 = ((red[(0 * 32 + row) * 2 + 1] + red[(1 * 32 + row) * 2 + 1]) +
-                                          red[(2 * 32 + row) * 2 + 1]) + red[(3 * 32 + row) * 2 + 1];
-                        const int PT = p.nphase * p.tiles_h * p.tiles_w;
-                        const int pt = (ph * p.tiles_h + th) * p.tiles_w + tw;
-                        float* dst = p.stats + ((static_cast<size_t>(b) * PT + pt) * 32 + nt * G + row) * 2;
-                        dst[0] = s;
-                        dst[1] = s2;
-                    }
-                }
-            }
+            const int PT = p.nphase * p.tiles_h * p.tiles_w;
+            const int pt = (ph * p.tiles_h + th) * p.tiles_w + tw;
+            float* sdst = (EPI == EPI_STATS)
+                              ? p.stats + ((static_cast<size_t>(b) * PT + pt) * 32 + nt * (BN / CPG)) * 2
+                              : nullptr;
+            conv_epilogue_tile<BN, CPG, EPI>(ea, taddr, bar_tempty + 8 * as, bias_s + nt * BN,
+                                             red_s + (it & 1) * (4 * 32 * 2), q, lane, valid, pix, nt * BN, sdst);
         }
     }
 

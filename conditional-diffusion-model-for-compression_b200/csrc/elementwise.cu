@@ -133,7 +133,8 @@ cudaError_t launch_gn_finalize(const float* partials, int PT, const float* gamma
 
 // ------------------------------------------------------------------------------------------------
 // Apply: y = SiLU(a*x + b) (+ r), 8 channels (16 B) per thread, grid-stride.
-__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+// x * sigmoid(x) with MUFU ex2 + MUFU rcp (5 instructions): the apply kernel is issue-bound otherwise
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 template <bool SILU, bool RES>
 __device__ __forceinline__ uint4 gn_apply_vec(const uint4 u, const uint4 rr, const float4 (&c)[4]) {
@@ -152,7 +153,7 @@ __device__ __forceinline__ uint4 gn_apply_vec(const uint4 u, const uint4 rr, con
             v0 += act_lo(rw[j]);
             v1 += act_hi(rw[j]);
         }
-        o[j] = pack_act2(v0, v1);
+        o[j] = pack_act2_nosat(v0, v1);  // |SiLU(GN(x))| (+ residual) cannot reach the fp16 limit
     }
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* __restrict__
     long long i = blockIdx.x * 256LL + threadIdx.x;
     const int cv = static_cast<int>(i % vecs_per_pix);
     int cur_b = -1;
+    const bool single = vecs_per_img >= nvec;  // one image: skip the 64-bit divide
     float4 c[4];
     for (; i < nvec; i += 2 * stride) {
         const long long i2 = i + stride;
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* __restrict__
             r0 = r[i];
             if (has2) r1 = r[i2];
         }
-        int b = static_cast<int>(i / vecs_per_img);
+        int b = single ? 0 : static_cast<int>(i / vecs_per_img);
         if (b != cur_b) {
             const float4* abp = reinterpret_cast<const float4*>(ab + (static_cast<size_t>(b) * vecs_per_pix + cv) * 8);
 #pragma unroll
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* __restrict__
         }
         y[i] = gn_apply_vec<SILU, RES>(u0, r0, c);
         if (has2) {
-            b = static_cast<int>(i2 / vecs_per_img);
+            b = single ? 0 : static_cast<int>(i2 / vecs_per_img);
             if (b != cur_b) {
                 const float4* abp = reinterpret_cast<const float4*>(ab + (static_cast<size_t>(b) * vecs_per_pix + cv) * 8);
 #pragma unroll

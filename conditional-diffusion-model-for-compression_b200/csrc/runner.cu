@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/cdc_b200.h"
+#include "conv_strip.cuh"
 #include "conv_tc.cuh"
 #include "kernels.cuh"
 
@@ -95,7 +96,7 @@ struct ConvBuild {
     int cpg = 1;
     float* stats = nullptr;
     const act_t* residual = nullptr;
-    int force_bn = 0;
+    int force_bn = 0;   // > 0: force the N tile of conv_tc.cu; -1: force conv_tc.cu with its own choice
     // DDIM
     float* x = nullptr;
     act_t* xpad = nullptr;
@@ -190,12 +191,71 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
     if (cb.epi != EPI_DDIM && (cb.out.H != OH || cb.out.W != OW || cb.out.C != w.n_pad))
         return fail("output tensor shape mismatch");
 
+    // ---- strip variant (conv_strip.cu): 3x3, stride 1, one N tile, image at least one segment wide ----
+    {
+        const int bn_s = cb.epi == EPI_DDIM ? 16 : w.n_pad;
+        const int CH = ctot / 64;
+        int NR = 0, NSW = 0;
+        const bool wide = gw >= 128 && (gw % 128 == 0 || gw >= 512);
+        if (cb.mode == MODE_S1 && cb.ksize == 3 && cb.force_bn == 0 && wide && strip_inst_ok(bn_s, cb.cpg, cb.epi) &&
+            strip_plan(bn_s, CH, &NR, &NSW)) {
+            auto sp = std::shared_ptr<StripParams>(new StripParams());
+            memset(sp.get(), 0, sizeof(StripParams));
+            for (size_t s = 0; s < cb.srcs.size(); ++s) {
+                const Act& a = cb.srcs[s];
+                if (encode_act_map(&sp->amap[s], a.p, a.C, a.W, a.H, B, static_cast<size_t>(a.C),
+                                   static_cast<size_t>(a.W) * a.C, static_cast<size_t>(a.H) * a.W * a.C, 130, 1))
+                    return fail("cuTensorMapEncodeTiled (strip activation) failed");
+            }
+            if (encode_w_map(&sp->wmap, w.w, w.taps * w.c_pad, w.n_pad, bn_s)) return fail("cuTensorMapEncodeTiled (weights) failed");
+            sp->chunks0 = cb.srcs[0].C / 64;
+            sp->CH = CH;
+            sp->H = gh;
+            sp->W = gw;
+            sp->batch = B;
+            sp->nseg = (gw + 127) / 128;
+            // rows per strip: the fewest strips that still give every SM a unit (halo rows cost 2 / L)
+            int L = 1;
+            while (static_cast<long>(B) * sp->nseg * ((gh + L - 1) / L) > num_sms && L < gh) ++L;
+            sp->L = L;
+            sp->strips_per_col = (gh + L - 1) / L;
+            sp->NR = NR;
+            sp->NSW = NSW;
+            sp->ldc = cb.epi == EPI_DDIM ? 3 : cb.out.C;
+            sp->n_total = w.n_pad;
+            sp->out = cb.out.p;
+            sp->bias = w.bias;
+            sp->residual = cb.residual;
+            sp->stats = cb.stats;
+            sp->x = cb.x;
+            sp->xpad = cb.xpad;
+            sp->x0_out = cb.x0_out;
+            const double Ms = static_cast<double>(B) * gh * gw;
+            op->name = cb.name;
+            op->flops = 2.0 * Ms * w.n_true * (9.0 * w.c_true);
+            op->bytes = 2.0 * (Ms * w.c_true + Ms * w.n_true + 9.0 * w.c_true * w.n_true);
+            const int epi = cb.epi, cpg = cb.cpg;
+            const std::vector<float>*c0 = cb.c0, *c1 = cb.c1;
+            op->run = [sp, bn_s, cpg, epi, num_sms, c0, c1](cudaStream_t s, int k) -> cudaError_t {
+                if (epi == EPI_DDIM) {
+                    if (!c0 || k < 0 || k >= static_cast<int>(c0->size())) return cudaErrorInvalidValue;
+                    StripParams q = *sp;
+                    q.c0 = (*c0)[k];
+                    q.c1 = (*c1)[k];
+                    return launch_conv_strip(q, bn_s, cpg, epi, num_sms, s);
+                }
+                return launch_conv_strip(*sp, bn_s, cpg, epi, num_sms, s);
+            };
+            return CDC_OK;
+        }
+    }
+
     // N tile
     const long m_tiles = static_cast<long>(nphase) * B * tiles_w * tiles_h;
     int bn = 0;
     if (cb.epi == EPI_DDIM) {
         bn = 16;
-    } else if (cb.force_bn) {
+    } else if (cb.force_bn > 0) {
         bn = cb.force_bn;
     } else {
         // Cost model from the round-1 per-layer measurements: a CTA ingests ~33 B/cycle from L2 through
@@ -314,9 +374,22 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
     return CDC_OK;
 }
 
+static bool conv_uses_strip(const ConvBuild& cb) {
+    int gw, gh, nphase, os, bwl, tw, th;
+    conv_geometry(cb, gw, gh, nphase, os, bwl, tw, th);
+    int ctot = 0;
+    for (const Act& a : cb.srcs) ctot += a.C;
+    const int bn_s = cb.epi == EPI_DDIM ? 16 : cb.w->n_pad;
+    int NR, NSW;
+    const bool wide = gw >= 128 && (gw % 128 == 0 || gw >= 512);
+    return cb.mode == MODE_S1 && cb.ksize == 3 && cb.force_bn == 0 && wide && strip_inst_ok(bn_s, cb.cpg, cb.epi) &&
+           strip_plan(bn_s, ctot / 64, &NR, &NSW);
+}
+
 static int conv_num_partials(const ConvBuild& cb) {
     int gw, gh, nphase, os, bwl, tw, th;
     conv_geometry(cb, gw, gh, nphase, os, bwl, tw, th);
+    if (conv_uses_strip(cb)) return gh * ((gw + 127) / 128);
     return nphase * tw * th;
 }
 
@@ -804,8 +877,8 @@ int cdc_create(const cdc_config* cfg, int device, cdc_ctx** out) {
         g_create_err = "cuTensorMapEncodeTiled entry point not found";
         return CDC_ERR_CUDA;
     }
-    if ((e = configure_conv_kernels()) != cudaSuccess) {
-        g_create_err = std::string("cudaFuncSetAttribute(conv_tc_kernel): ") + cudaGetErrorString(e);
+    if ((e = configure_conv_kernels()) != cudaSuccess || (e = configure_strip_kernels()) != cudaSuccess) {
+        g_create_err = std::string("cudaFuncSetAttribute(conv kernels): ") + cudaGetErrorString(e);
         return CDC_ERR_CUDA;
     }
     cdc_ctx* ctx = new cdc_ctx();
@@ -1171,8 +1244,8 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
         g_create_err = "not an sm_100 device";
         return CDC_ERR_ARCH;
     }
-    if (configure_conv_kernels() != cudaSuccess) {
-        g_create_err = "cudaFuncSetAttribute(conv_tc_kernel) failed";
+    if (configure_conv_kernels() != cudaSuccess || configure_strip_kernels() != cudaSuccess) {
+        g_create_err = "cudaFuncSetAttribute(conv kernels) failed";
         return CDC_ERR_CUDA;
     }
     Arena ar;

@@ -96,6 +96,13 @@ CONV_CASES = [
     ("ragged_s2_24x40", 1, 24, 40, [64], 128, 3, 1, 0),
     ("big_k4608_n256", 1, 16, 32, [256, 256], 256, 3, 0, 0),
     ("multi_tile_persistent", 4, 64, 128, [64], 64, 3, 0, 0),
+    # strip variant (conv_strip.cu): W a multiple of 128, one N tile; resident and streamed weights
+    ("strip_c64_n64_256x256", 1, 256, 256, [64], 64, 3, 0, 0),
+    ("strip_rows_not_multiple_of_L", 3, 50, 256, [64], 64, 3, 0, 0),
+    ("strip_dual_64+64_n64", 1, 64, 384, [64, 64], 64, 3, 0, 0),
+    ("strip_c128_n128", 2, 32, 128, [128], 128, 3, 0, 0),
+    ("strip_c64+128_n128_streamed", 1, 48, 256, [64, 128], 128, 3, 0, 0),
+    ("same_shape_through_conv_tc", 1, 64, 256, [64], 64, 3, 0, -1),
 ]
 
 
@@ -119,7 +126,7 @@ def test_conv_residual_epilogue():
     _check(o, _ref_conv(srcs, w, b, 1, 0, residual=r), "residual")
 
 
-@pytest.mark.parametrize("cfg", [(64, 1, 64, 128, 0), (128, 2, 32, 64, 0), (128, 1, 16, 16, 64), (192, 1, 32, 32, 0),
+@pytest.mark.parametrize("cfg", [(64, 2, 70, 256, 0), (128, 1, 32, 128, 0), (64, 1, 64, 128, -1), (64, 1, 64, 128, 0), (128, 2, 32, 64, 0), (128, 1, 16, 16, 64), (192, 1, 32, 32, 0),
                                  (256, 1, 16, 32, 256), (256, 1, 16, 16, 128), (256, 1, 16, 16, 64),
                                  (64, 1, 24, 48, 0)])
 def test_conv_groupnorm_partials(cfg):
