@@ -23,9 +23,10 @@ constexpr uint32_t kUmmaFormat = 0;  // tcgen05 kind::f16 a_format / b_format: 0
 #define CDC_TMA_DTYPE CU_TENSOR_MAP_DATA_TYPE_FLOAT16
 #define CDC_MMA_SYNC_T "f16"
 __host__ __device__ __forceinline__ float sat_act(float v) { return fminf(fmaxf(v, -65504.0f), 65504.0f); }
-__device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
-    __half2 h = __floats2half2_rn(sat_act(lo), sat_act(hi));
-    return *reinterpret_cast<uint32_t*>(&h);
+__device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {  // saturating: never stores inf
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
 __device__ __forceinline__ uint32_t pack_act2_nosat(float lo, float hi) {
     __half2 h = __floats2half2_rn(lo, hi);

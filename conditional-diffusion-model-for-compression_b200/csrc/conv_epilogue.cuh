@@ -44,17 +44,23 @@ __device__ __forceinline__ float warp_group_reduce(float (&s)[G], int lane) {
     return r;
 }
 
-// taddr: TMEM address of this warp's 32 lanes of the accumulator; bar_tempty: mbarrier (128 arrivals)
-// that hands the accumulator back to the MMA warp; bs: bias of this N tile (shared memory);
-// red: 4*32*2 floats of shared scratch (alternate between consecutive tiles);
-// stats_dst: this tile's first group slot in the partials buffer ([.. 32 groups ..][2]) or unused.
+// Eight epilogue warps share one tile: warp (q, half) owns TMEM lanes 32q..32q+31 (rows) and the
+// column range [half*BN/2, (half+1)*BN/2).  Two warps per SM sub-partition instead of one roughly
+// halves the latency-bound epilogue time (a lone warp ran at IPC ~0.3 in the round-1 profile).
+//
+// taddr: TMEM address of lane quarter q of the accumulator; bar_tempty: mbarrier (256 arrivals, 128 for
+// EPI_DDIM) that hands the accumulator back to the MMA warp; bs: bias of this N tile (shared memory);
+// red: 2*4*16*2 floats of shared scratch (alternate between consecutive tiles);
+// stats_dst: this tile's first group slot in the partials buffer ([.. groups ..][2]) or unused.
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+
 template <int BN, int CPG, int EPI>
 __device__ __forceinline__ void conv_epilogue_tile(const EpiArgs& e, uint32_t taddr, uint32_t bar_tempty,
-                                                   const float* bs, float* red, int q, int lane, bool valid,
-                                                   size_t pix, int n0, float* stats_dst) {
-    constexpr int G = (EPI == EPI_STATS) ? BN / CPG : 1;
-    const int row = q * 32 + lane;
+                                                   const float* bs, float* red, int q, int half, int lane, bool valid,
+                                                   size_t pix, int n0, float* stats_dst, long long* dbg = nullptr) {
     if constexpr (EPI == EPI_DDIM) {
+        if (half != 0) return;
         uint32_t v[16];
         tmem_ld16(taddr, v);
         tmem_ld_wait();
@@ -72,31 +78,43 @@ __device__ __forceinline__ void conv_epilogue_tile(const EpiArgs& e, uint32_t ta
             }
         }
     } else {
-        float gs[G], gq[G];
+        constexpr int HC = BN / 2;                                 // columns per warp
+        constexpr int NCH = HC / 32;                               // 32-column chunks per warp
+        constexpr int GH = (EPI == EPI_STATS) ? HC / CPG : 1;      // groups per warp
+        static_assert(HC % 32 == 0, "BN must be a multiple of 64");
+        float gs[GH], gq[GH];
 #pragma unroll
-        for (int g = 0; g < G; ++g) gs[g] = gq[g] = 0.0f;
-        act_t* orow = e.out + pix * e.ldc + n0;
-        const act_t* rrow = e.residual ? e.residual + pix * e.ldc + n0 : nullptr;
+        for (int g = 0; g < GH; ++g) gs[g] = gq[g] = 0.0f;
+        const int c0 = half * HC;
+        act_t* orow = e.out + pix * e.ldc + n0 + c0;
+        const act_t* rrow = e.residual ? e.residual + pix * e.ldc + n0 + c0 : nullptr;
+        const float msk = valid ? 1.0f : 0.0f;
 #pragma unroll
-        for (int ch = 0; ch < BN / 32; ++ch) {
+        for (int ch = 0; ch < NCH; ++ch) {
             uint32_t v[32];
-            tmem_ld32(taddr + ch * 32, v);
+            tmem_ld32(taddr + c0 + ch * 32, v);
             tmem_ld_wait();
-            if (ch == BN / 32 - 1) {  // accumulator drained: hand the TMEM stage back early
+            if (dbg && ch == 0) dbg[1] = clock64();
+            if (ch == NCH - 1) {  // this warp's share of the accumulator is drained
                 tc_fence_before();
                 mbar_arrive(bar_tempty);
             }
             float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bs[ch * 32 + j];
+            for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bs + c0 + ch * 32 + j4 * 4);
+                f[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + b4.x;
+                f[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + b4.y;
+                f[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + b4.z;
+                f[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + b4.w;
+            }
             if constexpr (EPI == EPI_STATS) {
-                const float msk = valid ? 1.0f : 0.0f;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int g = (ch * 32 + j) / CPG;
                     const float x = f[j] * msk;
                     gs[g] += x;
-                    gq[g] += x * x;
+                    gq[g] = fmaf(x, x, gq[g]);
                 }
             }
             if (valid) {
@@ -123,24 +141,27 @@ __device__ __forceinline__ void conv_epilogue_tile(const EpiArgs& e, uint32_t ta
                 }
             }
         }
+        if (dbg) dbg[2] = clock64();
         if constexpr (EPI == EPI_STATS) {
-            // warp butterfly -> 4 warps through smem -> one fixed-order partial per (tile, group)
-            const float ws = warp_group_reduce<G>(gs, lane);
-            const float wq = warp_group_reduce<G>(gq, lane);
-            constexpr int REP = 32 / G;
+            // warp butterfly -> 8 warps through smem -> one fixed-order partial per (tile, group)
+            const float ws = warp_group_reduce<GH>(gs, lane);
+            const float wq = warp_group_reduce<GH>(gq, lane);
+            constexpr int REP = 32 / GH;
             if ((lane & (REP - 1)) == 0) {
                 const int g = lane / REP;
-                red[(q * 32 + g) * 2 + 0] = ws;
-                red[(q * 32 + g) * 2 + 1] = wq;
+                red[((half * 4 + q) * 16 + g) * 2 + 0] = ws;
+                red[((half * 4 + q) * 16 + g) * 2 + 1] = wq;
             }
-            named_bar_sync(1, 128);
-            if (row < G) {
-                const float s = ((red[(0 * 32 + row) * 2] + red[(1 * 32 + row) * 2]) + red[(2 * 32 + row) * 2]) +
-                                red[(3 * 32 + row) * 2];
-                const float s2 = ((red[(0 * 32 + row) * 2 + 1] + red[(1 * 32 + row) * 2 + 1]) +
-                                  red[(2 * 32 + row) * 2 + 1]) + red[(3 * 32 + row) * 2 + 1];
-                stats_dst[row * 2 + 0] = s;
-                stats_dst[row * 2 + 1] = s2;
+            if (dbg) dbg[3] = clock64();
+            named_bar_sync(1, kEpiThreads);
+            const int t = (half * 4 + q) * 32 + lane;
+            if (t < 2 * GH) {
+                const int hh = t / GH, gl = t % GH;
+                const float* r0 = red + ((hh * 4) * 16 + gl) * 2;
+                const float s = ((r0[0] + r0[32]) + r0[64]) + r0[96];
+                const float s2 = ((r0[1] + r0[33]) + r0[65]) + r0[97];
+                stats_dst[t * 2 + 0] = s;
+                stats_dst[t * 2 + 1] = s2;
             }
         }
     }

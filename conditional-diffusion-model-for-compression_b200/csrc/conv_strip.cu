@@ -15,7 +15,7 @@
 //   Result    : A traffic per output row drops from 9 x 16 KB to 16.3 KB (x chunks).
 //
 //   warp 0 : row producer (TMA)      warp 1 : tcgen05.mma issuer     warp 2 : TMEM allocator
-//   warp 3 : weight producer (TMA)   warps 4-7 : epilogue (shared with conv_tc.cu)
+//   warp 3 : weight producer (TMA)   warps 4-11 : epilogue (shared with conv_tc.cu)
 //
 // Oracle counterpart: oracle/unet.py `conv(k=3)` inside RB / stem / final (the reference ships no code).
 #include <stdio.h>
@@ -32,7 +32,7 @@ constexpr int kStripBar = 512;             // barrier block
 constexpr int kStripAux = kStripBar + 768 * 4 + 2 * 4 * 32 * 2 * 4;
 
 template <int BN, int CPG, int EPI>
-__global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constant__ StripParams p) {
+__global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_strip_kernel(const __grid_constant__ StripParams p) {
     constexpr int WB = BN * 128;  // one (tap, chunk) weight slice
     constexpr int ACC_STRIDE = BN < 32 ? 32 : BN;
     constexpr int TMEM_COLS = (2 * ACC_STRIDE <= 32) ? 32 : (2 * ACC_STRIDE <= 64) ? 64 : (2 * ACC_STRIDE <= 128) ? 128 : 256;
@@ -72,15 +72,15 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
         mbar_init(bar_wres, 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(bar_tfull + 8 * s, 1);
-            mbar_init(bar_tempty + 8 * s, 128);
+            mbar_init(bar_tempty + 8 * s, EPI == EPI_DDIM ? 128 : kEpiThreads);
         }
         fence_mbar_init();
     }
-    if (warp == 2) {
+    if (warp == 2) {  // (warp-collective)
         tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_holder)), TMEM_COLS);
         tmem_relinquish();
     }
-    for (int i = threadIdx.x; i < p.n_total; i += 256) bias_s[i] = p.bias[i];
+    for (int i = threadIdx.x; i < p.n_total; i += 128 + kEpiThreads) bias_s[i] = p.bias[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -95,95 +95,116 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
         h1 = h0 + p.L < p.H ? h0 + p.L : p.H;
     };
 
+    // Producers and issuer run warp-converged; only the async instruction is predicated on lane 0.
+    const uint32_t leader = lane == 0 ? 1u : 0u;
     if (warp == 0) {
-        if (lane == 0) {
-            // -------------------------------------------------------- input-row producer
-            uint32_t e = 0;  // ring entry counter (continues across strips)
-            for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                int b, seg, h0, h1;
-                decode(u, b, seg, h0, h1);
-                for (int h = h0 - 1; h <= h1; ++h, ++e) {
-                    const uint32_t slot = e % NR, fill = e / NR;
-                    mbar_wait(bar_rempty + 8 * slot, (fill & 1) ^ 1);
-                    const uint32_t full = bar_rfull + 8 * slot;
-                    mbar_expect_tx(full, CH * kRowTx);
-                    for (int ch = 0; ch < CH; ++ch) {
-                        const bool s1 = ch >= p.chunks0;
-                        tma_load_4d(ring + (slot * CH + ch) * kRowBytes, s1 ? &p.amap[1] : &p.amap[0], full,
-                                    (s1 ? ch - p.chunks0 : ch) * 64, seg * 128 - 1, h, b);
-                    }
+        // ------------------------------------------------------------ input-row producer
+        uint32_t slot = 0, par = 0;  // ring position / fill parity (continues across strips)
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            int b, seg, h0, h1;
+            decode(u, b, seg, h0, h1);
+            const int w0 = seg * 128 - 1;
+            for (int h = h0 - 1; h <= h1; ++h) {
+                mbar_wait(bar_rempty + 8 * slot, par ^ 1);
+                const uint32_t full = bar_rfull + 8 * slot;
+                mbar_expect_tx_p(full, CH * kRowTx, leader);
+                uint32_t dst = ring + slot * CH * kRowBytes;
+                for (int ch = 0; ch < CH; ++ch, dst += kRowBytes) {
+                    const bool s1 = ch >= p.chunks0;
+                    tma_load_4d_p(dst, s1 ? &p.amap[1] : &p.amap[0], full, (s1 ? ch - p.chunks0 : ch) * 64, w0, h, b, leader);
+                }
+                if (++slot == static_cast<uint32_t>(NR)) {
+                    slot = 0;
+                    par ^= 1;
                 }
             }
         }
     } else if (warp == 3) {
-        if (lane == 0) {
-            // -------------------------------------------------------- weight producer
-            if (resident) {
-                mbar_expect_tx(bar_wres, 9 * CH * WB);
-                for (int i = 0; i < 9 * CH; ++i) tma_load_2d(wbase + i * WB, &p.wmap, bar_wres, i * 64, 0);
-            } else {
-                uint32_t ws = 0, wph = 0;
-                for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                    int b, seg, h0, h1;
-                    decode(u, b, seg, h0, h1);
-                    for (int h = h0; h < h1; ++h)
-                        for (int i = 0; i < 9 * CH; ++i) {  // K order = (tap, chunk), as the weight matrix
-                            mbar_wait(bar_wempty + 8 * ws, wph ^ 1);
-                            mbar_expect_tx(bar_wfull + 8 * ws, WB);
-                            tma_load_2d(wbase + ws * WB, &p.wmap, bar_wfull + 8 * ws, i * 64, 0);
-                            if (++ws == static_cast<uint32_t>(NSW)) {
-                                ws = 0;
-                                wph ^= 1;
-                            }
-                        }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // -------------------------------------------------------- MMA issuer
-            constexpr uint32_t idesc = make_idesc_f16(128, BN);
-            uint32_t e = 0, it = 0, ws = 0, wph = 0;
-            if (resident) {
-                mbar_wait(bar_wres, 0);
-                tc_fence_after();
-            }
+        // ------------------------------------------------------------ weight producer
+        if (resident) {
+            mbar_expect_tx_p(bar_wres, 9 * CH * WB, leader);
+            for (int i = 0; i < 9 * CH; ++i) tma_load_2d_p(wbase + i * WB, &p.wmap, bar_wres, i * 64, 0, leader);
+        } else {
+            uint32_t ws = 0, wph = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
                 int b, seg, h0, h1;
                 decode(u, b, seg, h0, h1);
-                const int rows = h1 - h0;
-                for (int j = 0; j < rows; ++j, ++it) {
-                    const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-                    mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
-                    if (j == 0) {
-                        mbar_wait(bar_rfull + 8 * (e % NR), (e / NR) & 1);
-                        mbar_wait(bar_rfull + 8 * ((e + 1) % NR), ((e + 1) / NR) & 1);
+                for (int h = h0; h < h1; ++h)
+                    for (int i = 0; i < 9 * CH; ++i) {  // K order = (tap, chunk), as the weight matrix
+                        mbar_wait(bar_wempty + 8 * ws, wph ^ 1);
+                        mbar_expect_tx_p(bar_wfull + 8 * ws, WB, leader);
+                        tma_load_2d_p(wbase + ws * WB, &p.wmap, bar_wfull + 8 * ws, i * 64, 0, leader);
+                        if (++ws == static_cast<uint32_t>(NSW)) {
+                            ws = 0;
+                            wph ^= 1;
+                        }
                     }
-                    mbar_wait(bar_rfull + 8 * ((e + j + 2) % NR), ((e + j + 2) / NR) & 1);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
-                    uint32_t first = 0;
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int kh = tap / 3, kw = tap - 3 * kh;
-                        const uint32_t slot = (e + j + kh) % NR;
-                        for (int ch = 0; ch < CH; ++ch) {
-                            uint32_t wb;
-                            if (resident) {
-                                wb = wbase + (tap * CH + ch) * WB;
-                            } else {
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        // The loop is kept free of divisions and 64-bit math: ring slots / parities advance
+        // incrementally and descriptors differ only in their low word.
+        constexpr uint32_t idesc = make_idesc_f16(128, BN);
+        const uint64_t desc_hi = make_sw128_desc(0) & 0xFFFFFFFF00000000ull;
+        const uint32_t slot_stride = static_cast<uint32_t>(CH) * kRowBytes;
+        uint32_t it = 0, ws = 0, wph = 0;
+        uint32_t wslot = 0, wpar = 0;  // next ring entry to wait for
+        uint32_t aslot = 0;            // ring slot of input row (h - 1) of the current output row
+        if (resident) {
+            mbar_wait(bar_wres, 0);
+            tc_fence_after();
+        }
+        auto wait_row = [&]() {
+            mbar_wait(bar_rfull + 8 * wslot, wpar);
+            if (++wslot == static_cast<uint32_t>(NR)) {
+                wslot = 0;
+                wpar ^= 1;
+            }
+        };
+        auto next_slot = [&](uint32_t s_) { return s_ + 1 == static_cast<uint32_t>(NR) ? 0u : s_ + 1; };
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            int b, seg, h0, h1;
+            decode(u, b, seg, h0, h1);
+            const int rows = h1 - h0;
+            wait_row();
+            wait_row();
+            for (int j = 0; j < rows; ++j, ++it) {
+                const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+                const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && it < 64;
+                if (dbg) p.dbg[it * 4 + 0] = clock64();
+                mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
+                if (dbg) p.dbg[it * 4 + 1] = clock64();
+                wait_row();
+                tc_fence_after();
+                if (dbg) p.dbg[it * 4 + 2] = clock64();
+                const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
+                const uint32_t s1 = next_slot(aslot), s2 = next_slot(s1);
+                const uint32_t rowaddr[3] = {ring + aslot * slot_stride, ring + s1 * slot_stride, ring + s2 * slot_stride};
+                uint32_t acc = 0;
+                uint32_t wb = wbase;
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        uint32_t aaddr = rowaddr[kh] + kw * 128;
+                        for (int ch = 0; ch < CH; ++ch, aaddr += kRowBytes) {
+                            if (!resident) {
                                 mbar_wait(bar_wfull + 8 * ws, wph);
                                 tc_fence_after();
                                 wb = wbase + ws * WB;
                             }
-                            const uint64_t adesc = make_sw128_desc(ring + (slot * CH + ch) * kRowBytes + kw * 128);
-                            const uint64_t bdesc = make_sw128_desc(wb);
+                            const uint64_t adesc = desc_hi | static_cast<uint64_t>((aaddr >> 4) & 0x3FFFu);
+                            const uint64_t bdesc = desc_hi | static_cast<uint64_t>((wb >> 4) & 0x3FFFu);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, first);
-                                first = 1;
+                                umma_f16_ss_p(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, acc, leader);
+                                acc = 1;
                             }
-                            if (!resident) {
-                                umma_commit(bar_wempty + 8 * ws);
+                            if (resident) {
+                                wb += WB;
+                            } else {
+                                umma_commit_p(bar_wempty + 8 * ws, leader);
                                 if (++ws == static_cast<uint32_t>(NSW)) {
                                     ws = 0;
                                     wph ^= 1;
@@ -191,19 +212,23 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
                             }
                         }
                     }
-                    umma_commit(bar_rempty + 8 * ((e + j) % NR));  // input row h-1 has served its last output row
-                    if (j == rows - 1) {
-                        umma_commit(bar_rempty + 8 * ((e + j + 1) % NR));
-                        umma_commit(bar_rempty + 8 * ((e + j + 2) % NR));
-                    }
-                    umma_commit(bar_tfull + 8 * as);
                 }
-                e += rows + 2;
+                umma_commit_p(bar_rempty + 8 * aslot, leader);  // input row h-1 has served its last output row
+                if (j == rows - 1) {
+                    umma_commit_p(bar_rempty + 8 * s1, leader);
+                    umma_commit_p(bar_rempty + 8 * s2, leader);
+                    aslot = next_slot(s2);
+                } else {
+                    aslot = s1;
+                }
+                umma_commit_p(bar_tfull + 8 * as, leader);
+                if (dbg) p.dbg[it * 4 + 3] = clock64();
             }
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------ epilogue
         const int q = warp & 3;
+        const int half = (warp - 4) >> 2;
         const int row = q * 32 + lane;
         const EpiArgs ea{p.out, p.residual, p.ldc, p.x, p.xpad, p.x0_out, p.c0, p.c1};
         uint32_t it = 0;
@@ -215,14 +240,23 @@ __global__ void __launch_bounds__(256, 1) conv_strip_kernel(const __grid_constan
             for (int h = h0; h < h1; ++h, ++it) {
                 const uint32_t as = it & 1, aphase = (it >> 1) & 1;
                 const size_t pix = (static_cast<size_t>(b) * p.H + h) * p.W + gx;
+                long long* edbg = (p.dbg != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0 && it < 32) ? p.dbg + 256 + it * 8 : nullptr;
+                if (edbg) edbg[4] = clock64();
                 mbar_wait(bar_tfull + 8 * as, aphase);
                 tc_fence_after();
+                if (edbg) edbg[0] = clock64();
+                if (p.dbg != nullptr && p.dbg[511] == 1) {  // tools only: measure the MMA phase without epilogue work
+                    tc_fence_before();
+                    mbar_arrive(bar_tempty + 8 * as);
+                    continue;
+                }
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * ACC_STRIDE;
                 float* sdst = (EPI == EPI_STATS)
                                   ? p.stats + ((static_cast<size_t>(b) * p.H * p.nseg + static_cast<size_t>(h) * p.nseg + seg) * 32) * 2
                                   : nullptr;
-                conv_epilogue_tile<BN, CPG, EPI>(ea, taddr, bar_tempty + 8 * as, bias_s, red_s + (it & 1) * (4 * 32 * 2),
-                                                 q, lane, valid, pix, 0, sdst);
+                conv_epilogue_tile<BN, CPG, EPI>(ea, taddr, bar_tempty + 8 * as, bias_s, red_s + (it & 1) * (2 * 4 * 16 * 2),
+                                                 q, half, lane, valid, pix, 0, sdst, edbg);
+                if (edbg) edbg[5] = clock64();
             }
         }
     }
@@ -287,7 +321,7 @@ cudaError_t launch_conv_strip(const StripParams& p, int bn, int cpg, int epi, in
     const int smem = strip_smem_bytes(bn, p.CH, p.NR, p.NSW);
 #define STRIP_CASE(BN_, CPG_, EPI_)                                        \
     if (bn == BN_ && cpg == CPG_ && epi == EPI_) {                         \
-        conv_strip_kernel<BN_, CPG_, EPI_><<<grid, 256, smem, stream>>>(p); \
+        conv_strip_kernel<BN_, CPG_, EPI_><<<grid, 128 + kEpiThreads, smem, stream>>>(p); \
         return cudaGetLastError();                                         \
     }
     STRIP_ALL_CASES()

@@ -24,6 +24,7 @@ struct alignas(64) StripParams {
     act_t* xpad;
     float* x0_out;
     float c0, c1;
+    long long* dbg;       // optional: issuer timeline of CTA 0 (clock64 stamps), tools only
 };
 
 bool strip_inst_ok(int bn, int cpg, int epi);

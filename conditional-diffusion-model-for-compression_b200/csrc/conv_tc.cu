@@ -10,7 +10,7 @@
 //   warp 0 : TMA producer (one elected lane)        smem ring: full[] / empty[] mbarriers
 //   warp 1 : tcgen05.mma issuer (one elected lane)  TMEM ring: tfull[] / tempty[] (2 accumulators)
 //   warp 2 : TMEM allocator
-//   warps 4-7 : epilogue (tcgen05.ld -> +bias -> GroupNorm partials / residual / DDIM -> global)
+//   warps 4-11 : epilogue (tcgen05.ld -> +bias -> GroupNorm partials / residual / DDIM -> global)
 //
 // Oracle counterpart: oracle/unet.py `conv`, `Up`, `RB` (the reference ships no code).
 #include <stdio.h>
@@ -40,10 +40,13 @@ struct ConvCfg {
     static constexpr int SMEM_BYTES = 1024 + NS * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + RED_BYTES;
 };
 
+constexpr int kConvThreads = 128 + kEpiThreads;  // 4 control warps + 8 epilogue warps
+
 template <int BN, int CPG, int EPI>
-__global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
     using Cfg = ConvCfg<BN>;
     constexpr int NS = Cfg::NS;
+
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
     const uint32_t base = (raw_u32 + 1023u) & ~1023u;  // 128B-swizzle atoms need 1024 B alignment
@@ -70,7 +73,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(bar_tfull + 8 * s, 1);
-            mbar_init(bar_tempty + 8 * s, 128);
+            mbar_init(bar_tempty + 8 * s, EPI == EPI_DDIM ? 128 : kEpiThreads);
         }
         fence_mbar_init();
     }
@@ -78,7 +81,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
         tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_holder)), Cfg::TMEM_COLS);
         tmem_relinquish();
     }
-    for (int i = threadIdx.x; i < p.n_total; i += 256) bias_s[i] = p.bias[i];
+    for (int i = threadIdx.x; i < p.n_total; i += kConvThreads) bias_s[i] = p.bias[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -95,61 +98,61 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
         b = m / p.nphase;
     };
 
+    // Producer and issuer run warp-converged; only the async instruction is predicated on lane 0.
+    const uint32_t leader = lane == 0 ? 1u : 0u;
     if (warp == 0) {
-        if (lane == 0) {
-            // ------------------------------------------------------------ TMA producer
-            uint32_t stage = 0, phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                int nt, ph, b, th, tw;
-                decode(tile, nt, ph, b, th, tw);
-                const KBlock* tab = p.kb + ph * p.nkb;
-                const int w0 = tw * BW, h0 = th * BH;
-                for (int i = 0; i < p.nkb; ++i) {
-                    const KBlock e = tab[i];
-                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
-                    const uint32_t full = bar_full + 8 * stage;
-                    mbar_expect_tx(full, Cfg::STAGE_BYTES);
-                    tma_load_4d(sa, &p.amap[e.map], full, e.c0, w0 + e.dw, h0 + e.dh, b);
-                    tma_load_2d(sa + Cfg::A_BYTES, &p.wmap, full, e.wk, nt * BN);
-                    if (++stage == NS) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+        // ---------------------------------------------------------------- TMA producer
+        uint32_t stage = 0, phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int nt, ph, b, th, tw;
+            decode(tile, nt, ph, b, th, tw);
+            const KBlock* tab = p.kb + ph * p.nkb;
+            const int w0 = tw * BW, h0 = th * BH;
+            for (int i = 0; i < p.nkb; ++i) {
+                const KBlock e = tab[i];
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
+                const uint32_t full = bar_full + 8 * stage;
+                mbar_expect_tx_p(full, Cfg::STAGE_BYTES, leader);
+                tma_load_4d_p(sa, &p.amap[e.map], full, e.c0, w0 + e.dw, h0 + e.dh, b, leader);
+                tma_load_2d_p(sa + Cfg::A_BYTES, &p.wmap, full, e.wk, nt * BN, leader);
+                if (++stage == NS) {
+                    stage = 0;
+                    phase ^= 1;
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ------------------------------------------------------------ MMA issuer
-            constexpr uint32_t idesc = make_idesc_f16(128, BN);
-            uint32_t stage = 0, phase = 0, it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-                const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-                mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
+        // ---------------------------------------------------------------- MMA issuer
+        constexpr uint32_t idesc = make_idesc_f16(128, BN);
+        const uint64_t desc_hi = make_sw128_desc(0) & 0xFFFFFFFF00000000ull;
+        uint32_t stage = 0, phase = 0, it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+            mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
+            for (int i = 0; i < p.nkb; ++i) {
+                mbar_wait(bar_full + 8 * stage, phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
-                for (int i = 0; i < p.nkb; ++i) {
-                    mbar_wait(bar_full + 8 * stage, phase);
-                    tc_fence_after();
-                    const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
-                    const uint64_t adesc = make_sw128_desc(sa);
-                    const uint64_t bdesc = make_sw128_desc(sa + Cfg::A_BYTES);
+                const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
+                const uint64_t adesc = desc_hi | static_cast<uint64_t>((sa >> 4) & 0x3FFFu);
+                const uint64_t bdesc = desc_hi | static_cast<uint64_t>(((sa + Cfg::A_BYTES) >> 4) & 0x3FFFu);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)  // 4 x (K = 16): +32 B inside the 128 B swizzle row
-                        umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0);
-                    umma_commit(bar_empty + 8 * stage);  // frees the smem slot once these MMAs retire
-                    if (++stage == NS) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+                for (int k = 0; k < 4; ++k)  // 4 x (K = 16): +32 B inside the 128 B swizzle row
+                    umma_f16_ss_p(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0, leader);
+                umma_commit_p(bar_empty + 8 * stage, leader);  // frees the smem slot once these MMAs retire
+                if (++stage == NS) {
+                    stage = 0;
+                    phase ^= 1;
                 }
-                umma_commit(bar_tfull + 8 * as);  // accumulator complete -> epilogue
             }
+            umma_commit_p(bar_tfull + 8 * as, leader);  // accumulator complete -> epilogue
         }
     } else if (warp >= 4) {
-        // ---------------------------------------------------------------- epilogue
-        const int q = warp & 3;  // TMEM sub-partition: lanes 32q .. 32q+31
+        // ---------------------------------------------------------------- epilogue (8 warps)
+        const int q = warp & 3;            // TMEM sub-partition: lanes 32q .. 32q+31
+        const int half = (warp - 4) >> 2;  // column half of the accumulator
         const int row = q * 32 + lane;
         const int ty = row >> BWl, tx = row & (BW - 1);
         const EpiArgs ea{p.out, p.residual, p.ldc, p.x, p.xpad, p.x0_out, p.c0, p.c1};
@@ -166,14 +169,13 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
             mbar_wait(bar_tfull + 8 * as, aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE;
-
             const int PT = p.nphase * p.tiles_h * p.tiles_w;
             const int pt = (ph * p.tiles_h + th) * p.tiles_w + tw;
             float* sdst = (EPI == EPI_STATS)
                               ? p.stats + ((static_cast<size_t>(b) * PT + pt) * 32 + nt * (BN / CPG)) * 2
                               : nullptr;
             conv_epilogue_tile<BN, CPG, EPI>(ea, taddr, bar_tempty + 8 * as, bias_s + nt * BN,
-                                             red_s + (it & 1) * (4 * 32 * 2), q, lane, valid, pix, nt * BN, sdst);
+                                             red_s + (it & 1) * (2 * 4 * 16 * 2), q, half, lane, valid, pix, nt * BN, sdst);
         }
     }
 
@@ -194,7 +196,7 @@ static cudaError_t launch_one(const ConvParams& p, int num_sms, cudaStream_t str
     auto kern = conv_tc_kernel<BN, CPG, EPI>;
     const int total = p.n_tiles * p.nphase * p.batch * p.tiles_h * p.tiles_w;
     const int grid = total < num_sms ? total : num_sms;
-    kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(p);
+    kern<<<grid, kConvThreads, Cfg::SMEM_BYTES, stream>>>(p);
     return cudaGetLastError();
 }
 

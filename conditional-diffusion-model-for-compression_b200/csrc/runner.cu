@@ -9,6 +9,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <functional>
@@ -103,6 +104,7 @@ struct ConvBuild {
     float* x0_out = nullptr;
     const std::vector<float>* c0 = nullptr;  // per-step sampler coefficients (host)
     const std::vector<float>* c1 = nullptr;
+    long long* dbg = nullptr;  // strip kernel issuer timeline (tools)
 };
 
 static int encode_act_map(CUtensorMap* m, const act_t* base, int C, int Wd, int Hd, int B, size_t sW, size_t sH,
@@ -230,6 +232,7 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
             sp->x = cb.x;
             sp->xpad = cb.xpad;
             sp->x0_out = cb.x0_out;
+            sp->dbg = cb.dbg;
             const double Ms = static_cast<double>(B) * gh * gw;
             op->name = cb.name;
             op->flops = 2.0 * Ms * w.n_true * (9.0 * w.c_true);
@@ -1286,6 +1289,13 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
         cb.stats = stats;
         if (pt_out) *pt_out = conv_num_partials(cb);
     }
+    long long* dbg = nullptr;
+    if (getenv("CDC_STRIP_DEBUG")) {
+        cudaMallocManaged(&dbg, 512 * sizeof(long long));
+        memset(dbg, 0, 512 * sizeof(long long));
+        if (atoi(getenv("CDC_STRIP_DEBUG")) == 2) dbg[511] = 1;
+        cb.dbg = dbg;
+    }
     Op op;
     std::string e;
     r = build_conv(cb, B, prop.multiProcessorCount, &op, &e);
@@ -1296,6 +1306,19 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
     }
     cudaError_t ce = op.run(S(s), 0);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(S(s));
+    if (dbg) {
+        printf("strip issuer timeline (CTA 0): row: wait_tempty wait_row mma+commit | since previous row start\n");
+        for (int i = 0; i < 24 && dbg[i * 4 + 3]; ++i)
+            printf("  %2d: %6lld %6lld %6lld | %6lld\n", i, dbg[i * 4 + 1] - dbg[i * 4 + 0], dbg[i * 4 + 2] - dbg[i * 4 + 1],
+                   dbg[i * 4 + 3] - dbg[i * 4 + 2], i ? dbg[i * 4 + 0] - dbg[(i - 1) * 4 + 0] : 0LL);
+        printf("epilogue warp 4 timeline: tile: wait_tfull | ldtm math+store butterfly bar+final | total\n");
+        for (int i = 2; i < 20; ++i) {
+            const long long* e = dbg + 256 + i * 8;
+            printf("  %2d: %6lld | %6lld %6lld %6lld %6lld | %6lld\n", i, e[0] - e[4], e[1] - e[0], e[2] - e[1], e[3] - e[2],
+                   e[5] - e[3], e[5] - e[4]);
+        }
+        cudaFree(dbg);
+    }
     ar.release();
     if (ce != cudaSuccess) {
         g_create_err = std::string("test_conv: ") + cudaGetErrorString(ce);
