@@ -31,7 +31,9 @@ constexpr int kRowTx = 130 * 128;          // bytes one row box delivers
 constexpr int kStripBar = 512;             // barrier block
 constexpr int kStripAux = kStripBar + 768 * 4 + 2 * 4 * 32 * 2 * 4;
 
-template <int BN, int CPG, int EPI>
+// CH (64-channel chunks of C_in) and RES (weights resident in shared memory) are compile-time so that the
+// issuer's 36*CH tcgen05.mma per output row are straight-line code with immediate descriptor offsets.
+template <int BN, int CPG, int EPI, int CH, bool RES>
 __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_strip_kernel(const __grid_constant__ StripParams p) {
     constexpr int WB = BN * 128;  // one (tap, chunk) weight slice
     constexpr int ACC_STRIDE = BN < 32 ? 32 : BN;
@@ -41,8 +43,8 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_strip_kernel(const 
     const uint32_t raw_u32 = smem_u32(smem_raw);
     const uint32_t base = (raw_u32 + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (base - raw_u32);
-    const int CH = p.CH, NR = p.NR, NSW = p.NSW;
-    const bool resident = NSW == 0;
+    const int NR = p.NR, NSW = p.NSW;
+    constexpr bool resident = RES;
     const uint32_t ring = base;
     const uint32_t wbase = ring + NR * CH * kRowBytes;
     const uint32_t wbytes = resident ? 9 * CH * WB : NSW * WB;
@@ -181,47 +183,49 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_strip_kernel(const 
                 const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
                 const uint32_t s1 = next_slot(aslot), s2 = next_slot(s1);
                 const uint32_t rowaddr[3] = {ring + aslot * slot_stride, ring + s1 * slot_stride, ring + s2 * slot_stride};
-                uint32_t acc = 0;
-                uint32_t wb = wbase;
+                // Elected-lane region with 32-bit descriptor low words and compile-time accumulate flags:
+                // 64 cycles per MMA (the M=128 operand-fetch floor) instead of 115 for a predicated-asm
+                // formulation of the same loop (tools/exp_mma_rate.cu, modes 4 / 5).
+                if (leader) {
+                    uint32_t wb = wbase;
 #pragma unroll
-                for (int kh = 0; kh < 3; ++kh) {
+                    for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-                    for (int kw = 0; kw < 3; ++kw) {
-                        uint32_t aaddr = rowaddr[kh] + kw * 128;
-                        for (int ch = 0; ch < CH; ++ch, aaddr += kRowBytes) {
-                            if (!resident) {
-                                mbar_wait(bar_wfull + 8 * ws, wph);
-                                tc_fence_after();
-                                wb = wbase + ws * WB;
-                            }
-                            const uint64_t adesc = desc_hi | static_cast<uint64_t>((aaddr >> 4) & 0x3FFFu);
-                            const uint64_t bdesc = desc_hi | static_cast<uint64_t>((wb >> 4) & 0x3FFFu);
+                        for (int kw = 0; kw < 3; ++kw) {
+                            uint32_t aaddr = rowaddr[kh] + kw * 128;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                umma_f16_ss_p(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, acc, leader);
-                                acc = 1;
-                            }
-                            if (resident) {
-                                wb += WB;
-                            } else {
-                                umma_commit_p(bar_wempty + 8 * ws, leader);
-                                if (++ws == static_cast<uint32_t>(NSW)) {
-                                    ws = 0;
-                                    wph ^= 1;
+                            for (int ch = 0; ch < CH; ++ch, aaddr += kRowBytes) {
+                                if (!resident) {
+                                    mbar_wait(bar_wfull + 8 * ws, wph);
+                                    tc_fence_after();
+                                    wb = wbase + ws * WB;
+                                }
+                                const uint32_t alo = (aaddr >> 4) & 0x3FFFu, blo = (wb >> 4) & 0x3FFFu;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    umma_f16_ss(d_tmem, desc_hi | (alo + 2 * k), desc_hi | (blo + 2 * k), idesc,
+                                                (kh | kw | k | ch) != 0 ? 1u : 0u);
+                                if (resident) {
+                                    wb += WB;
+                                } else {
+                                    umma_commit(bar_wempty + 8 * ws);
+                                    if (++ws == static_cast<uint32_t>(NSW)) {
+                                        ws = 0;
+                                        wph ^= 1;
+                                    }
                                 }
                             }
                         }
                     }
+                    umma_commit(bar_rempty + 8 * aslot);  // input row h-1 has served its last output row
+                    if (j == rows - 1) {
+                        umma_commit(bar_rempty + 8 * s1);
+                        umma_commit(bar_rempty + 8 * s2);
+                    }
+                    umma_commit(bar_tfull + 8 * as);
                 }
-                umma_commit_p(bar_rempty + 8 * aslot, leader);  // input row h-1 has served its last output row
-                if (j == rows - 1) {
-                    umma_commit_p(bar_rempty + 8 * s1, leader);
-                    umma_commit_p(bar_rempty + 8 * s2, leader);
-                    aslot = next_slot(s2);
-                } else {
-                    aslot = s1;
-                }
-                umma_commit_p(bar_tfull + 8 * as, leader);
+                __syncwarp();
+                aslot = (j == rows - 1) ? next_slot(s2) : s1;
                 if (dbg) p.dbg[it * 4 + 3] = clock64();
             }
         }
@@ -267,6 +271,18 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_strip_kernel(const 
 }
 
 // ------------------------------------------------------------------------------------------------ host
+// (BN, CPG, EPI, CH, RESIDENT) instantiations: exactly the layer shapes of the UNet / context net that
+// the strip variant serves; anything else goes through conv_tc.cu.
+#define STRIP_ALL_CASES()                  \
+    STRIP_CASE(64, 2, EPI_STATS, 1, true)   \
+    STRIP_CASE(64, 2, EPI_STATS, 2, false)  \
+    STRIP_CASE(64, 1, EPI_STORE, 1, true)   \
+    STRIP_CASE(64, 1, EPI_STORE, 2, false)  \
+    STRIP_CASE(128, 4, EPI_STATS, 1, true)  \
+    STRIP_CASE(128, 4, EPI_STATS, 2, false) \
+    STRIP_CASE(128, 1, EPI_STORE, 2, false) \
+    STRIP_CASE(16, 1, EPI_DDIM, 1, true)
+
 int strip_smem_bytes(int bn, int CH, int NR, int NSW) {
     const int wb = bn * 128;
     return 1024 + NR * CH * kRowBytes + (NSW == 0 ? 9 * CH * wb : NSW * wb) + kStripAux;
@@ -290,24 +306,19 @@ bool strip_plan(int bn, int CH, int* NR, int* NSW) {
     return false;
 }
 
-bool strip_inst_ok(int bn, int cpg, int epi) {
-    if (epi == EPI_STORE) return bn == 64 || bn == 128;
-    if (epi == EPI_STATS) return (bn == 64 && cpg == 2) || (bn == 128 && cpg == 4);
-    return epi == EPI_DDIM && bn == 16;
+bool strip_inst_ok(int bn, int cpg, int epi, int CH, bool resident) {
+#define STRIP_CASE(BN_, CPG_, EPI_, CH_, RES_) \
+    if (bn == BN_ && (EPI_ != EPI_STATS || cpg == CPG_) && epi == EPI_ && CH == CH_ && resident == RES_) return true;
+    STRIP_ALL_CASES()
+#undef STRIP_CASE
+    return false;
 }
-
-#define STRIP_ALL_CASES()        \
-    STRIP_CASE(64, 1, EPI_STORE)  \
-    STRIP_CASE(128, 1, EPI_STORE) \
-    STRIP_CASE(64, 2, EPI_STATS)  \
-    STRIP_CASE(128, 4, EPI_STATS) \
-    STRIP_CASE(16, 1, EPI_DDIM)
 
 cudaError_t configure_strip_kernels() {
     cudaError_t e;
-#define STRIP_CASE(BN_, CPG_, EPI_)                                                                         \
-    if ((e = cudaFuncSetAttribute(conv_strip_kernel<BN_, CPG_, EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  227 * 1024)) != cudaSuccess)                                             \
+#define STRIP_CASE(BN_, CPG_, EPI_, CH_, RES_)                                                                   \
+    if ((e = cudaFuncSetAttribute(conv_strip_kernel<BN_, CPG_, EPI_, CH_, RES_>,                                   \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess)      \
         return e;
     STRIP_ALL_CASES()
 #undef STRIP_CASE
@@ -315,14 +326,14 @@ cudaError_t configure_strip_kernels() {
 }
 
 cudaError_t launch_conv_strip(const StripParams& p, int bn, int cpg, int epi, int num_sms, cudaStream_t stream) {
-    if (epi != EPI_STATS) cpg = 1;
     const int units = p.batch * p.nseg * p.strips_per_col;
     const int grid = units < num_sms ? units : num_sms;
     const int smem = strip_smem_bytes(bn, p.CH, p.NR, p.NSW);
-#define STRIP_CASE(BN_, CPG_, EPI_)                                        \
-    if (bn == BN_ && cpg == CPG_ && epi == EPI_) {                         \
-        conv_strip_kernel<BN_, CPG_, EPI_><<<grid, 128 + kEpiThreads, smem, stream>>>(p); \
-        return cudaGetLastError();                                         \
+    const bool resident = p.NSW == 0;
+#define STRIP_CASE(BN_, CPG_, EPI_, CH_, RES_)                                                                \
+    if (bn == BN_ && (EPI_ != EPI_STATS || cpg == CPG_) && epi == EPI_ && p.CH == CH_ && resident == RES_) {  \
+        conv_strip_kernel<BN_, CPG_, EPI_, CH_, RES_><<<grid, 128 + kEpiThreads, smem, stream>>>(p);          \
+        return cudaGetLastError();                                                                           \
     }
     STRIP_ALL_CASES()
 #undef STRIP_CASE

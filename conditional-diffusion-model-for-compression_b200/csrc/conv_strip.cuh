@@ -27,7 +27,7 @@ struct alignas(64) StripParams {
     long long* dbg;       // optional: issuer timeline of CTA 0 (clock64 stamps), tools only
 };
 
-bool strip_inst_ok(int bn, int cpg, int epi);
+bool strip_inst_ok(int bn, int cpg, int epi, int CH, bool resident);
 bool strip_plan(int bn, int CH, int* NR, int* NSW);  // shared-memory plan; false if it does not fit
 int strip_smem_bytes(int bn, int CH, int NR, int NSW);
 cudaError_t configure_strip_kernels();

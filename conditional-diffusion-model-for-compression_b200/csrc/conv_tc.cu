@@ -136,18 +136,22 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
                 mbar_wait(bar_full + 8 * stage, phase);
                 tc_fence_after();
                 const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
-                const uint64_t adesc = desc_hi | static_cast<uint64_t>((sa >> 4) & 0x3FFFu);
-                const uint64_t bdesc = desc_hi | static_cast<uint64_t>(((sa + Cfg::A_BYTES) >> 4) & 0x3FFFu);
+                const uint32_t alo = (sa >> 4) & 0x3FFFu, blo = ((sa + Cfg::A_BYTES) >> 4) & 0x3FFFu;
+                if (leader) {  // elected-lane region, 32-bit descriptor math (see conv_strip.cu)
+                    umma_f16_ss(d_tmem, desc_hi | alo, desc_hi | blo, idesc, i != 0 ? 1u : 0u);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)  // 4 x (K = 16): +32 B inside the 128 B swizzle row
-                    umma_f16_ss_p(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0, leader);
-                umma_commit_p(bar_empty + 8 * stage, leader);  // frees the smem slot once these MMAs retire
+                    for (int k = 1; k < 4; ++k)  // 4 x (K = 16): +32 B inside the 128 B swizzle row
+                        umma_f16_ss(d_tmem, desc_hi | (alo + 2 * k), desc_hi | (blo + 2 * k), idesc, 1u);
+                    umma_commit(bar_empty + 8 * stage);  // frees the smem slot once these MMAs retire
+                }
+                __syncwarp();
                 if (++stage == NS) {
                     stage = 0;
                     phase ^= 1;
                 }
             }
-            umma_commit_p(bar_tfull + 8 * as, leader);  // accumulator complete -> epilogue
+            if (leader) umma_commit(bar_tfull + 8 * as);  // accumulator complete -> epilogue
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ---------------------------------------------------------------- epilogue (8 warps)

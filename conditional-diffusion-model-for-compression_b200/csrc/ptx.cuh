@@ -35,6 +35,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes (or the
+// hint expires) instead of letting it spin.  Spinning waiters share the SM sub-partition's issue slots
+// with the single-thread MMA issue stream; the round-1 timeline showed 115 instead of 64 cycles per
+// tcgen05.mma with default (short) try_wait polling.
+__device__ __forceinline__ bool mbar_try_wait_suspend(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(hint_ns)
+        : "memory");
+    return ok != 0;
+}
 // Bounded wait: a protocol bug must trap (sticky launch failure), never hang the GPU box.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;

@@ -199,8 +199,8 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
         const int CH = ctot / 64;
         int NR = 0, NSW = 0;
         const bool wide = gw >= 128 && (gw % 128 == 0 || gw >= 512);
-        if (cb.mode == MODE_S1 && cb.ksize == 3 && cb.force_bn == 0 && wide && strip_inst_ok(bn_s, cb.cpg, cb.epi) &&
-            strip_plan(bn_s, CH, &NR, &NSW)) {
+        if (cb.mode == MODE_S1 && cb.ksize == 3 && cb.force_bn == 0 && wide && strip_plan(bn_s, CH, &NR, &NSW) &&
+            strip_inst_ok(bn_s, cb.cpg, cb.epi, CH, NSW == 0)) {
             auto sp = std::shared_ptr<StripParams>(new StripParams());
             memset(sp.get(), 0, sizeof(StripParams));
             for (size_t s = 0; s < cb.srcs.size(); ++s) {
@@ -385,8 +385,8 @@ static bool conv_uses_strip(const ConvBuild& cb) {
     const int bn_s = cb.epi == EPI_DDIM ? 16 : cb.w->n_pad;
     int NR, NSW;
     const bool wide = gw >= 128 && (gw % 128 == 0 || gw >= 512);
-    return cb.mode == MODE_S1 && cb.ksize == 3 && cb.force_bn == 0 && wide && strip_inst_ok(bn_s, cb.cpg, cb.epi) &&
-           strip_plan(bn_s, ctot / 64, &NR, &NSW);
+    return cb.mode == MODE_S1 && cb.ksize == 3 && cb.force_bn == 0 && wide && strip_plan(bn_s, ctot / 64, &NR, &NSW) &&
+           strip_inst_ok(bn_s, cb.cpg, cb.epi, ctot / 64, NSW == 0);
 }
 
 static int conv_num_partials(const ConvBuild& cb) {
@@ -1311,6 +1311,9 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
         for (int i = 0; i < 24 && dbg[i * 4 + 3]; ++i)
             printf("  %2d: %6lld %6lld %6lld | %6lld\n", i, dbg[i * 4 + 1] - dbg[i * 4 + 0], dbg[i * 4 + 2] - dbg[i * 4 + 1],
                    dbg[i * 4 + 3] - dbg[i * 4 + 2], i ? dbg[i * 4 + 0] - dbg[(i - 1) * 4 + 0] : 0LL);
+        printf("row 10 per-tap issue cycles:");
+        for (int i = 0; i < 9; ++i) printf(" %lld", dbg[384 + i + 1] - dbg[384 + i]);
+        printf("\n");
         printf("epilogue warp 4 timeline: tile: wait_tfull | ldtm math+store butterfly bar+final | total\n");
         for (int i = 2; i < 20; ++i) {
             const long long* e = dbg + 256 + i * 8;

@@ -1,6 +1,6 @@
 """Print the strip kernel's issuer timeline for one level-0-shaped conv (CDC_STRIP_DEBUG=1)."""
 import ctypes as C, os, sys
-os.environ["CDC_STRIP_DEBUG"] = "1"
+os.environ.setdefault("CDC_STRIP_DEBUG", "1")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from cdc_b200 import _ffi
