@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 
 H, W, K_DDIM = 512, 768, 17
 METRIC = "decoded images/sec (768x512, 17-step DDIM)"
-WORKLOAD = "configs[1]: full decode of one 768x512 synthetic image, 17-step DDIM, bf16, batch 1 per GPU, CUDA-graphed step loop"
+WORKLOAD = "configs[1]: full decode of one 768x512 synthetic image, 17-step DDIM, 16-bit operands / fp32 accumulate, batch 1 per GPU, CUDA-graphed step loop"
 
 
 def peaks():
@@ -114,19 +114,19 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals = []
-    for i in range(args.warmup + args.steps):
-        if i == 1 and args.warmup > 1:
-            continue_fast = True  # noqa: F841  (every sample is independent; warm-ups only page in the weights)
+    # a CPU sample needs no more than one warm-up (it only pages in weights and the thread pool);
+    # keeps `--steps K --warmup W` within minutes whatever W the driver passes
+    warm = min(args.warmup, 1)
+    vals, t_begin = [], time.perf_counter()
+    for i in range(warm + args.steps):
         v, cores, t_ctx, t_step = cpu_oracle_sample(n_steps=1)
-        if i >= args.warmup:
+        if i >= warm:
             vals.append(v)
-        if i == 0 and args.warmup > 1:
-            # one warm-up sample is enough for a CPU path; keep the run within minutes
-            skip = args.warmup - 1
-            args.warmup -= skip
+        if time.perf_counter() - t_begin > 240 and vals:  # hard bound on the CPU arm's wall time
+            break
     v = statistics.mean(vals)
-    sample = f"1 context-net pass + 1 of {K_DDIM} DDIM steps of one 768x512 decode per bench step, extrapolated to a full decode"
+    sample = (f"1 context-net pass + 1 of {K_DDIM} DDIM steps of one 768x512 decode per bench step, extrapolated to a full "
+              f"decode; {len(vals)} of {args.steps} steps sampled")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "weak",
@@ -160,13 +160,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
 
+    # the product arm never touches oracle/: weights and inputs come from the package's own generators
     from cdc_b200 import CDCConfig, Decoder
-    from oracle.config import CDCConfig as OCfg
-    from oracle.weights import build_codec, build_unet, synthetic_init, synthetic_latent
-    ocfg = OCfg()
-    weights = dict(build_unet(ocfg).state_dict())
-    weights.update({"context." + k: v for k, v in build_codec(ocfg).context.state_dict().items()})
-    dec = Decoder(CDCConfig(), weights, device=dev)
+    from cdc_b200.synthetic import init_noise as synthetic_init, latent as synthetic_latent, random_weights
+    dec = Decoder(CDCConfig(), random_weights(CDCConfig(), seed=0, with_context=True), device=dev)
     dec.set_sample_schedule(K_DDIM)
     n_img = args.warmup + args.steps
     lat_h = [synthetic_latent(1, H, W, index=rank * 1000 + i).pin_memory() for i in range(n_img)]
@@ -224,10 +221,12 @@ def main():
     out = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "vs_baseline": None, "dtype": "fp16" if dec.L.cdc_act_dtype() == 1 else "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "image": [H, W], "ddim_steps": K_DDIM, "batch_per_gpu": 1,
                    "parallelism": f"image-sharded dp{world}, no data-path collective",
-                   "l2": "flushed between timed iterations (256 MiB write, outside the event brackets)"},
+                   "l2": "flushed between timed iterations (256 MiB write, outside the event brackets)",
+                   "precision": "fp16 storage + tcgen05 kind::f16 operands, fp32 accumulate/statistics/sampler state "
+                                "(bf16 operands miss the 1e-2 per-step tolerance: DESIGN.md section 5)"},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(lat_h[0].numel() * 4 + x_h[0].numel() * 4),
                 "d2h_bytes_per_step": int(x_h[0].numel() * 4)},

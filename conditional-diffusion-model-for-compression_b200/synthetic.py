@@ -1,0 +1,76 @@
+"""Random-init weights and synthetic inputs of the right architecture for benchmarking and smoke runs
+(there are no trained checkpoints: the reference ships none and there is no network).  Names and shapes
+follow the state dict the C ABI expects (include/cdc_b200.h, cdc_load_weights); values are
+PyTorch-default-like (uniform +-1/sqrt(fan_in)) and rounded to bf16-representable fp32."""
+import math
+
+import torch
+
+from .config import CDCConfig
+
+
+def _u(g, shape, fan_in):
+    b = 1.0 / math.sqrt(fan_in)
+    return ((torch.rand(shape, generator=g) * 2 - 1) * b).bfloat16().float()
+
+
+def _conv(d, g, name, cout, cin, k):
+    d[name + ".weight"] = _u(g, (cout, cin, k, k), cin * k * k)
+    d[name + ".bias"] = _u(g, (cout,), cin * k * k)
+
+
+def _rb(d, g, name, cin, cout, temb):
+    _conv(d, g, name + ".conv1", cout, cin, 3)
+    _conv(d, g, name + ".conv2", cout, cout, 3)
+    for gn in (".gn1", ".gn2"):
+        d[name + gn + ".weight"] = (1.0 + 0.1 * torch.randn(cout, generator=g)).bfloat16().float()
+        d[name + gn + ".bias"] = (0.1 * torch.randn(cout, generator=g)).bfloat16().float()
+    if temb:
+        d[name + ".film.weight"] = _u(g, (2 * cout, temb), temb)
+        d[name + ".film.bias"] = _u(g, (2 * cout,), temb)
+    if cin != cout:
+        _conv(d, g, name + ".res", cout, cin, 1)
+
+
+def random_weights(cfg: CDCConfig = CDCConfig(), seed: int = 0, with_context: bool = True):
+    g = torch.Generator().manual_seed(seed)
+    C, te, d = cfg.channels, cfg.temb, {}
+    d["temb.lin1.weight"], d["temb.lin1.bias"] = _u(g, (te, 64), 64), _u(g, (te,), 64)
+    d["temb.lin2.weight"], d["temb.lin2.bias"] = _u(g, (te, te), te), _u(g, (te,), te)
+    _conv(d, g, "stem", C[0], 3 + C[0], 3)
+    for i, c in enumerate(C):
+        cin = C[0] if i == 0 else C[i - 1] + C[i]
+        _rb(d, g, f"down.{i}.rb1", cin, c, te)
+        _rb(d, g, f"down.{i}.rb2", c, c, te)
+        _conv(d, g, f"down.{i}.down", c, c, 3)
+    _rb(d, g, "mid.rb1", C[-1], C[-1], te)
+    d["mid.attn.gn.weight"] = (1.0 + 0.1 * torch.randn(C[-1], generator=g)).bfloat16().float()
+    d["mid.attn.gn.bias"] = (0.1 * torch.randn(C[-1], generator=g)).bfloat16().float()
+    _conv(d, g, "mid.attn.qkv", 3 * C[-1], C[-1], 1)
+    _conv(d, g, "mid.attn.proj", C[-1], C[-1], 1)
+    _rb(d, g, "mid.rb2", C[-1], C[-1], te)
+    prev = C[-1]
+    for i in reversed(range(len(C))):
+        _conv(d, g, f"up.{i}.up.up", C[i], prev, 3)
+        _rb(d, g, f"up.{i}.rb1", 2 * C[i], C[i], te)
+        _rb(d, g, f"up.{i}.rb2", C[i], C[i], te)
+        prev = C[i]
+    _conv(d, g, "final", 3, C[0], 3)
+    if with_context:
+        prev = cfg.latent_ch
+        for i in reversed(range(len(C))):
+            _conv(d, g, f"context.ups.{i}.up", C[i], prev, 3)
+            _rb(d, g, f"context.rbs.{i}", C[i], C[i], 0)
+            prev = C[i]
+    return d
+
+
+def latent(B, H, W, index=0, ch=256):
+    """y_hat = rint(4 * randn) fp32 [B, ch, H/16, W/16] (SURVEY.md section 8d synthetic inputs)."""
+    g = torch.Generator().manual_seed(1000 + index)
+    return torch.round(4.0 * torch.randn(B, ch, H // 16, W // 16, generator=g))
+
+
+def init_noise(B, H, W, index=0, gamma=0.8):
+    g = torch.Generator().manual_seed(2000 + index)
+    return gamma * torch.randn(B, 3, H, W, generator=g)

@@ -44,3 +44,16 @@ def test_no_gpu_means_loud_failure(built):
     from cdc_b200 import CDCConfig, Decoder
     with pytest.raises(RuntimeError):
         Decoder(CDCConfig(), {}, device="cuda:0")
+
+
+def test_synthetic_weights_match_the_oracle_state_dict():
+    """The product's random-weight generator (bench / smoke) must produce exactly the tensor names and
+    shapes of the oracle's state dict, which is what cdc_load_weights consumes."""
+    from cdc_b200.synthetic import random_weights
+    from oracle.config import CDCConfig
+    from oracle.weights import build_codec, build_unet
+    w = random_weights()
+    ref = dict(build_unet(CDCConfig()).state_dict())
+    ref.update({"context." + k: v for k, v in build_codec(CDCConfig()).context.state_dict().items()})
+    assert set(w) == set(ref)
+    assert all(w[k].shape == ref[k].shape for k in w)
