@@ -267,7 +267,7 @@ def main():
                 f.write("op,gflop,mbytes,us,tflops,gbs\n")
                 for (n, fl, b), t in zip(ops, med):
                     f.write(f"{n},{fl / 1e9:.3f},{b / 1e6:.3f},{t * 1e3:.2f},{fl / (t / 1e3) / 1e12:.1f},{b / (t / 1e3) / 1e9:.0f}\n")
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:  # the CPU baseline is an N=1 figure (contract); torchrun also pins OMP threads
             v, cores, t_ctx, t_step = cpu_oracle_sample(n_steps=2)
             out["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
                                    "sample": f"oracle (fp32 torch eager, channels_last): 1 context-net pass ({t_ctx:.2f} s) + 2 of {K_DDIM} "

@@ -372,4 +372,33 @@ cudaError_t launch_repack_weight(const float* src, act_t* dst, int O, int I, int
     return cudaGetLastError();
 }
 
+// Nearest-x2-then-conv3x3 == four 2x2 convolutions on the low-resolution input, one per output parity
+// (py, px), with phase weights that are sums of the original taps:
+//   rows:  py = 0 -> {dh -1: kh 0 | dh 0: kh 1+2},   py = 1 -> {dh 0: kh 0+1 | dh +1: kh 2}   (same for columns)
+// dst: [O_pad][16 = (ph, a, b)][I_pad], summed in fp32 and rounded once (the originals are bf16-exact, so
+// the sums are almost always exact in fp16).  2.25x fewer MMAs than evaluating the 9 taps per parity.
+__global__ void repack_weight_up2_kernel(const float* __restrict__ src, act_t* __restrict__ dst, int O, int I,
+                                         int O_pad, int I_pad) {
+    const long long n = static_cast<long long>(O_pad) * 16 * I_pad;
+    for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < n; idx += gridDim.x * 256LL) {
+        const int i = static_cast<int>(idx % I_pad);
+        const int t = static_cast<int>((idx / I_pad) % 16);
+        const int o = static_cast<int>(idx / (static_cast<long long>(I_pad) * 16));
+        const int ph = t >> 2, a = (t >> 1) & 1, b = t & 1, py = ph >> 1, px = ph & 1;
+        const int kh0 = py == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2), kh1 = py == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+        const int kw0 = px == 0 ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2), kw1 = px == 0 ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+        float v = 0.f;
+        if (o < O && i < I)
+            for (int kh = kh0; kh <= kh1; ++kh)
+                for (int kw = kw0; kw <= kw1; ++kw) v += src[(static_cast<size_t>(o) * I + i) * 9 + kh * 3 + kw];
+        dst[idx] = to_act(v);
+    }
+}
+cudaError_t launch_repack_weight_up2(const float* src, act_t* dst, int O, int I, int O_pad, int I_pad, cudaStream_t s) {
+    const long long n = static_cast<long long>(O_pad) * 16 * I_pad;
+    repack_weight_up2_kernel<<<static_cast<int>((n + 255) / 256 < 2048 ? (n + 255) / 256 : 2048), 256, 0, s>>>(src, dst, O, I,
+                                                                                                            O_pad, I_pad);
+    return cudaGetLastError();
+}
+
 }  // namespace cdc

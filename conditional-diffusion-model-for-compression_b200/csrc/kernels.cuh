@@ -48,6 +48,9 @@ cudaError_t launch_x_out(const float* xs, float* x_nchw, int B, int HW, int to_i
 cudaError_t launch_repack_weight(const float* src, act_t* dst, int O, int I, int taps, int O_pad, int I_pad,
                                  int split, int split_pad, cudaStream_t s);
 
+// nearest-x2 + conv3x3 folded into 4 parity-specific 2x2 convs: dst [O_pad][16][I_pad] (see elementwise.cu)
+cudaError_t launch_repack_weight_up2(const float* src, act_t* dst, int O, int I, int O_pad, int I_pad, cudaStream_t s);
+
 // ---- attention (C7; oracle/unet.py Attn) --------------------------------------------------------
 // qkv [B*N][768] act_t (q | k | v, head h = channels 64h..64h+63) -> o [B*N][256] bf16
 cudaError_t launch_attention(const act_t* qkv, act_t* o, int B, int N, int heads, cudaStream_t s);

@@ -52,6 +52,7 @@ struct ConvW {  // repacked conv weights: act_t [n_pad][taps][c_pad], fp32 bias 
     act_t* w = nullptr;
     float* bias = nullptr;
     int n_true = 0, n_pad = 0, taps = 0, c_pad = 0, c_true = 0;
+    bool up2 = false;  // taps == 16: parity-specific pre-summed 2x2 weights for nearest-x2-input convs
 };
 
 struct Op {
@@ -182,7 +183,8 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
     }
     const ConvW& w = *cb.w;
     const int taps = cb.ksize * cb.ksize;
-    if (ctot != w.c_pad || taps != w.taps) return fail("weight layout does not match the sources");
+    if (ctot != w.c_pad || (w.up2 ? (cb.mode != MODE_UP2 || cb.ksize != 3) : taps != w.taps))
+        return fail("weight layout does not match the sources");
     auto cp = std::shared_ptr<ConvParams>(new ConvParams());
     memset(cp.get(), 0, sizeof(ConvParams));
     int gw, gh, nphase, os, bwl, tiles_w, tiles_h;
@@ -302,12 +304,31 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
     if (encode_w_map(&cp->wmap, w.w, w.taps * w.c_pad, w.n_pad, bn)) return fail("cuTensorMapEncodeTiled (weights) failed");
 
     // K-block table
-    int nkb = taps * (ctot / 64);
+    int nkb = (w.up2 ? 4 : taps) * (ctot / 64);
     if (nkb * nphase > kMaxKBlocks) return fail("K-block table overflow");
     const int pad = cb.ksize / 2;
     for (int ph = 0; ph < nphase; ++ph) {
         const int py = ph >> 1, px = ph & 1;
         int i = 0;
+        if (w.up2) {  // pre-summed parity weights: 2x2 taps, K index = ((ph*4 + a*2 + b) * ctot + channel)
+            for (int a = 0; a < 2; ++a)
+                for (int bb = 0; bb < 2; ++bb) {
+                    int soff = 0;
+                    for (size_t s = 0; s < cb.srcs.size(); ++s) {
+                        for (int c = 0; c < cb.srcs[s].C; c += 64) {
+                            KBlock& e = cp->kb[ph * nkb + i++];
+                            e.map = static_cast<int8_t>(s);
+                            e.dh = static_cast<int8_t>(py == 0 ? a - 1 : a);
+                            e.dw = static_cast<int8_t>(px == 0 ? bb - 1 : bb);
+                            e.pad = 0;
+                            e.c0 = static_cast<uint16_t>(c);
+                            e.wk = static_cast<uint16_t>((ph * 4 + a * 2 + bb) * ctot + soff + c);
+                        }
+                        soff += cb.srcs[s].C;
+                    }
+                }
+            continue;
+        }
         for (int kh = 0; kh < cb.ksize; ++kh)
             for (int kw = 0; kw < cb.ksize; ++kw) {
                 int dh = kh - pad, dw = kw - pad, msel = 0;
@@ -467,8 +488,8 @@ static const WeightT* find_w(cdc_ctx* ctx, const std::string& name) {
 // Repack "<pfx>.weight"/".bias" (OIHW fp32) to the K-conv layout.  `split`/`split_pad`: input channels
 // >= split start at slot split_pad (stem: 3 image channels padded to 64, then the 64 context channels).
 static int make_conv_w(cdc_ctx* ctx, Arena& ar, const float* wsrc, const float* bsrc, int O, int I, int ks, int split,
-                       int split_pad, bool is_final, ConvW* out, cudaStream_t s) {
-    const int taps = ks * ks;
+                       int split_pad, bool is_final, ConvW* out, cudaStream_t s, bool up2 = false) {
+    const int taps = up2 ? 16 : ks * ks;
     const int c_pad = (split < I && split_pad > split) ? split_pad + ((I - split + 63) / 64) * 64 : ((I + 63) / 64) * 64;
     const int n_pad = is_final ? 16 : ((O + 63) / 64) * 64;
     ConvW cw;
@@ -483,13 +504,17 @@ static int make_conv_w(cdc_ctx* ctx, Arena& ar, const float* wsrc, const float* 
     CK(cudaMemcpyAsync(cw.bias, bsrc, static_cast<size_t>(O) * 4, cudaMemcpyDeviceToDevice, s));
     const int sp = (split < I && split_pad > split) ? split : I;
     const int spp = (split < I && split_pad > split) ? split_pad : I;
-    CK(launch_repack_weight(wsrc, cw.w, O, I, taps, n_pad, c_pad, sp, spp, s));
+    cw.up2 = up2;
+    if (up2)
+        CK(launch_repack_weight_up2(wsrc, cw.w, O, I, n_pad, c_pad, s));
+    else
+        CK(launch_repack_weight(wsrc, cw.w, O, I, taps, n_pad, c_pad, sp, spp, s));
     *out = cw;
     return CDC_OK;
 }
 
 static int conv_from_store(cdc_ctx* ctx, const std::string& pfx, int O, int I, int ks, int split, int split_pad,
-                           bool is_final) {
+                           bool is_final, bool up2 = false) {
     const WeightT* w = find_w(ctx, pfx + ".weight");
     const WeightT* b = find_w(ctx, pfx + ".bias");
     if (!w || !b) return ctx->fail(CDC_ERR_WEIGHT, "missing weight tensor %s.weight/.bias", pfx.c_str());
@@ -497,7 +522,7 @@ static int conv_from_store(cdc_ctx* ctx, const std::string& pfx, int O, int I, i
         b->numel != static_cast<size_t>(O))
         return ctx->fail(CDC_ERR_WEIGHT, "%s: expected conv weight [%d,%d,%d,%d]", pfx.c_str(), O, I, ks, ks);
     ConvW cw;
-    int r = make_conv_w(ctx, ctx->warena, w->p, b->p, O, I, ks, split, split_pad, is_final, &cw, nullptr);
+    int r = make_conv_w(ctx, ctx->warena, w->p, b->p, O, I, ks, split, split_pad, is_final, &cw, nullptr, up2);
     if (r) return r;
     ctx->convs[pfx] = cw;
     return CDC_OK;
@@ -946,7 +971,7 @@ int cdc_finalize_weights(cdc_ctx* ctx) {
     int prev = C[3];
     for (int i = 3; i >= 0; --i) {
         const std::string p = "up." + std::to_string(i);
-        if ((r = conv_from_store(ctx, p + ".up.up", C[i], prev, 3, prev, prev, false))) return r;
+        if ((r = conv_from_store(ctx, p + ".up.up", C[i], prev, 3, prev, prev, false, true))) return r;
         if ((r = rb_weights(ctx, p + ".rb1", 2 * C[i], C[i], true))) return r;
         if ((r = rb_weights(ctx, p + ".rb2", C[i], C[i], true))) return r;
         prev = C[i];
@@ -962,7 +987,7 @@ int cdc_finalize_weights(cdc_ctx* ctx) {
         prev = ctx->cfg.latent_ch;
         for (int i = 3; i >= 0; --i) {
             const std::string s = std::to_string(i);
-            if ((r = conv_from_store(ctx, "context.ups." + s + ".up", C[i], prev, 3, prev, prev, false))) return r;
+            if ((r = conv_from_store(ctx, "context.ups." + s + ".up", C[i], prev, 3, prev, prev, false, true))) return r;
             if ((r = rb_weights(ctx, "context.rbs." + s, C[i], C[i], false))) return r;
             prev = C[i];
         }
@@ -1254,7 +1279,7 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
     Arena ar;
     ConvW cw;
     const int cin = c0 + c1;
-    int r = make_conv_w(ctx, ar, w_oihw, bias, cout, cin, ksize, cin, cin, false, &cw, S(s));
+    int r = make_conv_w(ctx, ar, w_oihw, bias, cout, cin, ksize, cin, cin, false, &cw, S(s), mode == MODE_UP2 && ksize == 3);
     if (r) {
         g_create_err = tmp.err;
         ar.release();
