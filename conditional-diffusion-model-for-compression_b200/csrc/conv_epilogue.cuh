@@ -58,7 +58,7 @@ constexpr int kEpiThreads = kEpiWarps * 32;
 template <int BN, int CPG, int EPI>
 __device__ __forceinline__ void conv_epilogue_tile(const EpiArgs& e, uint32_t taddr, uint32_t bar_tempty,
                                                    const float* bs, float* red, int q, int half, int lane, bool valid,
-                                                   size_t pix, int n0, float* stats_dst, long long* dbg = nullptr) {
+                                                   size_t pix, int n0, float* stats_dst, long long* dbg = nullptr, bool arrive = true) {
     if constexpr (EPI == EPI_DDIM) {
         if (half != 0) return;
         uint32_t v[16];
@@ -95,7 +95,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const EpiArgs& e, uint32_t ta
             tmem_ld32(taddr + c0 + ch * 32, v);
             tmem_ld_wait();
             if (dbg && ch == 0) dbg[1] = clock64();
-            if (ch == NCH - 1) {  // this warp's share of the accumulator is drained
+            if (ch == NCH - 1 && arrive) {  // this warp's share of the accumulator (group) is drained
                 tc_fence_before();
                 mbar_arrive(bar_tempty);
             }

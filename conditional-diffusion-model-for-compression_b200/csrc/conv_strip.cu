@@ -37,7 +37,11 @@ template <int BN, int CPG, int EPI, int CH, bool RES>
 __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_strip_kernel(const __grid_constant__ StripParams p) {
     constexpr int WB = BN * 128;  // one (tap, chunk) weight slice
     constexpr int ACC_STRIDE = BN < 32 ? 32 : BN;
-    constexpr int TMEM_COLS = (2 * ACC_STRIDE <= 32) ? 32 : (2 * ACC_STRIDE <= 64) ? 64 : (2 * ACC_STRIDE <= 128) ? 128 : 256;
+    // Streamed weights: every weight stage feeds R = 2 output rows (two accumulators), which halves the weight
+    // traffic and the issuer's waits / commits per MMA.  Resident weights: R = 1.
+    constexpr int R = RES ? 1 : 2;
+    constexpr int BUF_STRIDE = R * ACC_STRIDE;  // TMEM columns of one accumulator group
+    constexpr int TMEM_COLS = (2 * BUF_STRIDE <= 32) ? 32 : (2 * BUF_STRIDE <= 64) ? 64 : (2 * BUF_STRIDE <= 128) ? 128 : (2 * BUF_STRIDE <= 256) ? 256 : 512;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
@@ -131,7 +135,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_strip_kernel(const 
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
                 int b, seg, h0, h1;
                 decode(u, b, seg, h0, h1);
-                for (int h = h0; h < h1; ++h)
+                for (int h = h0; h < h1; h += R)            // one pass over the weights per group of R output rows
                     for (int i = 0; i < 9 * CH; ++i) {  // K order = (tap, chunk), as the weight matrix
                         mbar_wait(bar_wempty + 8 * ws, wph ^ 1);
                         mbar_expect_tx_p(bar_wfull + 8 * ws, WB, leader);
@@ -171,20 +175,23 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_strip_kernel(const 
             const int rows = h1 - h0;
             wait_row();
             wait_row();
-            for (int j = 0; j < rows; ++j, ++it) {
+            for (int j = 0; j < rows; j += R, ++it) {
+                const int nr = (R == 2 && j + 1 < rows) ? 2 : 1;  // output rows in this group
+                const bool last = j + R >= rows;
                 const uint32_t as = it & 1, aphase = (it >> 1) & 1;
                 const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && it < 64;
                 if (dbg) p.dbg[it * 4 + 0] = clock64();
                 mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
                 if (dbg) p.dbg[it * 4 + 1] = clock64();
-                wait_row();
+                for (int i = 0; i < nr; ++i) wait_row();
                 tc_fence_after();
                 if (dbg) p.dbg[it * 4 + 2] = clock64();
-                const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
-                const uint32_t s1 = next_slot(aslot), s2 = next_slot(s1);
-                const uint32_t rowaddr[3] = {ring + aslot * slot_stride, ring + s1 * slot_stride, ring + s2 * slot_stride};
+                const uint32_t d_tmem = tmem_base + as * BUF_STRIDE;
+                const uint32_t s1 = next_slot(aslot), s2 = next_slot(s1), s3 = next_slot(s2);
+                const uint32_t rowaddr[4] = {ring + aslot * slot_stride, ring + s1 * slot_stride, ring + s2 * slot_stride,
+                                             ring + s3 * slot_stride};
                 // Elected-lane region with 32-bit descriptor low words and compile-time accumulate flags:
-                // 64 cycles per MMA (the M=128 operand-fetch floor) instead of 115 for a predicated-asm
+                // 57-64 cycles per MMA (the M=128 operand-fetch floor) instead of 115 for a predicated-asm
                 // formulation of the same loop (tools/exp_mma_rate.cu, modes 4 / 5).
                 if (leader) {
                     uint32_t wb = wbase;
@@ -192,19 +199,26 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_strip_kernel(const 
                     for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
                         for (int kw = 0; kw < 3; ++kw) {
-                            uint32_t aaddr = rowaddr[kh] + kw * 128;
 #pragma unroll
-                            for (int ch = 0; ch < CH; ++ch, aaddr += kRowBytes) {
+                            for (int ch = 0; ch < CH; ++ch) {
                                 if (!resident) {
                                     mbar_wait(bar_wfull + 8 * ws, wph);
                                     tc_fence_after();
                                     wb = wbase + ws * WB;
                                 }
-                                const uint32_t alo = (aaddr >> 4) & 0x3FFFu, blo = (wb >> 4) & 0x3FFFu;
+                                const uint32_t blo = (wb >> 4) & 0x3FFFu;
+                                const uint32_t alo0 = ((rowaddr[kh] + kw * 128 + ch * kRowBytes) >> 4) & 0x3FFFu;
 #pragma unroll
                                 for (int k = 0; k < 4; ++k)
-                                    umma_f16_ss(d_tmem, desc_hi | (alo + 2 * k), desc_hi | (blo + 2 * k), idesc,
+                                    umma_f16_ss(d_tmem, desc_hi | (alo0 + 2 * k), desc_hi | (blo + 2 * k), idesc,
                                                 (kh | kw | k | ch) != 0 ? 1u : 0u);
+                                if (R == 2 && nr == 2) {
+                                    const uint32_t alo1 = ((rowaddr[kh + 1] + kw * 128 + ch * kRowBytes) >> 4) & 0x3FFFu;
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        umma_f16_ss(d_tmem + ACC_STRIDE, desc_hi | (alo1 + 2 * k), desc_hi | (blo + 2 * k),
+                                                    idesc, (kh | kw | k | ch) != 0 ? 1u : 0u);
+                                }
                                 if (resident) {
                                     wb += WB;
                                 } else {
@@ -216,16 +230,22 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_strip_kernel(const 
                                 }
                             }
                         }
+                        if (kh == 0) umma_commit(bar_rempty + 8 * aslot);  // input row h-1 is only read by the kh = 0 taps
                     }
-                    umma_commit(bar_rempty + 8 * aslot);  // input row h-1 has served its last output row
-                    if (j == rows - 1) {
-                        umma_commit(bar_rempty + 8 * s1);
-                        umma_commit(bar_rempty + 8 * s2);
+                    if (nr == 2) umma_commit(bar_rempty + 8 * s1);
+                    if (last) {  // the remaining rows of this strip are not needed by anyone
+                        if (nr == 2) {
+                            umma_commit(bar_rempty + 8 * s2);
+                            umma_commit(bar_rempty + 8 * s3);
+                        } else {
+                            umma_commit(bar_rempty + 8 * s1);
+                            umma_commit(bar_rempty + 8 * s2);
+                        }
                     }
                     umma_commit(bar_tfull + 8 * as);
                 }
                 __syncwarp();
-                aslot = (j == rows - 1) ? next_slot(s2) : s1;
+                aslot = last ? next_slot(nr == 2 ? s3 : s2) : (nr == 2 ? s2 : s1);
                 if (dbg) p.dbg[it * 4 + 3] = clock64();
             }
         }
@@ -235,15 +255,15 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_strip_kernel(const 
         const int half = (warp - 4) >> 2;
         const int row = q * 32 + lane;
         const EpiArgs ea{p.out, p.residual, p.ldc, p.x, p.xpad, p.x0_out, p.c0, p.c1};
-        uint32_t it = 0;
+        uint32_t it = 0, tile_ctr = 0;
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
             int b, seg, h0, h1;
             decode(u, b, seg, h0, h1);
             const int gx = seg * 128 + row;
             const bool valid = gx < p.W;
-            for (int h = h0; h < h1; ++h, ++it) {
+            for (int h = h0; h < h1; h += R, ++it) {
+                const int nr = (R == 2 && h + 1 < h1) ? 2 : 1;
                 const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-                const size_t pix = (static_cast<size_t>(b) * p.H + h) * p.W + gx;
                 long long* edbg = (p.dbg != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0 && it < 32) ? p.dbg + 256 + it * 8 : nullptr;
                 if (edbg) edbg[4] = clock64();
                 mbar_wait(bar_tfull + 8 * as, aphase);
@@ -254,12 +274,15 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_strip_kernel(const 
                     mbar_arrive(bar_tempty + 8 * as);
                     continue;
                 }
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * ACC_STRIDE;
-                float* sdst = (EPI == EPI_STATS)
-                                  ? p.stats + ((static_cast<size_t>(b) * p.H * p.nseg + static_cast<size_t>(h) * p.nseg + seg) * 32) * 2
-                                  : nullptr;
-                conv_epilogue_tile<BN, CPG, EPI>(ea, taddr, bar_tempty + 8 * as, bias_s, red_s + (it & 1) * (2 * 4 * 16 * 2),
-                                                 q, half, lane, valid, pix, 0, sdst, edbg);
+                for (int r = 0; r < nr; ++r, ++tile_ctr) {
+                    const size_t pix = (static_cast<size_t>(b) * p.H + (h + r)) * p.W + gx;
+                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BUF_STRIDE + r * ACC_STRIDE;
+                    float* sdst = (EPI == EPI_STATS)
+                                      ? p.stats + ((static_cast<size_t>(b) * p.H * p.nseg + static_cast<size_t>(h + r) * p.nseg + seg) * 32) * 2
+                                      : nullptr;
+                    conv_epilogue_tile<BN, CPG, EPI>(ea, taddr, bar_tempty + 8 * as, bias_s, red_s + (tile_ctr & 1) * (2 * 4 * 16 * 2),
+                                                     q, half, lane, valid, pix, 0, sdst, edbg, r == nr - 1);
+                }
                 if (edbg) edbg[5] = clock64();
             }
         }
@@ -296,7 +319,7 @@ bool strip_plan(int bn, int CH, int* NR, int* NSW) {
             *NSW = 0;
             return true;
         }
-    for (int nr = 6; nr >= 4; --nr)
+    for (int nr = 6; nr >= 5; --nr)  // streamed weights run two output rows per group: 4 live rows + 1 in flight
         for (int nsw = 6; nsw >= 3; --nsw)
             if (strip_smem_bytes(bn, CH, nr, nsw) <= limit) {
                 *NR = nr;

@@ -197,6 +197,16 @@ void run(const char* name, int grid, int nmma, int row_off, int commit_every, in
 
 int main() {
     const int n = 36 * 64;
+    // mode 0: plain single-thread issue, by N (the kh-fused strip kernel issues N = 192 / 96 MMAs)
+    for (int grid : {148}) {
+        run<32>("plain issue", grid, n, 0, 0, 1, 0, 1);
+        run<64>("plain issue", grid, n, 0, 0, 1, 0, 1);
+        run<96>("plain issue", grid, n, 0, 0, 1, 0, 1);
+        run<128>("plain issue", grid, n, 0, 0, 1, 0, 1);
+        run<192>("plain issue", grid, n, 0, 0, 1, 0, 1);
+        run<256>("plain issue", grid, n, 0, 0, 1, 0, 1);
+        run<192>("plain issue, commit/12", grid, n, 0, 12, 1, 0, 1);
+    }
     for (int grid : {148}) {
         run<64>("micro baseline if(elect) x4", grid, n, 0, 0, 0, 3, 1);
         run<64>("strip issuer replica (pred asm)", grid, n, 0, 0, 0, 4, 1);
