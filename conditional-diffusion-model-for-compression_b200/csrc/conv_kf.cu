@@ -1,0 +1,484 @@
+// K-conv, kh-fused strip variant: 3x3 stride-1 convolution with the three vertical taps of an input row
+// stacked along the MMA's N dimension.
+//
+// Why: tcgen05.mma (M = 128, K = 16, SS operands) costs max(~55, N/2) cycles (tools/exp_mma_n.cu on B200):
+// below N = 128 the instruction is bound by the fetch of its 4 KB A tile, so a C_out = 64 layer issued as
+// N = 64 MMAs cannot exceed ~56 % of the tensor pipe.  But input row r, shifted by kw, is the A operand of
+// THREE taps: (kh = 0 -> output row r+1), (kh = 1 -> r), (kh = 2 -> r-1).  Their weights are stacked to a
+// [3 * BN][64] B operand and the three output rows live in adjacent TMEM column blocks, so ONE N = 3*BN MMA
+// does the work of three: N = 192 runs at the 96-cycle tensor floor (32 cycles per 64 columns, 100 %).
+//
+//   work unit : a vertical strip = 128 output columns x L output rows of one image, one N tile of BN channels
+//   A operand : ring of input-row chunks in shared memory (TMA box {64 ch, 130 px, 1, 1}, zero fill = conv
+//               padding); every (row, 64-channel chunk) is loaded once, consumed by its own 12 MMAs and released
+//   B operand : the N tile's whole [kw][chunk][kh reversed][BN][64] weight block, resident in shared memory
+//   D         : ring of 8 accumulators (BN TMEM columns each); output row j of the running row counter g
+//               lives in slot (g + j) & 7, so the window {r-1, r, r+1} is contiguous except when it wraps
+//               (then the MMA is split in two)
+//   first use : every MMA accumulates; the epilogue re-zeroes an accumulator (tcgen05.st) right after draining it,
+//               so the issue stream has no special first K step
+//
+//   warp 0 : input-row producer (TMA)   warp 1 : tcgen05.mma issuer   warp 2 : TMEM allocator
+//   warp 3 : weight loader (TMA, once)  warps 4-11 : epilogue
+//
+// Epilogue: +bias, GroupNorm partial sums kept in registers over the whole strip (one fixed-order partial row
+// per strip: bitwise reproducible), fp16 pack, then either a swizzled shared-memory tile + one TMA store per
+// output row (coalesced 16 KB writes) or direct 16-byte stores; EPI_DDIM applies the sampler update.
+//
+// Oracle counterpart: oracle/unet.py `conv(k=3)` inside RB / stem / final (the reference ships no code).
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <type_traits>
+
+#include "conv_epilogue.cuh"
+#include "conv_kf.cuh"
+#include "ptx.cuh"
+
+namespace cdc {
+
+constexpr int kKfRowBytes = 17 * 1024;  // 130 pixels x 128 B = 16640, padded to a 1024 B multiple
+constexpr int kKfRowTx = 130 * 128;
+constexpr int kKfAcc = 8;               // accumulator ring
+constexpr int kKfAux = 1024 + 2 * 8 * 16 * 2 * 4;  // barriers + TMEM holder + bias, stats scratch
+
+template <int BN, int CPG, int EPI, int CH, bool STAGE>
+__global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __grid_constant__ KfParams p) {
+    constexpr int WB = BN * 128;  // one (tap, chunk) weight block
+    constexpr uint32_t WB16 = WB >> 4;
+    constexpr int TMEM_COLS = kKfAcc * BN < 32 ? 32 : kKfAcc * BN;
+    constexpr int STAGE_BYTES = STAGE ? 2 * 128 * BN * 2 : 0;
+    static_assert(!STAGE || BN == 64, "staged TMA store is built for 128-byte output rows");
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_u32 = smem_u32(smem_raw);
+    const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - raw_u32);
+    const int NS = p.NS;
+    const uint32_t ring = base;
+    const uint32_t wbase = ring + NS * kKfRowBytes;
+    const uint32_t stage = wbase + 9 * CH * WB;
+    const uint32_t aux = stage + STAGE_BYTES;
+    uint8_t* aux_gen = gen + (aux - base);
+    // barriers: row_full[4] row_empty[4] tfull[8] tempty[8] wres
+    const uint32_t bar_rfull = aux, bar_rempty = aux + 32, bar_tfull = aux + 64, bar_tempty = aux + 128, bar_wres = aux + 192;
+    volatile uint32_t* tmem_holder = reinterpret_cast<volatile uint32_t*>(aux_gen + 200);
+    float* bias_s = reinterpret_cast<float*>(aux_gen + 256);
+    float* red_s = reinterpret_cast<float*>(aux_gen + 1024);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nt = blockIdx.x / p.G1, cta = blockIdx.x % p.G1;
+    const int units = p.batch * p.nseg * p.S;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&p.amap[0]);
+        prefetch_tensormap(&p.wmap);
+        if (STAGE) prefetch_tensormap(&p.omap);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < 4; ++s) {
+            mbar_init(bar_rfull + 8 * s, 1);
+            mbar_init(bar_rempty + 8 * s, 1);
+        }
+        for (int s = 0; s < kKfAcc; ++s) {
+            mbar_init(bar_tfull + 8 * s, 1);
+            mbar_init(bar_tempty + 8 * s, EPI == EPI_DDIM ? 128 : kEpiThreads);
+        }
+        mbar_init(bar_wres, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) {  // (warp-collective)
+        tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_holder)), TMEM_COLS);
+        tmem_relinquish();
+    }
+    for (int i = threadIdx.x; i < BN; i += 128 + kEpiThreads) bias_s[i] = p.bias[nt * BN + i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 3 && lane == 0) {
+        // Weights are constants: their load need not wait for the preceding kernel (PDL).
+        // smem block order [kw][chunk][2 - kh]: the kh taps of one (kw, chunk) form one contiguous B operand.
+        mbar_expect_tx(bar_wres, 9 * CH * WB);
+        for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw)
+                for (int ch = 0; ch < CH; ++ch)
+                    tma_load_2d(wbase + ((kw * CH + ch) * 3 + (2 - kh)) * WB, &p.wmap, bar_wres,
+                                ((kh * 3 + kw) * CH + ch) * 64, nt * BN);
+    }
+    pdl_launch_dependents();
+    pdl_wait();  // everything below touches activations written by the preceding kernels
+
+    auto decode = [&](int u, int& b, int& seg, int& si, int& h0, int& L) {
+        si = u % p.S;
+        const int t = u / p.S;
+        seg = t % p.nseg;
+        b = t / p.nseg;
+        h0 = si * p.H / p.S;
+        L = (si + 1) * p.H / p.S - h0;
+    };
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ input-row producer
+        if (lane == 0) {
+            uint32_t slot = 0, par = 0;  // ring position / fill parity (continues across strips)
+            uint32_t g = 0;
+            for (int u = cta; u < units; u += p.G1) {
+                int b, seg, si, h0, L;
+                decode(u, b, seg, si, h0, L);
+                const int w0 = seg * 128 - 1;
+                for (int i = 0; i < L + 2; ++i) {
+                    if (i < L) {  // input row i opens the accumulator of output row i: drained and re-zeroed?
+                        const uint32_t gi = g + i;
+                        mbar_wait(bar_tempty + 8 * (gi & 7), (gi >> 3) & 1);
+                    }
+#pragma unroll
+                    for (int ch = 0; ch < CH; ++ch) {  // one ring slot per (row, 64-channel chunk)
+                        mbar_wait(bar_rempty + 8 * slot, par ^ 1);
+                        const uint32_t full = bar_rfull + 8 * slot;
+                        mbar_expect_tx(full, kKfRowTx);
+                        const bool s1 = ch >= p.chunks0;
+                        tma_load_4d(ring + slot * kKfRowBytes, s1 ? &p.amap[1] : &p.amap[0], full, (s1 ? ch - p.chunks0 : ch) * 64, w0,
+                                    h0 - 1 + i, b);
+                        if (++slot == static_cast<uint32_t>(NS)) {
+                            slot = 0;
+                            par ^= 1;
+                        }
+                    }
+                }
+                g += L;
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        // The warp runs the loop converged (descriptor arithmetic stays warp-uniform) and one elected lane issues.
+        // One mbarrier wait per input row (row_full also certifies that the accumulator the row opens is drained and
+        // re-zeroed: the producer checked), placed in the MIDDLE of the previous row's MMA stream so that the MMAs
+        // already queued in the tensor pipe cover its latency.  Every MMA accumulates (the epilogue re-zeroes slots).
+        {
+            constexpr uint32_t idesc0 = make_idesc_f16(128, 0);
+            constexpr uint32_t NB = static_cast<uint32_t>(BN >> 3) << 17;  // idesc increment per window slot
+            constexpr int T = 12, TH = 6;  // K steps per (input row, chunk); position of the wait for the next chunk
+            const uint64_t desc_hi = make_sw128_desc(0) & 0xFFFFFFFF00000000ull;
+            const uint32_t wlo = wbase >> 4;
+            uint32_t rslot = 0, rpar = 0;
+            uint32_t g = 0;  // running output-row counter: row j of the current strip uses accumulator (g + j) & 7
+            mbar_wait(bar_wres, 0);
+            for (int u = cta; u < units; u += p.G1) {
+                int b, seg, si, h0, L;
+                decode(u, b, seg, si, h0, L);
+                mbar_wait(bar_rfull + 8 * rslot, rpar);  // first chunk of the strip
+                tc_fence_after();
+                for (int i = 0; i < L + 2; ++i) {
+                    const int jlo = i >= 2 ? i - 2 : 0;
+                    const int jhi = i < L ? i : L - 1;
+                    const uint32_t cnt = static_cast<uint32_t>(jhi - jlo + 1);
+                    const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && u == cta && i < 40 && lane == 0;
+                    if (dbg) p.dbg[i * 4 + 0] = clock64();
+                    const uint32_t slo = (g + jlo) & 7;
+                    const uint32_t khp = static_cast<uint32_t>(2 - (i - jlo));  // reversed kh of the first window slot
+                    const uint32_t nA = cnt < 8 - slo ? cnt : 8 - slo, nB = cnt - nA;
+                    const uint32_t dA = tmem_base + slo * BN, dB = tmem_base;
+                    const uint32_t bA = khp * WB16, bB = (khp + nA) * WB16;
+                    const uint32_t iA = idesc0 + nA * NB, iB = idesc0 + nB * NB;
+#pragma unroll
+                    for (int ch = 0; ch < CH; ++ch) {
+                        const uint32_t alo_base = (ring + rslot * kKfRowBytes) >> 4;
+                        // K steps t = kw * 4 + k in [t0, t1); a wrapped window issues its two pieces back to back
+                        // per half (alternating MMA shapes costs ~30 cycles per switch)
+                        auto steps = [&](auto t0c, auto t1c) {
+                            constexpr int t0 = decltype(t0c)::value, t1 = decltype(t1c)::value;
+#pragma unroll
+                            for (int t = t0; t < t1; ++t) {
+                                const int k = t & 3, kw = t >> 2;
+                                const uint32_t alo = alo_base + kw * 8 + 2 * k;
+                                const uint32_t blo = wlo + ((kw * CH + ch) * 3) * WB16 + 2 * k;
+                                umma_f16_ss(dA, desc_hi | alo, desc_hi | (blo + bA), iA, 1u);
+                            }
+                            if (nB != 0) {
+#pragma unroll
+                                for (int t = t0; t < t1; ++t) {
+                                    const int k = t & 3, kw = t >> 2;
+                                    const uint32_t alo = alo_base + kw * 8 + 2 * k;
+                                    const uint32_t blo = wlo + ((kw * CH + ch) * 3) * WB16 + 2 * k;
+                                    umma_f16_ss(dB, desc_hi | alo, desc_hi | (blo + bB), iB, 1u);
+                                }
+                            }
+                        };
+                        if (elect_one_sync()) steps(std::integral_constant<int, 0>{}, std::integral_constant<int, TH>{});
+                        __syncwarp();
+                        if (dbg && ch == 0) p.dbg[i * 4 + 1] = clock64();
+                        const uint32_t nslot = rslot + 1 == static_cast<uint32_t>(NS) ? 0u : rslot + 1;
+                        if (ch + 1 < CH || i + 1 < L + 2) {  // next chunk (a new row's first chunk also certifies its accumulator)
+                            mbar_wait(bar_rfull + 8 * nslot, nslot == 0 ? rpar ^ 1 : rpar);
+                            tc_fence_after();
+                        }
+                        if (dbg && ch == 0) p.dbg[i * 4 + 2] = clock64();
+                        if (elect_one_sync()) {
+                            steps(std::integral_constant<int, TH>{}, std::integral_constant<int, T>{});
+                            umma_commit(bar_rempty + 8 * rslot);  // chunk consumed
+                            if (ch == CH - 1 && i >= 2) umma_commit(bar_tfull + 8 * ((g + i - 2) & 7));  // output row i-2 complete
+                        }
+                        __syncwarp();
+                        rslot = nslot;
+                        if (nslot == 0) rpar ^= 1;
+                    }
+                    if (dbg) p.dbg[i * 4 + 3] = clock64();
+                }
+                g += L;
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------ epilogue (8 warps)
+        const int q = warp & 3;            // TMEM sub-partition: lanes 32q .. 32q+31
+        const int half = (warp - 4) >> 2;  // column half of the accumulator
+        const int row = q * 32 + lane;
+        uint32_t g = 0, tile_ctr = 0, unit_ctr = 0;
+        if constexpr (EPI == EPI_DDIM) {
+            if (half == 0) {
+                const float b0 = bias_s[0], b1 = bias_s[1], b2 = bias_s[2];
+                for (int s_ = 0; s_ < kKfAcc; ++s_) {  // arm every accumulator: zero, then the first "drained" arrive
+                    tmem_zero<16>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + s_ * BN);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(bar_tempty + 8 * s_);
+                }
+                for (int u = cta; u < units; u += p.G1) {
+                    int b, seg, si, h0, L;
+                    decode(u, b, seg, si, h0, L);
+                    const int gx = seg * 128 + row;
+                    const bool valid = gx < p.W;
+                    for (int j = 0; j < L; ++j) {
+                        const uint32_t gj = g + j, slot = gj & 7;
+                        mbar_wait(bar_tfull + 8 * slot, (gj >> 3) & 1);
+                        tc_fence_after();
+                        uint32_t v[16];
+                        tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * BN, v);
+                        tmem_ld_wait();
+                        tmem_zero<16>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * BN);
+                        tmem_st_wait();
+                        tc_fence_before();
+                        mbar_arrive(bar_tempty + 8 * slot);
+                        if (valid) {
+                            const size_t pix = (static_cast<size_t>(b) * p.H + (h0 + j)) * p.W + gx;
+                            const float bb[3] = {b0, b1, b2};
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                const float x0 = __uint_as_float(v[c]) + bb[c];
+                                const float xt = p.x[pix * 3 + c];
+                                const float xn = p.c0 * fminf(fmaxf(x0, -1.0f), 1.0f) + p.c1 * xt;
+                                p.x[pix * 3 + c] = xn;
+                                p.xpad[pix * 64 + c] = to_act(xn);
+                                if (p.x0_out) p.x0_out[pix * 3 + c] = x0;
+                            }
+                        }
+                    }
+                    g += L;
+                }
+            }
+        } else {
+            constexpr int HC = BN / 2;                             // columns per thread
+            constexpr int GH = (EPI == EPI_STATS) ? HC / CPG : 1;  // groups per thread
+            static_assert(HC == 32 || HC == 16, "BN must be 64 or 32");
+            float bias_r[HC];
+#pragma unroll
+            for (int c = 0; c < HC; ++c) bias_r[c] = bias_s[half * HC + c];
+            const bool store_leader = warp == 4 && lane == 0;
+            for (int s_ = 0; s_ < kKfAcc; ++s_) {  // arm every accumulator: zero, then the first "drained" arrive
+                tmem_zero<HC>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + s_ * BN + half * HC);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(bar_tempty + 8 * s_);
+            }
+            for (int u = cta; u < units; u += p.G1, ++unit_ctr) {
+                int b, seg, si, h0, L;
+                decode(u, b, seg, si, h0, L);
+                const int gx = seg * 128 + row;
+                const bool valid = gx < p.W;
+                const float msk = valid ? 1.0f : 0.0f;
+                float gs[GH], gq[GH];
+#pragma unroll
+                for (int i = 0; i < GH; ++i) gs[i] = gq[i] = 0.0f;
+                for (int j = 0; j < L; ++j, ++tile_ctr) {
+                    const uint32_t gj = g + j, slot = gj & 7;
+                    long long* edbg = (p.dbg != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0 && u == cta && j < 30) ? p.dbg + 256 + j * 8 : nullptr;
+                    if (edbg) edbg[0] = clock64();
+                    mbar_wait(bar_tfull + 8 * slot, (gj >> 3) & 1);
+                    tc_fence_after();
+                    if (edbg) edbg[1] = clock64();
+                    if (p.dbg != nullptr && p.dbg[511] == 1) {  // tools only: MMA phase without epilogue work
+                        tmem_zero<HC>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * BN + half * HC);
+                        tmem_st_wait();
+                        tc_fence_before();
+                        mbar_arrive(bar_tempty + 8 * slot);
+                        continue;
+                    }
+                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * BN + half * HC;
+                    uint32_t v[HC];
+                    if constexpr (HC == 32) tmem_ld32(taddr, v);
+                    else tmem_ld16(taddr, v);
+                    tmem_ld_wait();
+                    tmem_zero<HC>(taddr);  // re-arm the slot: every MMA accumulates
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(bar_tempty + 8 * slot);
+                    if (edbg) edbg[2] = clock64();
+                    float f[HC];
+#pragma unroll
+                    for (int c = 0; c < HC; ++c) f[c] = __uint_as_float(v[c]) + bias_r[c];
+                    if constexpr (EPI == EPI_STATS) {
+#pragma unroll
+                        for (int c = 0; c < HC; ++c) {
+                            const float x = f[c] * msk;
+                            gs[c / CPG] += x;
+                            gq[c / CPG] = fmaf(x, x, gq[c / CPG]);
+                        }
+                    }
+                    uint4 o[HC / 8];
+#pragma unroll
+                    for (int s4 = 0; s4 < HC / 8; ++s4) {
+                        o[s4].x = pack_act2(f[s4 * 8 + 0], f[s4 * 8 + 1]);
+                        o[s4].y = pack_act2(f[s4 * 8 + 2], f[s4 * 8 + 3]);
+                        o[s4].z = pack_act2(f[s4 * 8 + 4], f[s4 * 8 + 5]);
+                        o[s4].w = pack_act2(f[s4 * 8 + 6], f[s4 * 8 + 7]);
+                    }
+                    if (edbg) edbg[3] = clock64();
+                    if constexpr (STAGE) {
+                        // 128 pixel rows x 128 B, 128-byte swizzle: 16-byte chunk c of row r sits at chunk c ^ (r & 7)
+                        const uint32_t sb = stage + (tile_ctr & 1) * (128 * BN * 2) + row * 128;
+#pragma unroll
+                        for (int s4 = 0; s4 < HC / 8; ++s4) {
+                            const uint32_t c = half * (HC / 8) + s4;
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + ((c ^ (row & 7)) << 4)), "r"(o[s4].x),
+                                         "r"(o[s4].y), "r"(o[s4].z), "r"(o[s4].w)
+                                         : "memory");
+                        }
+                        fence_proxy_async_smem();
+                        if (edbg) edbg[4] = clock64();
+                        if (store_leader) bulk_wait_group_read<0>();  // the previous row's store has left its buffer
+                        named_bar_sync(1, kEpiThreads);
+                        if (edbg) edbg[5] = clock64();
+                        if (store_leader) {
+                            tma_store_4d(&p.omap, stage + (tile_ctr & 1) * (128 * BN * 2), nt * BN, seg * 128, h0 + j, b);
+                            bulk_commit_group();
+                        }
+                    } else if (valid) {
+                        const size_t pix = (static_cast<size_t>(b) * p.H + (h0 + j)) * p.W + gx;
+                        uint4* dst = reinterpret_cast<uint4*>(p.out + pix * p.ldc + nt * BN + half * HC);
+#pragma unroll
+                        for (int s4 = 0; s4 < HC / 8; ++s4) dst[s4] = o[s4];
+                    }
+                    if (edbg) edbg[6] = clock64();
+                }
+                g += L;
+                if constexpr (EPI == EPI_STATS) {
+                    // one fixed-order partial per (strip, group): warp butterfly -> 4 lane quarters through smem
+                    const float ws = warp_group_reduce<GH>(gs, lane);
+                    const float wq = warp_group_reduce<GH>(gq, lane);
+                    constexpr int REP = 32 / GH;
+                    float* red = red_s + (unit_ctr & 1) * (8 * 16 * 2);
+                    if ((lane & (REP - 1)) == 0) {
+                        const int gl = lane / REP;
+                        red[((half * 4 + q) * 16 + gl) * 2 + 0] = ws;
+                        red[((half * 4 + q) * 16 + gl) * 2 + 1] = wq;
+                    }
+                    named_bar_sync(2, kEpiThreads);
+                    const int t = (half * 4 + q) * 32 + lane;
+                    if (t < 2 * GH) {
+                        const int hh = t / GH, gl = t % GH;
+                        const float* r0 = red + ((hh * 4) * 16 + gl) * 2;
+                        const float s = ((r0[0] + r0[32]) + r0[64]) + r0[96];
+                        const float s2 = ((r0[1] + r0[33]) + r0[65]) + r0[97];
+                        float* dst = p.stats + ((static_cast<size_t>(b) * (p.nseg * p.S) + seg * p.S + si) * 32 + nt * (BN / CPG)) * 2;
+                        dst[t * 2 + 0] = s;
+                        dst[t * 2 + 1] = s2;
+                    }
+                }
+            }
+            if (STAGE && store_leader) bulk_wait_group<0>();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+// (BN, CPG, EPI, CH, STAGED) instantiations: the layer shapes of the UNet / context net this variant serves.
+#define KF_ALL_CASES()                    \
+    KF_CASE(64, 2, EPI_STATS, 1, true)    \
+    KF_CASE(64, 2, EPI_STATS, 1, false)   \
+    KF_CASE(64, 2, EPI_STATS, 2, false)   \
+    KF_CASE(64, 4, EPI_STATS, 1, true)    \
+    KF_CASE(64, 4, EPI_STATS, 2, false)   \
+    KF_CASE(64, 1, EPI_STORE, 1, true)    \
+    KF_CASE(64, 1, EPI_STORE, 2, false)   \
+    KF_CASE(16, 1, EPI_DDIM, 1, false)
+
+int kf_smem_bytes(int bn, int CH, int NS, bool staged) {
+    return 1024 + NS * kKfRowBytes + 9 * CH * bn * 128 + (staged ? 2 * 128 * bn * 2 : 0) + kKfAux;
+}
+
+bool kf_plan(int bn, int CH, int* NS, bool* staged) {
+    const int limit = 227 * 1024;
+    static const bool nostage = getenv("CDC_KF_NOSTAGE") != nullptr;  // experiment switch
+    for (int st = nostage ? 0 : 1; st >= 0; --st) {  // NS = ring slots of one (row, chunk) each
+        if (st && bn != 64) continue;
+        for (int ns = 4; ns >= 3; --ns)
+            if (kf_smem_bytes(bn, CH, ns, st != 0) <= limit) {
+                *NS = ns;
+                *staged = st != 0;
+                return true;
+            }
+    }
+    return false;
+}
+
+bool kf_inst_ok(int bn, int cpg, int epi, int CH) {
+    int ns;
+    bool st;
+    if (!kf_plan(bn, CH, &ns, &st)) return false;
+#define KF_CASE(BN_, CPG_, EPI_, CH_, ST_) \
+    if (bn == BN_ && (EPI_ != EPI_STATS || cpg == CPG_) && epi == EPI_ && CH == CH_ && st == ST_) return true;
+    KF_ALL_CASES()
+#undef KF_CASE
+    return false;
+}
+
+cudaError_t configure_kf_kernels() {
+    cudaError_t e;
+#define KF_CASE(BN_, CPG_, EPI_, CH_, ST_)                                                                  \
+    if ((e = cudaFuncSetAttribute(conv_kf_kernel<BN_, CPG_, EPI_, CH_, ST_>,                                  \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) \
+        return e;
+    KF_ALL_CASES()
+#undef KF_CASE
+    return cudaSuccess;
+}
+
+cudaError_t launch_conv_kf(const KfParams& p, int bn, int cpg, int epi, int CH, bool pdl, cudaStream_t stream) {
+    int ns;
+    bool st;
+    if (!kf_plan(bn, CH, &ns, &st) || ns != p.NS) return cudaErrorInvalidValue;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(p.n_tiles * p.G1);
+    cfg.blockDim = dim3(128 + kEpiThreads);
+    cfg.dynamicSmemBytes = kf_smem_bytes(bn, CH, ns, st);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+#define KF_CASE(BN_, CPG_, EPI_, CH_, ST_)                                                          \
+    if (bn == BN_ && (EPI_ != EPI_STATS || cpg == CPG_) && epi == EPI_ && CH == CH_ && st == ST_)     \
+        return cudaLaunchKernelEx(&cfg, conv_kf_kernel<BN_, CPG_, EPI_, CH_, ST_>, p);
+    KF_ALL_CASES()
+#undef KF_CASE
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace cdc

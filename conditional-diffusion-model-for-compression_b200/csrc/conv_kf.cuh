@@ -1,0 +1,35 @@
+// Parameter block of the kh-fused strip conv (conv_kf.cu): 3x3 / stride 1, resident weights.
+#pragma once
+#include "conv_tc.cuh"
+
+namespace cdc {
+
+struct alignas(64) KfParams {
+    CUtensorMap amap[2];  // activation sources, box {64 ch, 130 px, 1 row, 1 image}
+    CUtensorMap wmap;     // weights [n_pad][9 * CH * 64] K-major, box {64, BN}
+    CUtensorMap omap;     // output, box {BN ch, 128 px, 1 row, 1 image} (staged TMA store only)
+    int chunks0;          // 64-channel chunks that come from source 0 (the rest from source 1)
+    int H, W, batch;
+    int nseg;             // ceil(W / 128) column segments
+    int S;                // strips per column (rows are spread evenly over them)
+    int NS;               // input-row ring slots
+    int n_tiles;          // N tiles of BN output channels; every CTA keeps ONE tile's weights resident
+    int G1;               // CTAs per N tile (grid = n_tiles * G1)
+    int ldc;              // channels of the output tensor
+    act_t* out;
+    const float* bias;    // [n_tiles * BN]
+    float* stats;         // EPI_STATS: [batch][nseg * S][32][2], one partial row per strip
+    float* x;             // EPI_DDIM (see ConvParams)
+    act_t* xpad;
+    float* x0_out;
+    float c0, c1;
+    long long* dbg;       // optional: issuer / epilogue timeline of CTA 0 (clock64 stamps), tools only
+};
+
+bool kf_inst_ok(int bn, int cpg, int epi, int CH);
+bool kf_plan(int bn, int CH, int* NS, bool* staged);  // shared-memory plan; false if the weights do not fit
+int kf_smem_bytes(int bn, int CH, int NS, bool staged);
+cudaError_t configure_kf_kernels();
+cudaError_t launch_conv_kf(const KfParams& p, int bn, int cpg, int epi, int CH, bool pdl, cudaStream_t stream);
+
+}  // namespace cdc

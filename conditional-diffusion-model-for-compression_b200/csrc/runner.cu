@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "../../include/cdc_b200.h"
+#include "conv_kf.cuh"
 #include "conv_strip.cuh"
 #include "conv_tc.cuh"
 #include "kernels.cuh"
@@ -26,6 +27,7 @@
 namespace cdc {
 
 static std::string g_create_err;
+static bool g_pdl = false;  // launch with programmatic stream serialization (set while building / capturing the graph)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -169,6 +171,41 @@ static void conv_geometry(const ConvBuild& cb, int& gw, int& gh, int& nphase, in
     tiles_h = (gh + BH - 1) / BH;
 }
 
+
+// ---- kh-fused strip variant (conv_kf.cu): 3x3, stride 1, resident weights, N tiles of 64 (16 for the final conv) ----
+struct KfGeom {
+    int bn, CH, n_tiles, nseg, S, G1, NS;
+    bool staged;
+};
+static bool kf_disabled() {
+    static int v = -1;
+    if (v < 0) v = getenv("CDC_NO_KF") ? 1 : 0;
+    return v == 1;
+}
+static bool conv_uses_kf(const ConvBuild& cb, int B, int num_sms, KfGeom* g) {
+    if (kf_disabled() || cb.mode != MODE_S1 || cb.ksize != 3 || cb.force_bn != 0 || cb.residual) return false;
+    const int gw = cb.srcs[0].W, gh = cb.srcs[0].H;
+    if (!(gw >= 128 && (gw % 128 == 0 || gw >= 512))) return false;
+    int ctot = 0;
+    for (const Act& a : cb.srcs) ctot += a.C;
+    g->CH = ctot / 64;
+    g->bn = cb.epi == EPI_DDIM ? 16 : 64;
+    if (cb.w->n_pad % g->bn) return false;
+    g->n_tiles = cb.w->n_pad / g->bn;
+    if (cb.epi == EPI_DDIM && g->n_tiles != 1) return false;
+    if (!kf_inst_ok(g->bn, cb.cpg, cb.epi, g->CH) || !kf_plan(g->bn, g->CH, &g->NS, &g->staged)) return false;
+    g->nseg = (gw + 127) / 128;
+    const int cols = B * g->nseg;  // independent strip columns per N tile
+    int G1 = num_sms / g->n_tiles;
+    if (G1 < 1) G1 = 1;
+    int S = G1 / cols;
+    if (S < 1) S = 1;
+    if (S > gh) S = gh;
+    g->S = S;
+    g->G1 = cols * S < G1 ? cols * S : G1;
+    return true;
+}
+
 static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::string* err) {
     auto fail = [&](const std::string& m) {
         *err = "conv " + cb.name + ": " + m;
@@ -194,6 +231,61 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
     const int OH = cb.mode == MODE_UP2 ? 2 * gh : gh, OW = cb.mode == MODE_UP2 ? 2 * gw : gw;
     if (cb.epi != EPI_DDIM && (cb.out.H != OH || cb.out.W != OW || cb.out.C != w.n_pad))
         return fail("output tensor shape mismatch");
+
+
+    // ---- kh-fused strip variant (conv_kf.cu) ----
+    {
+        KfGeom kg;
+        if (conv_uses_kf(cb, B, num_sms, &kg)) {
+            auto kp = std::shared_ptr<KfParams>(new KfParams());
+            memset(kp.get(), 0, sizeof(KfParams));
+            for (size_t s = 0; s < cb.srcs.size(); ++s) {
+                const Act& a = cb.srcs[s];
+                if (encode_act_map(&kp->amap[s], a.p, a.C, a.W, a.H, B, static_cast<size_t>(a.C),
+                                   static_cast<size_t>(a.W) * a.C, static_cast<size_t>(a.H) * a.W * a.C, 130, 1))
+                    return fail("cuTensorMapEncodeTiled (kf activation) failed");
+            }
+            if (encode_w_map(&kp->wmap, w.w, w.taps * w.c_pad, w.n_pad, kg.bn)) return fail("cuTensorMapEncodeTiled (weights) failed");
+            if (kg.staged &&
+                encode_act_map(&kp->omap, cb.out.p, cb.out.C, cb.out.W, cb.out.H, B, static_cast<size_t>(cb.out.C),
+                               static_cast<size_t>(cb.out.W) * cb.out.C, static_cast<size_t>(cb.out.H) * cb.out.W * cb.out.C, 128, 1))
+                return fail("cuTensorMapEncodeTiled (kf output) failed");
+            kp->chunks0 = cb.srcs[0].C / 64;
+            kp->H = gh;
+            kp->W = gw;
+            kp->batch = B;
+            kp->nseg = kg.nseg;
+            kp->S = kg.S;
+            kp->NS = kg.NS;
+            kp->n_tiles = kg.n_tiles;
+            kp->G1 = kg.G1;
+            kp->ldc = cb.epi == EPI_DDIM ? 3 : cb.out.C;
+            kp->out = cb.out.p;
+            kp->bias = w.bias;
+            kp->stats = cb.stats;
+            kp->x = cb.x;
+            kp->xpad = cb.xpad;
+            kp->x0_out = cb.x0_out;
+            kp->dbg = cb.dbg;
+            const double Ms = static_cast<double>(B) * gh * gw;
+            op->name = cb.name;
+            op->flops = 2.0 * Ms * w.n_true * (9.0 * w.c_true);
+            op->bytes = 2.0 * (Ms * w.c_true + Ms * w.n_true + 9.0 * w.c_true * w.n_true);
+            const int epi = cb.epi, cpg = cb.cpg, bn_k = kg.bn, CHk = kg.CH;
+            const std::vector<float>*c0 = cb.c0, *c1 = cb.c1;
+            op->run = [kp, bn_k, cpg, epi, CHk, c0, c1](cudaStream_t s, int k) -> cudaError_t {
+                if (epi == EPI_DDIM) {
+                    if (!c0 || k < 0 || k >= static_cast<int>(c0->size())) return cudaErrorInvalidValue;
+                    KfParams q = *kp;
+                    q.c0 = (*c0)[k];
+                    q.c1 = (*c1)[k];
+                    return launch_conv_kf(q, bn_k, cpg, epi, CHk, g_pdl, s);
+                }
+                return launch_conv_kf(*kp, bn_k, cpg, epi, CHk, g_pdl, s);
+            };
+            return CDC_OK;
+        }
+    }
 
     // ---- strip variant (conv_strip.cu): 3x3, stride 1, one N tile, image at least one segment wide ----
     {
@@ -410,9 +502,11 @@ static bool conv_uses_strip(const ConvBuild& cb) {
            strip_inst_ok(bn_s, cb.cpg, cb.epi, ctot / 64, NSW == 0);
 }
 
-static int conv_num_partials(const ConvBuild& cb) {
+static int conv_num_partials(const ConvBuild& cb, int B, int num_sms) {
     int gw, gh, nphase, os, bwl, tw, th;
     conv_geometry(cb, gw, gh, nphase, os, bwl, tw, th);
+    KfGeom kg;
+    if (conv_uses_kf(cb, B, num_sms, &kg)) return kg.nseg * kg.S;
     if (conv_uses_strip(cb)) return gh * ((gw + 127) / 128);
     return nphase * tw * th;
 }
@@ -651,7 +745,7 @@ struct PlanB {
         c1.cpg = cpg;
         c1.stats = ctx->partials;
         conv(c1);
-        gn(name + ".gn1", wp + ".gn1", film_idx, conv_num_partials(c1), t1, nullptr, t1, true);
+        gn(name + ".gn1", wp + ".gn1", film_idx, conv_num_partials(c1, ctx->B, ctx->num_sms), t1, nullptr, t1, true);
         ConvBuild c2;
         c2.name = name + ".conv2";
         c2.srcs = {t1};
@@ -673,7 +767,7 @@ struct PlanB {
             conv(cr);
             resp = r.p;
         }
-        gn(name + ".gn2", wp + ".gn2", -1, conv_num_partials(c2), t2, resp, out, true);
+        gn(name + ".gn2", wp + ".gn2", -1, conv_num_partials(c2, ctx->B, ctx->num_sms), t2, resp, out, true);
     }
 };
 
@@ -905,7 +999,8 @@ int cdc_create(const cdc_config* cfg, int device, cdc_ctx** out) {
         g_create_err = "cuTensorMapEncodeTiled entry point not found";
         return CDC_ERR_CUDA;
     }
-    if ((e = configure_conv_kernels()) != cudaSuccess || (e = configure_strip_kernels()) != cudaSuccess) {
+    if ((e = configure_conv_kernels()) != cudaSuccess || (e = configure_strip_kernels()) != cudaSuccess ||
+        (e = configure_kf_kernels()) != cudaSuccess) {
         g_create_err = std::string("cudaFuncSetAttribute(conv kernels): ") + cudaGetErrorString(e);
         return CDC_ERR_CUDA;
     }
@@ -1272,7 +1367,7 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
         g_create_err = "not an sm_100 device";
         return CDC_ERR_ARCH;
     }
-    if (configure_conv_kernels() != cudaSuccess || configure_strip_kernels() != cudaSuccess) {
+    if (configure_conv_kernels() != cudaSuccess || configure_strip_kernels() != cudaSuccess || configure_kf_kernels() != cudaSuccess) {
         g_create_err = "cudaFuncSetAttribute(conv kernels) failed";
         return CDC_ERR_CUDA;
     }
@@ -1312,7 +1407,7 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
         cb.epi = EPI_STATS;
         cb.cpg = cout / 32;
         cb.stats = stats;
-        if (pt_out) *pt_out = conv_num_partials(cb);
+        if (pt_out) *pt_out = conv_num_partials(cb, B, prop.multiProcessorCount);
     }
     long long* dbg = nullptr;
     if (getenv("CDC_STRIP_DEBUG")) {
@@ -1331,6 +1426,22 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
     }
     cudaError_t ce = op.run(S(s), 0);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(S(s));
+    KfGeom kgd;
+    if (dbg && conv_uses_kf(cb, B, prop.multiProcessorCount, &kgd)) {
+        printf("kf issuer timeline (CTA 0, first strip; S=%d NS=%d staged=%d): row: issue_a wait_next issue_b | since previous row start\n", kgd.S,
+               kgd.NS, kgd.staged ? 1 : 0);
+        for (int i = 0; i < 40 && dbg[i * 4 + 3]; ++i)
+            printf("  %2d: %6lld %6lld %6lld | %6lld\n", i, dbg[i * 4 + 1] - dbg[i * 4 + 0], dbg[i * 4 + 2] - dbg[i * 4 + 1],
+                   dbg[i * 4 + 3] - dbg[i * 4 + 2], i ? dbg[i * 4 + 0] - dbg[(i - 1) * 4 + 0] : 0LL);
+        printf("kf epilogue warp 4 timeline: tile: wait_tfull ldtm math sts+fence bar tma | total, since previous\n");
+        for (int i = 0; i < 30 && dbg[256 + i * 8 + 1]; ++i) {
+            const long long* e = dbg + 256 + i * 8;
+            printf("  %2d: %6lld %6lld %6lld %6lld %6lld %6lld | %6lld %6lld\n", i, e[1] - e[0], e[2] - e[1], e[3] - e[2], e[4] - e[3],
+                   e[5] - e[4], e[6] - e[5], e[6] - e[0], i ? e[0] - (e - 8)[0] : 0LL);
+        }
+        cudaFree(dbg);
+        dbg = nullptr;
+    }
     if (dbg) {
         printf("strip issuer timeline (CTA 0): row: wait_tempty wait_row mma+commit | since previous row start\n");
         for (int i = 0; i < 24 && dbg[i * 4 + 3]; ++i)

@@ -103,6 +103,14 @@ CONV_CASES = [
     ("strip_c128_n128", 2, 32, 128, [128], 128, 3, 0, 0),
     ("strip_c64+128_n128_streamed", 1, 48, 256, [64, 128], 128, 3, 0, 0),
     ("same_shape_through_conv_tc", 1, 64, 256, [64], 64, 3, 0, -1),
+    # kh-fused strip variant (conv_kf.cu): ragged last segment, 1-row strips, long strips (accumulator ring wraps),
+    # several units per CTA, two N tiles with two input chunks
+    ("kf_ragged_w640", 1, 20, 640, [64], 64, 3, 0, 0),
+    ("kf_two_rows", 1, 2, 256, [64], 64, 3, 0, 0),
+    ("kf_long_strips", 8, 40, 1024, [64], 64, 3, 0, 0),
+    ("kf_units_gt_ctas", 40, 16, 512, [64], 64, 3, 0, 0),
+    ("kf_c128_n128_two_tiles", 1, 96, 384, [128], 128, 3, 0, 0),
+    ("kf_dual_64+64_long", 2, 130, 256, [64, 64], 64, 3, 0, 0),
 ]
 
 
@@ -126,13 +134,15 @@ def test_conv_residual_epilogue():
     _check(o, _ref_conv(srcs, w, b, 1, 0, residual=r), "residual")
 
 
-@pytest.mark.parametrize("cfg", [(64, 2, 70, 256, 0), (128, 1, 32, 128, 0), (64, 1, 64, 128, -1), (64, 1, 64, 128, 0), (128, 2, 32, 64, 0), (128, 1, 16, 16, 64), (192, 1, 32, 32, 0),
+@pytest.mark.parametrize("cfg", [(64, 2, 70, 256, 0), (128, 1, 32, 128, 0), (64, 8, 40, 1024, 0), (64, 40, 16, 512, 0), (128, 1, 96, 384, 0, 128),
+                                 (64, 1, 50, 640, 0, 128), (64, 1, 64, 128, -1), (64, 1, 64, 128, 0), (128, 2, 32, 64, 0), (128, 1, 16, 16, 64), (192, 1, 32, 32, 0),
                                  (256, 1, 16, 32, 256), (256, 1, 16, 16, 128), (256, 1, 16, 16, 64),
                                  (64, 1, 24, 48, 0)])
 def test_conv_groupnorm_partials(cfg):
-    cout, B, H, W, fbn = cfg
-    srcs = [_mk((B, 64, H, W), 5)]
-    w = _mk((cout, 64, 3, 3), 6, scale=1 / 24.0)
+    cout, B, H, W, fbn = cfg[:5]
+    cin = cfg[5] if len(cfg) > 5 else 64
+    srcs = [_mk((B, cin, H, W), 5)]
+    w = _mk((cout, cin, 3, 3), 6, scale=1 / (3.0 * np.sqrt(cin)))
     b = _mk((cout,), 7)
     o, part = _run_conv(srcs, w, b, 3, 0, fbn, stats=True)
     ref = _ref_conv(srcs, w, b, 3, 0)
