@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcdc_b200.so")
+LIB_PATH = os.environ.get("CDC_LIB_PATH") or os.path.join(_HERE, "libcdc_b200.so")  # override: A/B builds in tools/
 
 # every symbol include/cdc_b200.h declares
 SYMBOLS = [

@@ -3,6 +3,7 @@
 // legacy mma.sync tensor path (attention is 0.25 % of step FLOPs at 768x512; K-conv is the
 // tcgen05 kernel).  Oracle counterpart: oracle/unet.py Attn.forward.
 #include "kernels.cuh"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace cdc {
@@ -37,6 +38,8 @@ __global__ void __launch_bounds__(128) attention_kernel(const act_t* __restrict_
     const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kAttBQ;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const act_t* base = qkv + static_cast<size_t>(b) * N * ld + h * kAttD;
+    pdl_launch_dependents();
+    pdl_wait();  // qkv is written by the preceding conv (it is only read through cp.async below)
 
     auto load_tile = [&](act_t (*dst)[kAttPitch], const act_t* src, int row0) {
         for (int i = tid; i < 64 * 8; i += 128) {
@@ -166,8 +169,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const act_t* __restrict_
 
 cudaError_t launch_attention(const act_t* qkv, act_t* o, int B, int N, int heads, cudaStream_t s) {
     dim3 grid((N + kAttBQ - 1) / kAttBQ, heads, B);
-    attention_kernel<<<grid, 128, 0, s>>>(qkv, o, N, heads);
-    return cudaGetLastError();
+    return launch_pdl(attention_kernel, grid, dim3(128), 0, s, qkv, o, N, heads);
 }
 
 }  // namespace cdc

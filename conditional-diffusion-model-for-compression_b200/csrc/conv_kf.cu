@@ -33,6 +33,7 @@
 
 #include "conv_epilogue.cuh"
 #include "conv_kf.cuh"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace cdc {
@@ -46,7 +47,7 @@ template <int BN, int CPG, int EPI, int CH, bool STAGE>
 __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __grid_constant__ KfParams p) {
     constexpr int WB = BN * 128;  // one (tap, chunk) weight block
     constexpr uint32_t WB16 = WB >> 4;
-    constexpr int TMEM_COLS = kKfAcc * BN < 32 ? 32 : kKfAcc * BN;
+    constexpr int TMEM_COLS = kKfAcc * BN <= 128 ? 128 : kKfAcc * BN <= 256 ? 256 : 512;  // power of two
     constexpr int STAGE_BYTES = STAGE ? 2 * 128 * BN * 2 : 0;
     static_assert(!STAGE || BN == 64, "staged TMA store is built for 128-byte output rows");
 
@@ -68,6 +69,13 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nt = blockIdx.x / p.G1, cta = blockIdx.x % p.G1;
+    const bool kdbg = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 32;
+    if (kdbg) {
+        p.dbg[500] = clock64();
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        p.dbg[508] = static_cast<long long>(gt);
+    }
     const int units = p.batch * p.nseg * p.S;
 
     if (warp == 0 && lane == 0) {
@@ -96,6 +104,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    if (kdbg) p.dbg[501] = clock64();
 
     if (warp == 3 && lane == 0) {
         // Weights are constants: their load need not wait for the preceding kernel (PDL).
@@ -165,12 +174,15 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
             const uint32_t wlo = wbase >> 4;
             uint32_t rslot = 0, rpar = 0;
             uint32_t g = 0;  // running output-row counter: row j of the current strip uses accumulator (g + j) & 7
+            if (kdbg) p.dbg[502] = clock64();
             mbar_wait(bar_wres, 0);
+            if (kdbg) p.dbg[503] = clock64();
             for (int u = cta; u < units; u += p.G1) {
                 int b, seg, si, h0, L;
                 decode(u, b, seg, si, h0, L);
                 mbar_wait(bar_rfull + 8 * rslot, rpar);  // first chunk of the strip
                 tc_fence_after();
+                if (kdbg && u == cta) p.dbg[504] = clock64();
                 for (int i = 0; i < L + 2; ++i) {
                     const int jlo = i >= 2 ? i - 2 : 0;
                     const int jhi = i < L ? i : L - 1;
@@ -229,6 +241,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
                 }
                 g += L;
             }
+            if (kdbg) p.dbg[505] = clock64();
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------ epilogue (8 warps)
@@ -281,7 +294,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
         } else {
             constexpr int HC = BN / 2;                             // columns per thread
             constexpr int GH = (EPI == EPI_STATS) ? HC / CPG : 1;  // groups per thread
-            static_assert(HC == 32 || HC == 16, "BN must be 64 or 32");
+            static_assert(HC == 32 || HC == 24 || HC == 16, "BN must be 64, 48 or 32");
             float bias_r[HC];
 #pragma unroll
             for (int c = 0; c < HC; ++c) bias_r[c] = bias_s[half * HC + c];
@@ -317,8 +330,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
                     }
                     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * BN + half * HC;
                     uint32_t v[HC];
-                    if constexpr (HC == 32) tmem_ld32(taddr, v);
-                    else tmem_ld16(taddr, v);
+                    tmem_ld_cols<HC>(taddr, v);
                     tmem_ld_wait();
                     tmem_zero<HC>(taddr);  // re-arm the slot: every MMA accumulates
                     tmem_st_wait();
@@ -403,6 +415,12 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
 
     tc_fence_before();
     __syncthreads();
+    if (kdbg) {
+        p.dbg[506] = clock64();
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        p.dbg[509] = static_cast<long long>(gt);
+    }
     if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
@@ -410,12 +428,15 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
 // (BN, CPG, EPI, CH, STAGED) instantiations: the layer shapes of the UNet / context net this variant serves.
 #define KF_ALL_CASES()                    \
     KF_CASE(64, 2, EPI_STATS, 1, true)    \
-    KF_CASE(64, 2, EPI_STATS, 1, false)   \
     KF_CASE(64, 2, EPI_STATS, 2, false)   \
     KF_CASE(64, 4, EPI_STATS, 1, true)    \
     KF_CASE(64, 4, EPI_STATS, 2, false)   \
     KF_CASE(64, 1, EPI_STORE, 1, true)    \
     KF_CASE(64, 1, EPI_STORE, 2, false)   \
+    KF_CASE(32, 4, EPI_STATS, 3, false)   \
+    KF_CASE(32, 4, EPI_STATS, 4, false)   \
+    KF_CASE(48, 6, EPI_STATS, 3, false)   \
+    KF_CASE(32, 8, EPI_STATS, 4, false)   \
     KF_CASE(16, 1, EPI_DDIM, 1, false)
 
 int kf_smem_bytes(int bn, int CH, int NS, bool staged) {
@@ -459,23 +480,15 @@ cudaError_t configure_kf_kernels() {
     return cudaSuccess;
 }
 
-cudaError_t launch_conv_kf(const KfParams& p, int bn, int cpg, int epi, int CH, bool pdl, cudaStream_t stream) {
+cudaError_t launch_conv_kf(const KfParams& p, int bn, int cpg, int epi, int CH, cudaStream_t stream) {
     int ns;
     bool st;
     if (!kf_plan(bn, CH, &ns, &st) || ns != p.NS) return cudaErrorInvalidValue;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(p.n_tiles * p.G1);
-    cfg.blockDim = dim3(128 + kEpiThreads);
-    cfg.dynamicSmemBytes = kf_smem_bytes(bn, CH, ns, st);
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
+    const dim3 grid(p.n_tiles * p.G1), block(128 + kEpiThreads);
+    const size_t smem = kf_smem_bytes(bn, CH, ns, st);
 #define KF_CASE(BN_, CPG_, EPI_, CH_, ST_)                                                          \
     if (bn == BN_ && (EPI_ != EPI_STATS || cpg == CPG_) && epi == EPI_ && CH == CH_ && st == ST_)     \
-        return cudaLaunchKernelEx(&cfg, conv_kf_kernel<BN_, CPG_, EPI_, CH_, ST_>, p);
+        return launch_pdl(conv_kf_kernel<BN_, CPG_, EPI_, CH_, ST_>, grid, block, smem, stream, p);
     KF_ALL_CASES()
 #undef KF_CASE
     return cudaErrorInvalidValue;

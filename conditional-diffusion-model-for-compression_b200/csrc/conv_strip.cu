@@ -22,6 +22,7 @@
 
 #include "conv_epilogue.cuh"
 #include "conv_strip.cuh"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace cdc {
@@ -91,6 +92,8 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_strip_kernel(const 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_launch_dependents();
+    pdl_wait();
 
     auto decode = [&](int u, int& b, int& seg, int& h0, int& h1) {
         const int si = u % p.strips_per_col;
@@ -355,8 +358,7 @@ cudaError_t launch_conv_strip(const StripParams& p, int bn, int cpg, int epi, in
     const bool resident = p.NSW == 0;
 #define STRIP_CASE(BN_, CPG_, EPI_, CH_, RES_)                                                                \
     if (bn == BN_ && (EPI_ != EPI_STATS || cpg == CPG_) && epi == EPI_ && p.CH == CH_ && resident == RES_) {  \
-        conv_strip_kernel<BN_, CPG_, EPI_, CH_, RES_><<<grid, 128 + kEpiThreads, smem, stream>>>(p);          \
-        return cudaGetLastError();                                                                           \
+        return launch_pdl(conv_strip_kernel<BN_, CPG_, EPI_, CH_, RES_>, dim3(grid), dim3(128 + kEpiThreads), smem, stream, p); \
     }
     STRIP_ALL_CASES()
 #undef STRIP_CASE

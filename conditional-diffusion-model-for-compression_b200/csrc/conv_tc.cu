@@ -17,6 +17,7 @@
 
 #include "conv_epilogue.cuh"
 #include "conv_tc.cuh"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace cdc {
@@ -86,6 +87,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_launch_dependents();
+    pdl_wait();  // the prologue above overlapped the preceding kernel's tail
 
     auto decode = [&](int tile, int& nt, int& ph, int& b, int& th, int& tw) {
         nt = tile % p.n_tiles;
@@ -200,8 +203,7 @@ static cudaError_t launch_one(const ConvParams& p, int num_sms, cudaStream_t str
     auto kern = conv_tc_kernel<BN, CPG, EPI>;
     const int total = p.n_tiles * p.nphase * p.batch * p.tiles_h * p.tiles_w;
     const int grid = total < num_sms ? total : num_sms;
-    kern<<<grid, kConvThreads, Cfg::SMEM_BYTES, stream>>>(p);
-    return cudaGetLastError();
+    return launch_pdl(kern, dim3(grid), dim3(kConvThreads), Cfg::SMEM_BYTES, stream, p);
 }
 
 #define CDC_ALL_CASES()          \

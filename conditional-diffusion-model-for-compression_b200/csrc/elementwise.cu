@@ -2,6 +2,7 @@
 // time-embedding MLP + FiLM vectors, layout conversion at the API boundary, weight repack.
 // Oracle counterparts: oracle/unet.py RB, Attn.gn, TimeEmbed; SURVEY.md 2.2 C5, C6, C8.
 #include "kernels.cuh"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace cdc {
@@ -13,9 +14,12 @@ constexpr int kStatsPix = 64;
 
 int gn_stats_num_partials(int HW) { return (HW + kStatsPix - 1) / kStatsPix; }
 
-__global__ void __launch_bounds__(256) gn_stats_kernel(const act_t* __restrict__ x, float* __restrict__ partials,
-                                                       int HW, int C, int PT) {
+// (tensors written by the preceding kernel are read through plain pointers, not const __restrict__: under PDL the
+// kernel is resident before that data is final, so the non-coherent read-only path must not be used for them)
+__global__ void __launch_bounds__(256) gn_stats_kernel(const act_t* x, float* partials, int HW, int C, int PT) {
     __shared__ float s_sum[8][512], s_sq[8][512];  // [row-in-pass][channel] (C <= 512)
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.y, pt = blockIdx.x;
     const int vecs = C / 8;                 // uint4 per pixel
     const int rows = (256 / vecs) < 8 ? (256 / vecs) : 8;  // pixels per pass (smem rows)
@@ -74,19 +78,20 @@ cudaError_t launch_gn_stats(const act_t* x, float* partials, int B, int HW, int 
     if (C % 32 != 0 || C > 512 || C < 32) return cudaErrorInvalidValue;
     const int PT = gn_stats_num_partials(HW);
     if (PT_out) *PT_out = PT;
-    gn_stats_kernel<<<dim3(PT, B), 256, 0, s>>>(x, partials, HW, C, PT);
-    return cudaGetLastError();
+    return launch_pdl(gn_stats_kernel, dim3(PT, B), dim3(256), 0, s, x, partials, HW, C, PT);
 }
 
 // ------------------------------------------------------------------------------------------------
 // Finalize: one CTA per (group, image).  Thread t sums partials t, t+256, ... in order, then a fixed
 // shared-memory tree; double accumulation.  The CTA then writes (a, b) for its C/32 channels.
-__global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restrict__ partials, int PT,
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const float* partials, int PT,
                                                           const float* __restrict__ gamma,
                                                           const float* __restrict__ beta,
-                                                          const float* __restrict__ film, float2* __restrict__ ab,
+                                                          const float* __restrict__ film, float2* ab,
                                                           int C, int HW, float eps) {
     __shared__ double s_s[256], s_q[256];
+    pdl_launch_dependents();
+    pdl_wait();
     const int g = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
     const float2* src = reinterpret_cast<const float2*>(partials) + static_cast<size_t>(b) * PT * 32 + g;
     double s = 0.0, q = 0.0;
@@ -127,8 +132,7 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restric
 
 cudaError_t launch_gn_finalize(const float* partials, int PT, const float* gamma, const float* beta, const float* film,
                                float2* ab, int B, int C, int HW, float eps, cudaStream_t s) {
-    gn_finalize_kernel<<<dim3(32, B), 256, 0, s>>>(partials, PT, gamma, beta, film, ab, C, HW, eps);
-    return cudaGetLastError();
+    return launch_pdl(gn_finalize_kernel, dim3(32, B), dim3(256), 0, s, partials, PT, gamma, beta, film, ab, C, HW, eps);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -161,9 +165,9 @@ __device__ __forceinline__ uint4 gn_apply_vec(const uint4 u, const uint4 rr, con
 // The grid stride is a multiple of the vectors per pixel, so a thread always owns the same 8 channels:
 // its (a, b) pairs live in registers and are reloaded only when the image index changes.
 template <bool SILU, bool RES>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* __restrict__ x, const float2* __restrict__ ab,
-                                                       const uint4* __restrict__ r, uint4* __restrict__ y,
+__global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* x, const float2* ab, const uint4* r, uint4* y,
                                                        long long nvec, int vecs_per_pix, long long vecs_per_img) {
+    pdl_wait();  // (no early trigger here: see pdl_launch_dependents)
     const long long stride = gridDim.x * 256LL;
     long long i = blockIdx.x * 256LL + threadIdx.x;
     const int cv = static_cast<int>(i % vecs_per_pix);
@@ -217,15 +221,10 @@ cudaError_t launch_gn_apply(const act_t* x, const float2* ab, const act_t* r, ac
     const uint4* rv = reinterpret_cast<const uint4*>(r);
     uint4* yv = reinterpret_cast<uint4*>(y);
     const int g = static_cast<int>(grid);
-    if (silu && r)
-        gn_apply_kernel<true, true><<<g, 256, 0, s>>>(xv, ab, rv, yv, nvec, vpp, vpi);
-    else if (silu)
-        gn_apply_kernel<true, false><<<g, 256, 0, s>>>(xv, ab, rv, yv, nvec, vpp, vpi);
-    else if (r)
-        gn_apply_kernel<false, true><<<g, 256, 0, s>>>(xv, ab, rv, yv, nvec, vpp, vpi);
-    else
-        gn_apply_kernel<false, false><<<g, 256, 0, s>>>(xv, ab, rv, yv, nvec, vpp, vpi);
-    return cudaGetLastError();
+    if (silu && r) return launch_pdl(gn_apply_kernel<true, true>, dim3(g), dim3(256), 0, s, xv, ab, rv, yv, nvec, vpp, vpi);
+    if (silu) return launch_pdl(gn_apply_kernel<true, false>, dim3(g), dim3(256), 0, s, xv, ab, rv, yv, nvec, vpp, vpi);
+    if (r) return launch_pdl(gn_apply_kernel<false, true>, dim3(g), dim3(256), 0, s, xv, ab, rv, yv, nvec, vpp, vpi);
+    return launch_pdl(gn_apply_kernel<false, false>, dim3(g), dim3(256), 0, s, xv, ab, rv, yv, nvec, vpp, vpi);
 }
 
 // ------------------------------------------------------------------------------------------------

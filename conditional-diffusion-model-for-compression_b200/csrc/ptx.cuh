@@ -102,6 +102,9 @@ __device__ __forceinline__ void bulk_wait_group() {
 // Programmatic dependent launch: wait for the preceding kernel's memory to be visible / let the next
 // kernel's CTAs start their prologue.  Both are no-ops when the launch carries no PDL attribute.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Early trigger: only kernels whose dependents are small (GroupNorm finalize / apply, or a conv that cannot become
+// resident before this one's CTAs exit anyway) call this.  gn_apply does NOT: its dependent is a conv whose CTAs would
+// claim most of the register file next to the still-running apply CTAs (measured: -1.7 % when every kernel triggered).
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---------------------------------------------------------------- tcgen05 / TMEM
@@ -217,19 +220,40 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+// this warp's 32 lanes x NCOL consecutive fp32 columns (NCOL = 32, 24 or 16); follow with tmem_ld_wait()
+template <int NCOL>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[NCOL]) {
+    static_assert(NCOL == 32 || NCOL == 24 || NCOL == 16, "32, 24 or 16 columns");
+    if constexpr (NCOL == 32) {
+        tmem_ld32(taddr, v);
+    } else {
+        uint32_t(&lo)[16] = reinterpret_cast<uint32_t(&)[16]>(v);
+        tmem_ld16(taddr, lo);
+        if constexpr (NCOL == 24) tmem_ld8(taddr + 16, &v[16]);
+    }
+}
 // registers -> TMEM: zero this warp's 32 lanes x NCOL consecutive columns (re-arms an accumulator so that every
 // MMA into it can run with accumulate = 1)
 template <int NCOL>
 __device__ __forceinline__ void tmem_zero(uint32_t taddr) {
-    static_assert(NCOL == 16 || NCOL == 32, "16 or 32 columns");
+    static_assert(NCOL == 16 || NCOL == 24 || NCOL == 32, "16, 24 or 32 columns");
     const uint32_t z = 0;
+    if constexpr (NCOL == 24) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr + 16), "r"(z) : "memory");
+    }
     if constexpr (NCOL == 32) {
         asm volatile(
             "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
             "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
             "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(z)
             : "memory");
-    } else {
+    } else {  // 16, and the first 16 of 24
         asm volatile(
             "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
             "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(z)

@@ -27,7 +27,6 @@
 namespace cdc {
 
 static std::string g_create_err;
-static bool g_pdl = false;  // launch with programmatic stream serialization (set while building / capturing the graph)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -185,15 +184,24 @@ static bool kf_disabled() {
 static bool conv_uses_kf(const ConvBuild& cb, int B, int num_sms, KfGeom* g) {
     if (kf_disabled() || cb.mode != MODE_S1 || cb.ksize != 3 || cb.force_bn != 0 || cb.residual) return false;
     const int gw = cb.srcs[0].W, gh = cb.srcs[0].H;
-    if (!(gw >= 128 && (gw % 128 == 0 || gw >= 512))) return false;
+    g->nseg = (gw + 127) / 128;
+    if (gw * 100 < g->nseg * 128 * 35) return false;  // segments are 128 pixels wide: too much of the tile would be padding
     int ctot = 0;
     for (const Act& a : cb.srcs) ctot += a.C;
     g->CH = ctot / 64;
-    g->bn = cb.epi == EPI_DDIM ? 16 : 64;
-    if (cb.w->n_pad % g->bn) return false;
+    // largest N tile whose whole weight block stays resident in shared memory (and holds whole GroupNorm groups)
+    g->bn = 0;
+    const int cands[3] = {64, 48, 32};
+    for (int c : cands) {
+        const int bn = cb.epi == EPI_DDIM ? 16 : c;
+        if (cb.w->n_pad % bn || (cb.epi == EPI_STATS && bn % cb.cpg)) continue;
+        if (!kf_inst_ok(bn, cb.cpg, cb.epi, g->CH) || !kf_plan(bn, g->CH, &g->NS, &g->staged)) continue;
+        g->bn = bn;
+        break;
+    }
+    if (!g->bn) return false;
     g->n_tiles = cb.w->n_pad / g->bn;
     if (cb.epi == EPI_DDIM && g->n_tiles != 1) return false;
-    if (!kf_inst_ok(g->bn, cb.cpg, cb.epi, g->CH) || !kf_plan(g->bn, g->CH, &g->NS, &g->staged)) return false;
     g->nseg = (gw + 127) / 128;
     const int cols = B * g->nseg;  // independent strip columns per N tile
     int G1 = num_sms / g->n_tiles;
@@ -279,9 +287,9 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
                     KfParams q = *kp;
                     q.c0 = (*c0)[k];
                     q.c1 = (*c1)[k];
-                    return launch_conv_kf(q, bn_k, cpg, epi, CHk, g_pdl, s);
+                    return launch_conv_kf(q, bn_k, cpg, epi, CHk, s);
                 }
-                return launch_conv_kf(*kp, bn_k, cpg, epi, CHk, g_pdl, s);
+                return launch_conv_kf(*kp, bn_k, cpg, epi, CHk, s);
             };
             return CDC_OK;
         }
@@ -1410,11 +1418,15 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
         if (pt_out) *pt_out = conv_num_partials(cb, B, prop.multiProcessorCount);
     }
     long long* dbg = nullptr;
+    long long* dbg_dev = nullptr;
+    std::vector<long long> dbg_host(512, 0);
     if (getenv("CDC_STRIP_DEBUG")) {
-        cudaMallocManaged(&dbg, 512 * sizeof(long long));
-        memset(dbg, 0, 512 * sizeof(long long));
-        if (atoi(getenv("CDC_STRIP_DEBUG")) == 2) dbg[511] = 1;
-        cb.dbg = dbg;
+        // plain device memory (managed memory would page-fault inside the timed regions)
+        cudaMalloc(&dbg_dev, 512 * sizeof(long long));
+        std::vector<long long> init(512, 0);
+        if (atoi(getenv("CDC_STRIP_DEBUG")) == 2) init[511] = 1;
+        cudaMemcpy(dbg_dev, init.data(), 512 * sizeof(long long), cudaMemcpyHostToDevice);
+        cb.dbg = dbg_dev;
     }
     Op op;
     std::string e;
@@ -1426,6 +1438,38 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
     }
     cudaError_t ce = op.run(S(s), 0);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(S(s));
+    if (ce == cudaSuccess && getenv("CDC_TEST_CONV_REPS")) {  // tools/conv_bench.py: device time of the conv launch alone
+        const int reps = atoi(getenv("CDC_TEST_CONV_REPS"));
+        void* flush = nullptr;
+        const size_t fb = 256u << 20;  // > L2
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        float tot = 0.f, tmin = 1e30f;
+        if (cudaMalloc(&flush, fb) == cudaSuccess) {
+            for (int i = 0; i < reps && ce == cudaSuccess; ++i) {
+                cudaMemsetAsync(flush, i, fb, S(s));
+                cudaEventRecord(e0, S(s));
+                ce = op.run(S(s), 0);
+                cudaEventRecord(e1, S(s));
+                cudaStreamSynchronize(S(s));
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, e0, e1);
+                tot += ms;
+                tmin = ms < tmin ? ms : tmin;
+            }
+            cudaFree(flush);
+            printf("conv_bench: %s mean %.2f us min %.2f us over %d flushed runs, %.1f TFLOP/s (mean)\n", op.name.c_str(), 1e3 * tot / reps,
+                   1e3 * tmin, reps, op.flops / (tot / reps * 1e-3) / 1e12);
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    if (dbg_dev) {
+        cudaMemcpy(dbg_host.data(), dbg_dev, 512 * sizeof(long long), cudaMemcpyDeviceToHost);
+        cudaFree(dbg_dev);
+        dbg = dbg_host.data();
+    }
     KfGeom kgd;
     if (dbg && conv_uses_kf(cb, B, prop.multiProcessorCount, &kgd)) {
         printf("kf issuer timeline (CTA 0, first strip; S=%d NS=%d staged=%d): row: issue_a wait_next issue_b | since previous row start\n", kgd.S,
@@ -1433,13 +1477,16 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
         for (int i = 0; i < 40 && dbg[i * 4 + 3]; ++i)
             printf("  %2d: %6lld %6lld %6lld | %6lld\n", i, dbg[i * 4 + 1] - dbg[i * 4 + 0], dbg[i * 4 + 2] - dbg[i * 4 + 1],
                    dbg[i * 4 + 3] - dbg[i * 4 + 2], i ? dbg[i * 4 + 0] - dbg[(i - 1) * 4 + 0] : 0LL);
+        printf("kf CTA 0 phases (cycles): prologue %lld, to-issuer %lld, weights wait %lld, first row wait %lld, main loop %lld, drain+exit %lld\n",
+               dbg[501] - dbg[500], dbg[502] - dbg[501], dbg[503] - dbg[502], dbg[504] - dbg[503], dbg[505] - dbg[504], dbg[506] - dbg[505]);
+        printf("kf CTA 0: %lld cycles in %lld ns -> SM clock %.0f MHz\n", dbg[506] - dbg[500], dbg[509] - dbg[508],
+               1e3 * static_cast<double>(dbg[506] - dbg[500]) / static_cast<double>(dbg[509] - dbg[508]));
         printf("kf epilogue warp 4 timeline: tile: wait_tfull ldtm math sts+fence bar tma | total, since previous\n");
         for (int i = 0; i < 30 && dbg[256 + i * 8 + 1]; ++i) {
             const long long* e = dbg + 256 + i * 8;
             printf("  %2d: %6lld %6lld %6lld %6lld %6lld %6lld | %6lld %6lld\n", i, e[1] - e[0], e[2] - e[1], e[3] - e[2], e[4] - e[3],
                    e[5] - e[4], e[6] - e[5], e[6] - e[0], i ? e[0] - (e - 8)[0] : 0LL);
         }
-        cudaFree(dbg);
         dbg = nullptr;
     }
     if (dbg) {
@@ -1456,7 +1503,7 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
             printf("  %2d: %6lld | %6lld %6lld %6lld %6lld | %6lld\n", i, e[0] - e[4], e[1] - e[0], e[2] - e[1], e[3] - e[2],
                    e[5] - e[3], e[5] - e[4]);
         }
-        cudaFree(dbg);
+        
     }
     ar.release();
     if (ce != cudaSuccess) {

@@ -1,11 +1,15 @@
-"""Print the strip kernel's issuer timeline for one level-0-shaped conv (CDC_STRIP_DEBUG=1)."""
+"""Print the strip kernels' issuer / epilogue timeline for one conv (CDC_STRIP_DEBUG=1) and time the launch with CUDA
+events (second, warm call).  Usage: strip_timeline.py [cin] [cout] [H] [W]"""
 import ctypes as C, os, sys
 os.environ.setdefault("CDC_STRIP_DEBUG", "1")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from cdc_b200 import _ffi
 L = _ffi.lib()
-B, H, W, cin, cout = 1, 512, 768, int(sys.argv[1]) if len(sys.argv) > 1 else 64, int(sys.argv[2]) if len(sys.argv) > 2 else 64
+a = [int(v) for v in sys.argv[1:]]
+cin, cout = (a + [64, 64])[:2] if len(a) < 2 else a[:2]
+H, W = (a[2], a[3]) if len(a) >= 4 else (512, 768)
+B = 1
 dt = torch.float16 if L.cdc_act_dtype() == 1 else torch.bfloat16
 x = torch.randn(B, H, W, cin, device="cuda").to(dt)
 w = (torch.randn(cout, cin, 3, 3, device="cuda") / 24).float()
