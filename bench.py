@@ -236,19 +236,11 @@ def main():
     if rank == 0:
         # ---- roofline of the dominant kernel (K-conv), measured live: one denoise step op by op ----
         ops = dec.step_ops()
-        reps = 5
-        per_op = [[] for _ in ops]
         dec.decode(lat_d[0], K_DDIM, init=x_d[0])
         torch.cuda.synchronize()
-        for _ in range(reps):
-            for j in range(len(ops)):
-                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s.record()
-                dec.run_step_op(j, 8)
-                e.record()
-                per_op[j].append((s, e))
-        torch.cuda.synchronize()
-        med = [statistics.median(s.elapsed_time(e) for s, e in lst) for lst in per_op]
+        # in-stream per-op device times (ms): ops enqueued back to back by the library with an event between launches
+        runs = [dec.profile_step(8, warm=1) for _ in range(5)]
+        med = [statistics.median(r[j] for r in runs) / 1e3 for j in range(len(ops))]
         conv = [(n, f, b, t) for (n, f, b), t in zip(ops, med) if f > 0 and "sdpa" not in n]
         conv_ms = sum(t for *_, t in conv)
         conv_fl = sum(f for _, f, _, _ in conv)

@@ -43,7 +43,7 @@ constexpr int kKfRowTx = 130 * 128;
 constexpr int kKfAcc = 8;               // accumulator ring
 constexpr int kKfAux = 1024 + 2 * 8 * 16 * 2 * 4;  // barriers + TMEM holder + bias, stats scratch
 
-template <int BN, int CPG, int EPI, int CH, bool STAGE>
+template <int BN, int CPG, int EPI, int CH, bool STAGE, bool XK16>
 __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __grid_constant__ KfParams p) {
     constexpr int WB = BN * 128;  // one (tap, chunk) weight block
     constexpr uint32_t WB16 = WB >> 4;
@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
 #pragma unroll
                             for (int t = t0; t < t1; ++t) {
                                 const int k = t & 3, kw = t >> 2;
+                                if (XK16 && ch == 0 && k != 0) continue;  // stem: chunk 0 = x_t, channels 16..63 are zero
                                 const uint32_t alo = alo_base + kw * 8 + 2 * k;
                                 const uint32_t blo = wlo + ((kw * CH + ch) * 3) * WB16 + 2 * k;
                                 umma_f16_ss(dA, desc_hi | alo, desc_hi | (blo + bA), iA, 1u);
@@ -213,6 +214,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
 #pragma unroll
                                 for (int t = t0; t < t1; ++t) {
                                     const int k = t & 3, kw = t >> 2;
+                                    if (XK16 && ch == 0 && k != 0) continue;
                                     const uint32_t alo = alo_base + kw * 8 + 2 * k;
                                     const uint32_t blo = wlo + ((kw * CH + ch) * 3) * WB16 + 2 * k;
                                     umma_f16_ss(dB, desc_hi | alo, desc_hi | (blo + bB), iB, 1u);
@@ -250,46 +252,58 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
         const int row = q * 32 + lane;
         uint32_t g = 0, tile_ctr = 0, unit_ctr = 0;
         if constexpr (EPI == EPI_DDIM) {
+            // 3 real output channels: thread = pixel.  The two warp groups (half 0 / 1) take alternate output rows, and
+            // x_t of the row is fetched BEFORE the wait for its accumulator so the global-load latency is hidden.
+            const float b0 = bias_s[0], b1 = bias_s[1], b2 = bias_s[2];
+            const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
             if (half == 0) {
-                const float b0 = bias_s[0], b1 = bias_s[1], b2 = bias_s[2];
                 for (int s_ = 0; s_ < kKfAcc; ++s_) {  // arm every accumulator: zero, then the first "drained" arrive
-                    tmem_zero<16>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + s_ * BN);
+                    tmem_zero<16>(tq + s_ * BN);
                     tmem_st_wait();
                     tc_fence_before();
                     mbar_arrive(bar_tempty + 8 * s_);
                 }
-                for (int u = cta; u < units; u += p.G1) {
-                    int b, seg, si, h0, L;
-                    decode(u, b, seg, si, h0, L);
-                    const int gx = seg * 128 + row;
-                    const bool valid = gx < p.W;
-                    for (int j = 0; j < L; ++j) {
-                        const uint32_t gj = g + j, slot = gj & 7;
-                        mbar_wait(bar_tfull + 8 * slot, (gj >> 3) & 1);
-                        tc_fence_after();
-                        uint32_t v[16];
-                        tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * BN, v);
-                        tmem_ld_wait();
-                        tmem_zero<16>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * BN);
-                        tmem_st_wait();
-                        tc_fence_before();
-                        mbar_arrive(bar_tempty + 8 * slot);
-                        if (valid) {
-                            const size_t pix = (static_cast<size_t>(b) * p.H + (h0 + j)) * p.W + gx;
-                            const float bb[3] = {b0, b1, b2};
+            }
+            for (int u = cta; u < units; u += p.G1) {
+                int b, seg, si, h0, L;
+                decode(u, b, seg, si, h0, L);
+                const int gx = seg * 128 + row;
+                const bool valid = gx < p.W;
+                for (int j = half; j < L; j += 2) {
+                    const uint32_t gj = g + j, slot = gj & 7;
+                    const size_t pix = (static_cast<size_t>(b) * p.H + (h0 + j)) * p.W + gx;
+                    float xt[3] = {0.f, 0.f, 0.f};
+                    if (valid) {
 #pragma unroll
-                            for (int c = 0; c < 3; ++c) {
-                                const float x0 = __uint_as_float(v[c]) + bb[c];
-                                const float xt = p.x[pix * 3 + c];
-                                const float xn = p.c0 * fminf(fmaxf(x0, -1.0f), 1.0f) + p.c1 * xt;
-                                p.x[pix * 3 + c] = xn;
-                                p.xpad[pix * 64 + c] = to_act(xn);
-                                if (p.x0_out) p.x0_out[pix * 3 + c] = x0;
-                            }
-                        }
+                        for (int c = 0; c < 3; ++c) xt[c] = p.x[pix * 3 + c];
                     }
-                    g += L;
+                    mbar_wait(bar_tfull + 8 * slot, (gj >> 3) & 1);
+                    tc_fence_after();
+                    uint32_t v[16];
+                    tmem_ld16(tq + slot * BN, v);
+                    tmem_ld_wait();
+                    tmem_zero<16>(tq + slot * BN);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(bar_tempty + 8 * slot);
+                    if (valid) {
+                        const float bb[3] = {b0, b1, b2};
+                        float xn[3];
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const float x0 = __uint_as_float(v[c]) + bb[c];
+                            xn[c] = p.c0 * fminf(fmaxf(x0, -1.0f), 1.0f) + p.c1 * xt[c];
+                            p.x[pix * 3 + c] = xn[c];
+                            if (p.x0_out) p.x0_out[pix * 3 + c] = x0;
+                        }
+                        // channels 0..2 of the stem's 64-channel x_t copy and the (always zero) channel 3: one 8-byte store
+                        uint2 pk;
+                        pk.x = pack_act2(xn[0], xn[1]);
+                        pk.y = pack_act2(xn[2], 0.0f);
+                        *reinterpret_cast<uint2*>(p.xpad + pix * 64) = pk;
+                    }
                 }
+                g += L;
             }
         } else {
             constexpr int HC = BN / 2;                             // columns per thread
@@ -426,18 +440,19 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
 
 // ------------------------------------------------------------------------------------------------ host
 // (BN, CPG, EPI, CH, STAGED) instantiations: the layer shapes of the UNet / context net this variant serves.
-#define KF_ALL_CASES()                    \
-    KF_CASE(64, 2, EPI_STATS, 1, true)    \
-    KF_CASE(64, 2, EPI_STATS, 2, false)   \
-    KF_CASE(64, 4, EPI_STATS, 1, true)    \
-    KF_CASE(64, 4, EPI_STATS, 2, false)   \
-    KF_CASE(64, 1, EPI_STORE, 1, true)    \
-    KF_CASE(64, 1, EPI_STORE, 2, false)   \
-    KF_CASE(32, 4, EPI_STATS, 3, false)   \
-    KF_CASE(32, 4, EPI_STATS, 4, false)   \
-    KF_CASE(48, 6, EPI_STATS, 3, false)   \
-    KF_CASE(32, 8, EPI_STATS, 4, false)   \
-    KF_CASE(16, 1, EPI_DDIM, 1, false)
+#define KF_ALL_CASES()                           \
+    KF_CASE(64, 2, EPI_STATS, 1, true, false)    \
+    KF_CASE(64, 2, EPI_STATS, 2, false, false)   \
+    KF_CASE(64, 4, EPI_STATS, 1, true, false)    \
+    KF_CASE(64, 4, EPI_STATS, 2, false, false)   \
+    KF_CASE(64, 1, EPI_STORE, 1, true, false)    \
+    KF_CASE(64, 1, EPI_STORE, 2, false, false)   \
+    KF_CASE(64, 1, EPI_STORE, 2, false, true)    \
+    KF_CASE(32, 4, EPI_STATS, 3, false, false)   \
+    KF_CASE(32, 4, EPI_STATS, 4, false, false)   \
+    KF_CASE(48, 6, EPI_STATS, 3, false, false)   \
+    KF_CASE(32, 8, EPI_STATS, 4, false, false)   \
+    KF_CASE(16, 1, EPI_DDIM, 1, false, false)
 
 int kf_smem_bytes(int bn, int CH, int NS, bool staged) {
     return 1024 + NS * kKfRowBytes + 9 * CH * bn * 128 + (staged ? 2 * 128 * bn * 2 : 0) + kKfAux;
@@ -462,7 +477,7 @@ bool kf_inst_ok(int bn, int cpg, int epi, int CH) {
     int ns;
     bool st;
     if (!kf_plan(bn, CH, &ns, &st)) return false;
-#define KF_CASE(BN_, CPG_, EPI_, CH_, ST_) \
+#define KF_CASE(BN_, CPG_, EPI_, CH_, ST_, X_) \
     if (bn == BN_ && (EPI_ != EPI_STATS || cpg == CPG_) && epi == EPI_ && CH == CH_ && st == ST_) return true;
     KF_ALL_CASES()
 #undef KF_CASE
@@ -471,8 +486,8 @@ bool kf_inst_ok(int bn, int cpg, int epi, int CH) {
 
 cudaError_t configure_kf_kernels() {
     cudaError_t e;
-#define KF_CASE(BN_, CPG_, EPI_, CH_, ST_)                                                                  \
-    if ((e = cudaFuncSetAttribute(conv_kf_kernel<BN_, CPG_, EPI_, CH_, ST_>,                                  \
+#define KF_CASE(BN_, CPG_, EPI_, CH_, ST_, X_)                                                              \
+    if ((e = cudaFuncSetAttribute(conv_kf_kernel<BN_, CPG_, EPI_, CH_, ST_, X_>,                              \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) \
         return e;
     KF_ALL_CASES()
@@ -480,15 +495,15 @@ cudaError_t configure_kf_kernels() {
     return cudaSuccess;
 }
 
-cudaError_t launch_conv_kf(const KfParams& p, int bn, int cpg, int epi, int CH, cudaStream_t stream) {
+cudaError_t launch_conv_kf(const KfParams& p, int bn, int cpg, int epi, int CH, bool xk16, cudaStream_t stream) {
     int ns;
     bool st;
     if (!kf_plan(bn, CH, &ns, &st) || ns != p.NS) return cudaErrorInvalidValue;
     const dim3 grid(p.n_tiles * p.G1), block(128 + kEpiThreads);
     const size_t smem = kf_smem_bytes(bn, CH, ns, st);
-#define KF_CASE(BN_, CPG_, EPI_, CH_, ST_)                                                          \
-    if (bn == BN_ && (EPI_ != EPI_STATS || cpg == CPG_) && epi == EPI_ && CH == CH_ && st == ST_)     \
-        return launch_pdl(conv_kf_kernel<BN_, CPG_, EPI_, CH_, ST_>, grid, block, smem, stream, p);
+#define KF_CASE(BN_, CPG_, EPI_, CH_, ST_, X_)                                                                \
+    if (bn == BN_ && (EPI_ != EPI_STATS || cpg == CPG_) && epi == EPI_ && CH == CH_ && st == ST_ && xk16 == X_)   \
+        return launch_pdl(conv_kf_kernel<BN_, CPG_, EPI_, CH_, ST_, X_>, grid, block, smem, stream, p);
     KF_ALL_CASES()
 #undef KF_CASE
     return cudaErrorInvalidValue;

@@ -30,6 +30,6 @@ bool kf_inst_ok(int bn, int cpg, int epi, int CH);
 bool kf_plan(int bn, int CH, int* NS, bool* staged);  // shared-memory plan; false if the weights do not fit
 int kf_smem_bytes(int bn, int CH, int NS, bool staged);
 cudaError_t configure_kf_kernels();
-cudaError_t launch_conv_kf(const KfParams& p, int bn, int cpg, int epi, int CH, cudaStream_t stream);
+cudaError_t launch_conv_kf(const KfParams& p, int bn, int cpg, int epi, int CH, bool xk16, cudaStream_t stream);  // xk16: chunk 0 has 16 real channels (stem)
 
 }  // namespace cdc

@@ -107,6 +107,7 @@ struct ConvBuild {
     const std::vector<float>* c0 = nullptr;  // per-step sampler coefficients (host)
     const std::vector<float>* c1 = nullptr;
     long long* dbg = nullptr;  // strip kernel issuer timeline (tools)
+    bool x16 = false;          // source 0 carries at most 16 non-zero channels (the stem's x_t copy)
 };
 
 static int encode_act_map(CUtensorMap* m, const act_t* base, int C, int Wd, int Hd, int B, size_t sW, size_t sH,
@@ -280,16 +281,17 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
             op->flops = 2.0 * Ms * w.n_true * (9.0 * w.c_true);
             op->bytes = 2.0 * (Ms * w.c_true + Ms * w.n_true + 9.0 * w.c_true * w.n_true);
             const int epi = cb.epi, cpg = cb.cpg, bn_k = kg.bn, CHk = kg.CH;
+            const bool xk = cb.x16 && cb.epi == EPI_STORE && kg.bn == 64 && kg.CH == 2 && cb.srcs[0].C == 64;
             const std::vector<float>*c0 = cb.c0, *c1 = cb.c1;
-            op->run = [kp, bn_k, cpg, epi, CHk, c0, c1](cudaStream_t s, int k) -> cudaError_t {
+            op->run = [kp, bn_k, cpg, epi, CHk, xk, c0, c1](cudaStream_t s, int k) -> cudaError_t {
                 if (epi == EPI_DDIM) {
                     if (!c0 || k < 0 || k >= static_cast<int>(c0->size())) return cudaErrorInvalidValue;
                     KfParams q = *kp;
                     q.c0 = (*c0)[k];
                     q.c1 = (*c1)[k];
-                    return launch_conv_kf(q, bn_k, cpg, epi, CHk, s);
+                    return launch_conv_kf(q, bn_k, cpg, epi, CHk, xk, s);
                 }
-                return launch_conv_kf(*kp, bn_k, cpg, epi, CHk, s);
+                return launch_conv_kf(*kp, bn_k, cpg, epi, CHk, xk, s);
             };
             return CDC_OK;
         }
@@ -813,6 +815,7 @@ static int build_plans(cdc_ctx* ctx) {
     {
         ConvBuild cb;
         cb.name = "stem";
+        cb.x16 = true;
         cb.srcs = {ctx->xpad, ctx->cond[0]};
         cb.w = &ctx->convs["stem"];
         cb.out = h;
@@ -948,8 +951,25 @@ static int capture_graph(cdc_ctx* ctx) {
     CK(cudaStreamBeginCapture(ctx->cap_stream, cudaStreamCaptureModeThreadLocal));
     cudaError_t e = cudaSuccess;
     std::string bad;
+    // tools only: CDC_GRAPH_SKIP=substr[,substr...] leaves ops whose name contains a substring out of the graph, so that
+    // the in-graph cost of a class of ops can be read off as a difference of replay times (results are then garbage)
+    std::vector<std::string> skip;
+    if (const char* sk = getenv("CDC_GRAPH_SKIP")) {
+        std::string t(sk);
+        size_t pos = 0;
+        while (pos <= t.size()) {
+            const size_t c = t.find(',', pos);
+            const std::string w = t.substr(pos, c == std::string::npos ? std::string::npos : c - pos);
+            if (!w.empty()) skip.push_back(w);
+            if (c == std::string::npos) break;
+            pos = c + 1;
+        }
+    }
     for (int k = 0; k < ctx->K && e == cudaSuccess; ++k)
         for (Op& op : ctx->step_ops) {
+            bool skipped = false;
+            for (const std::string& w : skip) skipped = skipped || op.name.find(w) != std::string::npos;
+            if (skipped) continue;
             e = op.run(ctx->cap_stream, k);
             if (e != cudaSuccess) {
                 bad = op.name;
@@ -1337,6 +1357,32 @@ int cdc_run_step_op(cdc_ctx* ctx, int i, int k, cdc_stream s) {
     NEED_PLAN();
     if (i < 0 || i >= static_cast<int>(ctx->step_ops.size()) || k < 0 || k >= ctx->K) return ctx->fail(CDC_ERR_SHAPE, "bad op/step index");
     CK(ctx->step_ops[i].run(S(s), k));
+    return CDC_OK;
+}
+
+// Per-op device time of one denoise step, measured in stream order: all ops are enqueued back to back with an event
+// between consecutive launches (the host stays ahead of the GPU, so the differences are the ops' in-stream durations
+// including the inter-kernel gap -- what the captured graph replays), after `warm` untimed steps.
+int cdc_profile_step(cdc_ctx* ctx, int k, int warm, float* us_out, cdc_stream s) {
+    NEED_PLAN();
+    if (k < 0 || k >= ctx->K || !us_out) return ctx->fail(CDC_ERR_SHAPE, "bad step index / output");
+    const size_t n = ctx->step_ops.size();
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    for (int w = 0; w < warm; ++w)
+        for (Op& op : ctx->step_ops) CK(op.run(S(s), k));
+    CK(cudaEventRecord(ev[0], S(s)));
+    for (size_t i = 0; i < n; ++i) {
+        CK(ctx->step_ops[i].run(S(s), k));
+        CK(cudaEventRecord(ev[i + 1], S(s)));
+    }
+    CK(cudaStreamSynchronize(S(s)));
+    for (size_t i = 0; i < n; ++i) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+        us_out[i] = ms * 1e3f;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
     return CDC_OK;
 }
 

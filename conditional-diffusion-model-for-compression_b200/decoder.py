@@ -185,6 +185,14 @@ class Decoder:
     def run_step_op(self, i, k=0):
         _ffi.check(self.ctx, self.L.cdc_run_step_op(self.ctx, i, k, _stream_ptr()), "cdc_run_step_op")
 
+    def profile_step(self, k=0, warm=1):
+        """In-stream device time (us) of every op of step k (launched back to back, CUDA events in the library)."""
+        import ctypes as C
+        n = self.L.cdc_num_step_ops(self.ctx)
+        buf = (C.c_float * n)()
+        _ffi.check(self.ctx, self.L.cdc_profile_step(self.ctx, k, warm, buf, _stream_ptr()), "cdc_profile_step")
+        return list(buf)
+
     # ---- integer path (same names as the oracle) -----------------------------------------------
     def quantize_symbols(self, y, mu):
         return quantize_symbols(y, mu, device=self.device)

@@ -94,6 +94,8 @@ const char* cdc_step_op_name(cdc_ctx* ctx, int i);
 double cdc_step_op_flops(cdc_ctx* ctx, int i);
 double cdc_step_op_bytes(cdc_ctx* ctx, int i);
 int cdc_run_step_op(cdc_ctx* ctx, int i, int k, cdc_stream s);
+/* in-stream device time (microseconds) of every op of step k, after `warm` untimed steps; us_out[cdc_num_step_ops] */
+int cdc_profile_step(cdc_ctx* ctx, int k, int warm, float* us_out, cdc_stream s);
 
 /* ---- oracle/entropy.py quantize_symbols / cdf_lookup (stateless) ------------------------------- */
 /* q = rint(y - mu) int32 (half-to-even), y_hat = q + mu.  mu_mod == 0: mu is elementwise;
