@@ -84,8 +84,7 @@ def lib():
     L.cdc_quantize.argtypes = [f32p, f32p, i32p, f32p, i64, i64, i64, p]
     L.cdc_cdf_lookup.argtypes = [i32p, f32p, i32p, i32p, i32p, i32p, f32p, i32, i64, i32p, i32p, i32p, i32p, i32p,
                                  i64, p]
-    L.cdc_test_conv.argtypes = [i32, p, i32, p, i32, i32, i32, i32, f32p, f32p, i32, i32, i32, i32, p, p, f32p,
-                                C.POINTER(i32), p]
+    L.cdc_test_conv.argtypes = [i32, p, i32, p, i32, i32, i32, i32, f32p, f32p, i32, i32, i32, i32, p, p, p, p]
     L.cdc_test_attention.argtypes = [p, p, i32, i32, i32, p]
     L.cdc_test_gn.argtypes = [p, p, p, f32p, f32p, f32p, i32, i32, i32, i32, C.c_float, p]
     for s in SYMBOLS:

@@ -3,6 +3,7 @@
 // Called by the 4 epilogue warps (128 threads); thread = TMEM lane = output pixel.
 #pragma once
 #include "conv_tc.cuh"
+#include "gn_sums.cuh"
 #include "ptx.cuh"
 
 namespace cdc {
@@ -51,14 +52,14 @@ __device__ __forceinline__ float warp_group_reduce(float (&s)[G], int lane) {
 // taddr: TMEM address of lane quarter q of the accumulator; bar_tempty: mbarrier (256 arrivals, 128 for
 // EPI_DDIM) that hands the accumulator back to the MMA warp; bs: bias of this N tile (shared memory);
 // red: 2*4*16*2 floats of shared scratch (alternate between consecutive tiles);
-// stats_dst: this tile's first group slot in the partials buffer ([.. groups ..][2]) or unused.
+// gn_dst: accumulator slot of this image, offset to the first group of this N tile (gn_sums.cuh), or unused.
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 
 template <int BN, int CPG, int EPI>
 __device__ __forceinline__ void conv_epilogue_tile(const EpiArgs& e, uint32_t taddr, uint32_t bar_tempty,
                                                    const float* bs, float* red, int q, int half, int lane, bool valid,
-                                                   size_t pix, int n0, float* stats_dst, long long* dbg = nullptr, bool arrive = true) {
+                                                   size_t pix, int n0, gn_sum_t* gn_dst, long long* dbg = nullptr, bool arrive = true) {
     if constexpr (EPI == EPI_DDIM) {
         if (half != 0) return;
         uint32_t v[16];
@@ -160,8 +161,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const EpiArgs& e, uint32_t ta
                 const float* r0 = red + ((hh * 4) * 16 + gl) * 2;
                 const float s = ((r0[0] + r0[32]) + r0[64]) + r0[96];
                 const float s2 = ((r0[1] + r0[33]) + r0[65]) + r0[97];
-                stats_dst[t * 2 + 0] = s;
-                stats_dst[t * 2 + 1] = s2;
+                gn_sums_add(gn_dst, t, s, s2);
             }
         }
     }

@@ -21,8 +21,8 @@
 //   warp 0 : input-row producer (TMA)   warp 1 : tcgen05.mma issuer   warp 2 : TMEM allocator
 //   warp 3 : weight loader (TMA, once)  warps 4-11 : epilogue
 //
-// Epilogue: +bias, GroupNorm partial sums kept in registers over the whole strip (one fixed-order partial row
-// per strip: bitwise reproducible), fp16 pack, then either a swizzled shared-memory tile + one TMA store per
+// Epilogue: +bias, GroupNorm sums kept in registers over the whole strip and added once per strip to the
+// fixed-point accumulators of gn_sums.cuh (integer atomics: bitwise reproducible), fp16 pack, then either a swizzled shared-memory tile + one TMA store per
 // output row (coalesced 16 KB writes) or direct 16-byte stores; EPI_DDIM applies the sampler update.
 //
 // Oracle counterpart: oracle/unet.py `conv(k=3)` inside RB / stem / final (the reference ships no code).
@@ -417,13 +417,12 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
                         const float* r0 = red + ((hh * 4) * 16 + gl) * 2;
                         const float s = ((r0[0] + r0[32]) + r0[64]) + r0[96];
                         const float s2 = ((r0[1] + r0[33]) + r0[65]) + r0[97];
-                        float* dst = p.stats + ((static_cast<size_t>(b) * (p.nseg * p.S) + seg * p.S + si) * 32 + nt * (BN / CPG)) * 2;
-                        dst[t * 2 + 0] = s;
-                        dst[t * 2 + 1] = s2;
+                        gn_sums_add(p.gn_acc + static_cast<size_t>(b) * 64, nt * (BN / CPG) + t, s, s2);
                     }
                 }
             }
             if (STAGE && store_leader) bulk_wait_group<0>();
+
         }
     }
 

@@ -18,7 +18,7 @@ struct alignas(64) KfParams {
     int ldc;              // channels of the output tensor
     act_t* out;
     const float* bias;    // [n_tiles * BN]
-    float* stats;         // EPI_STATS: [batch][nseg * S][32][2], one partial row per strip
+    gn_sum_t* gn_acc;     // EPI_STATS: [batch][32][2] fixed-point accumulators (gn_sums.cuh), zero on entry
     float* x;             // EPI_DDIM (see ConvParams)
     act_t* xpad;
     float* x0_out;

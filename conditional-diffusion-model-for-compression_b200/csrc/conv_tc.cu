@@ -176,11 +176,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
             mbar_wait(bar_tfull + 8 * as, aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE;
-            const int PT = p.nphase * p.tiles_h * p.tiles_w;
-            const int pt = (ph * p.tiles_h + th) * p.tiles_w + tw;
-            float* sdst = (EPI == EPI_STATS)
-                              ? p.stats + ((static_cast<size_t>(b) * PT + pt) * 32 + nt * (BN / CPG)) * 2
-                              : nullptr;
+            gn_sum_t* sdst = (EPI == EPI_STATS) ? p.gn_acc + (static_cast<size_t>(b) * 32 + nt * (BN / CPG)) * 2 : nullptr;
             conv_epilogue_tile<BN, CPG, EPI>(ea, taddr, bar_tempty + 8 * as, bias_s + nt * BN,
                                              red_s + (it & 1) * (2 * 4 * 16 * 2), q, half, lane, valid, pix, nt * BN, sdst);
         }

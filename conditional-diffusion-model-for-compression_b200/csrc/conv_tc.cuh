@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "gn_sums.cuh"
+
 namespace cdc {
 
 constexpr int kMaxMaps = 8;      // activation tensor maps per launch (2 sources x 4 stride-2 phases)
@@ -25,7 +27,7 @@ struct KBlock {
 
 enum ConvEpilogue : int {
     EPI_STORE = 0,  // +bias (+bf16 residual) -> act_t NHWC
-    EPI_STATS = 1,  // EPI_STORE and per-(tile, group) sum / sum-of-squares partials for GroupNorm
+    EPI_STATS = 1,  // EPI_STORE and per-(image, group) sum / sum-of-squares for GroupNorm (integer atomics)
     EPI_DDIM = 2,   // final conv: x0 = acc+bias; x_prev = c0*clamp(x0) + c1*x_t (fp32), act_t copy for the stem
 };
 
@@ -46,7 +48,7 @@ struct alignas(64) ConvParams {
     act_t* out;
     const float* bias;                 // [n_total]
     const act_t* residual;     // optional, same layout as out
-    float* stats;                      // EPI_STATS: [batch][PT][32][2]
+    gn_sum_t* gn_acc;                  // EPI_STATS: [batch][32][2] fixed-point accumulators (gn_sums.cuh), zero on entry
     // EPI_DDIM
     float* x;                          // [B*H*W][3] fp32, updated in place
     act_t* xpad;               // [B*H*W][64] bf16, channels 0..2 rewritten

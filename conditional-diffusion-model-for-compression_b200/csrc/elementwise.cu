@@ -1,6 +1,7 @@
 // HBM-/latency-bound kernels around K-conv: GroupNorm statistics / finalize / apply(+SiLU,+residual),
 // time-embedding MLP + FiLM vectors, layout conversion at the API boundary, weight repack.
 // Oracle counterparts: oracle/unet.py RB, Attn.gn, TimeEmbed; SURVEY.md 2.2 C5, C6, C8.
+#include "gn_sums.cuh"
 #include "kernels.cuh"
 #include "launch.cuh"
 #include "ptx.cuh"
@@ -12,11 +13,9 @@ namespace cdc {
 // One CTA per (image, 64-pixel chunk); fixed-order reductions only.
 constexpr int kStatsPix = 64;
 
-int gn_stats_num_partials(int HW) { return (HW + kStatsPix - 1) / kStatsPix; }
-
 // (tensors written by the preceding kernel are read through plain pointers, not const __restrict__: under PDL the
 // kernel is resident before that data is final, so the non-coherent read-only path must not be used for them)
-__global__ void __launch_bounds__(256) gn_stats_kernel(const act_t* x, float* partials, int HW, int C, int PT) {
+__global__ void __launch_bounds__(256) gn_stats_kernel(const act_t* x, gn_sum_t* acc, int HW, int C) {
     __shared__ float s_sum[8][512], s_sq[8][512];  // [row-in-pass][channel] (C <= 512)
     pdl_launch_dependents();
     pdl_wait();
@@ -67,74 +66,19 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const act_t* x, float* pa
             a += c_sum[t * cpg + j];
             d += c_sq[t * cpg + j];
         }
-        float* dst = partials + ((static_cast<size_t>(b) * PT + pt) * 32 + t) * 2;
-        dst[0] = a;
-        dst[1] = d;
+        gn_sums_add(acc + static_cast<size_t>(b) * 64, t, a, d);
     }
 }
 
-cudaError_t launch_gn_stats(const act_t* x, float* partials, int B, int HW, int C, int* PT_out,
-                            cudaStream_t s) {
+cudaError_t launch_gn_stats(const act_t* x, gn_sum_t* acc, int B, int HW, int C, cudaStream_t s) {
     if (C % 32 != 0 || C > 512 || C < 32) return cudaErrorInvalidValue;
-    const int PT = gn_stats_num_partials(HW);
-    if (PT_out) *PT_out = PT;
-    return launch_pdl(gn_stats_kernel, dim3(PT, B), dim3(256), 0, s, x, partials, HW, C, PT);
+    const int PT = (HW + kStatsPix - 1) / kStatsPix;
+    return launch_pdl(gn_stats_kernel, dim3(PT, B), dim3(256), 0, s, x, acc, HW, C);
 }
 
 // ------------------------------------------------------------------------------------------------
 // Finalize: one CTA per (group, image).  Thread t sums partials t, t+256, ... in order, then a fixed
 // shared-memory tree; double accumulation.  The CTA then writes (a, b) for its C/32 channels.
-__global__ void __launch_bounds__(256) gn_finalize_kernel(const float* partials, int PT,
-                                                          const float* __restrict__ gamma,
-                                                          const float* __restrict__ beta,
-                                                          const float* __restrict__ film, float2* ab,
-                                                          int C, int HW, float eps) {
-    __shared__ double s_s[256], s_q[256];
-    pdl_launch_dependents();
-    pdl_wait();
-    const int g = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
-    const float2* src = reinterpret_cast<const float2*>(partials) + static_cast<size_t>(b) * PT * 32 + g;
-    double s = 0.0, q = 0.0;
-    for (int pt = t; pt < PT; pt += 256) {
-        const float2 v = src[static_cast<size_t>(pt) * 32];
-        s += v.x;
-        q += v.y;
-    }
-    s_s[t] = s;
-    s_q[t] = q;
-    __syncthreads();
-#pragma unroll
-    for (int m = 128; m >= 1; m >>= 1) {
-        if (t < m) {
-            s_s[t] += s_s[t + m];
-            s_q[t] += s_q[t + m];
-        }
-        __syncthreads();
-    }
-    const int cpg = C / 32;
-    if (t < cpg) {
-        const double n = static_cast<double>(cpg) * HW;
-        const double mean = s_s[0] / n;
-        double var = s_q[0] / n - mean * mean;
-        if (var < 0.0) var = 0.0;
-        const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-        const int c = g * cpg + t;
-        float a = gamma[c] * rstd;
-        float bb = beta[c] - static_cast<float>(mean) * a;
-        if (film) {
-            const float sc = 1.0f + film[c], sh = film[C + c];
-            a *= sc;
-            bb = bb * sc + sh;
-        }
-        ab[static_cast<size_t>(b) * C + c] = make_float2(a, bb);
-    }
-}
-
-cudaError_t launch_gn_finalize(const float* partials, int PT, const float* gamma, const float* beta, const float* film,
-                               float2* ab, int B, int C, int HW, float eps, cudaStream_t s) {
-    return launch_pdl(gn_finalize_kernel, dim3(32, B), dim3(256), 0, s, partials, PT, gamma, beta, film, ab, C, HW, eps);
-}
-
 // ------------------------------------------------------------------------------------------------
 // Apply: y = SiLU(a*x + b) (+ r), 8 channels (16 B) per thread, grid-stride.
 // x * sigmoid(x) = x * (0.5 + 0.5 * tanh(x / 2)): ONE MUFU op (tanh.approx.f32, max relative error 2^-11, below the
@@ -169,18 +113,93 @@ __device__ __forceinline__ uint4 gn_apply_vec(const uint4 u, const uint4 rr, con
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// GroupNorm coefficients of this thread's 8 channels, y = a*x + b with the affine and FiLM (1 + s, sh) folded in, from
+// the fixed-point (sum, sum of squares) accumulators of the image (gn_sums.cuh).  Same arithmetic as the oracle's
+// F.group_norm + FiLM (oracle/unet.py RB): mean / variance in double, rstd = 1 / sqrt(var + eps).
+struct GnCoef {
+    const gn_sum_t* acc;   // [B][32][2]; written by the preceding kernel: plain (coherent) loads only
+    const float* gamma;
+    const float* beta;
+    const float* film;     // [2C] (scale | shift) of this step, or null
+    int C, HW;
+    float eps;
+};
+// (mean, rstd) of every (image, group), once per CTA: exact integer totals -> double mean / variance (a handful of
+// FP64 multiply-adds), rstd in fp32 (MUFU rsqrt + one Newton step, < 1 ulp) like the oracle's fp32 group_norm.
+__device__ __forceinline__ void gn_group_stats(const GnCoef& g, int B, float2* s_mr) {
+    const int cpg = g.C / 32;
+    const double inv_n = kGnFixInv / (static_cast<double>(cpg) * g.HW);
+    for (int i = threadIdx.x; i < B * 32; i += blockDim.x) {
+        const gn_sum_t* a = g.acc + static_cast<size_t>(i) * 2;
+        const double m = static_cast<double>(a[0]) * inv_n;
+        double var = static_cast<double>(a[1]) * inv_n - m * m;
+        const float v = fmaxf(static_cast<float>(var), 0.0f) + g.eps;
+        float r = rsqrtf(v);
+        r = r * (1.5f - 0.5f * v * r * r);
+        s_mr[i] = make_float2(static_cast<float>(m), r);
+    }
+    __syncthreads();
+}
+// This thread's 8 channels: GroupNorm affine and FiLM, loaded once (they do not depend on the statistics, so the
+// loads are issued before the statistics phase and overlap it)
+struct GnChan {
+    float gamma[8], beta[8], sc[8], sh[8];
+};
+__device__ __forceinline__ void gn_load_chan(const GnCoef& g, int c0, GnChan& k) {
+    const float4* ga = reinterpret_cast<const float4*>(g.gamma + c0);
+    const float4* be = reinterpret_cast<const float4*>(g.beta + c0);
+    const float4 g0 = ga[0], g1 = ga[1], b0 = be[0], b1 = be[1];
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, h0 = s0, h1 = s0;
+    if (g.film) {
+        const float4* fs = reinterpret_cast<const float4*>(g.film + c0);
+        const float4* fh = reinterpret_cast<const float4*>(g.film + g.C + c0);
+        s0 = fs[0], s1 = fs[1], h0 = fh[0], h1 = fh[1];
+    }
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, hh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        k.gamma[j] = gg[j];
+        k.beta[j] = bb[j];
+        k.sc[j] = 1.0f + ss[j];
+        k.sh[j] = hh[j];
+    }
+}
+__device__ __forceinline__ void gn_coef(const GnChan& k, const float2* s_mr, int b, int c0, int cpg, float4 (&c)[4]) {
+    float ab[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float2 mr = s_mr[b * 32 + (c0 + j) / cpg];
+        const float a = k.gamma[j] * mr.y;
+        const float bb = k.beta[j] - mr.x * a;
+        ab[2 * j] = a * k.sc[j];               // FiLM: (a*x + b) * (1 + s) + sh   (s = sh = 0 without FiLM)
+        ab[2 * j + 1] = bb * k.sc[j] + k.sh[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[j] = make_float4(ab[4 * j], ab[4 * j + 1], ab[4 * j + 2], ab[4 * j + 3]);
+}
+
 // The grid stride is a multiple of the vectors per pixel, so a thread always owns the same 8 channels:
-// its (a, b) pairs live in registers and are reloaded only when the image index changes.
+// its (a, b) pairs live in registers and are recomputed only when the image index changes.  64 registers at most:
+// 4 CTAs per SM, and the grid is exactly one resident wave (the statistics prologue is paid once per CTA).
 template <bool SILU, bool RES>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* x, const float2* ab, const uint4* r, uint4* y,
-                                                       long long nvec, int vecs_per_pix, long long vecs_per_img) {
+__global__ void __launch_bounds__(256, 4) gn_apply_kernel(const uint4* x, const uint4* r, uint4* y, long long nvec, int vecs_per_pix,
+                                                          long long vecs_per_img, const GnCoef g, int B) {
+    extern __shared__ float2 s_mr[];  // [B][32] (mean, rstd)
     pdl_wait();  // (no early trigger here: see pdl_launch_dependents)
     const long long stride = gridDim.x * 256LL;
     long long i = blockIdx.x * 256LL + threadIdx.x;
-    const int cv = static_cast<int>(i % vecs_per_pix);
-    int cur_b = -1;
+    const int cv = static_cast<int>(i % vecs_per_pix), cpg = g.C / 32;
     const bool single = vecs_per_img >= nvec;  // one image: skip the 64-bit divide
     float4 c[4];
+    int cur_b;
+    {   // channel constants and the first vectors are in flight before the statistics phase (none depends on it)
+        GnChan k;
+        gn_load_chan(g, cv * 8, k);
+        gn_group_stats(g, B, s_mr);
+        cur_b = (single || i >= nvec) ? 0 : static_cast<int>(i / vecs_per_img);
+        gn_coef(k, s_mr, cur_b, cv * 8, cpg, c);
+    }
     for (; i < nvec; i += 2 * stride) {
         const long long i2 = i + stride;
         const bool has2 = i2 < nvec;
@@ -192,19 +211,19 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* x, const flo
             if (has2) r1 = r[i2];
         }
         int b = single ? 0 : static_cast<int>(i / vecs_per_img);
-        if (b != cur_b) {
-            const float4* abp = reinterpret_cast<const float4*>(ab + (static_cast<size_t>(b) * vecs_per_pix + cv) * 8);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) c[j] = abp[j];
+        if (b != cur_b) {  // (batch > 1 only) reload this thread's channel constants: L2 hits
+            GnChan k;
+            gn_load_chan(g, cv * 8, k);
+            gn_coef(k, s_mr, b, cv * 8, cpg, c);
             cur_b = b;
         }
         y[i] = gn_apply_vec<SILU, RES>(u0, r0, c);
         if (has2) {
             b = single ? 0 : static_cast<int>(i2 / vecs_per_img);
             if (b != cur_b) {
-                const float4* abp = reinterpret_cast<const float4*>(ab + (static_cast<size_t>(b) * vecs_per_pix + cv) * 8);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) c[j] = abp[j];
+                GnChan k;
+                gn_load_chan(g, cv * 8, k);
+                gn_coef(k, s_mr, b, cv * 8, cpg, c);
                 cur_b = b;
             }
             y[i2] = gn_apply_vec<SILU, RES>(u1, r1, c);
@@ -212,26 +231,29 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* x, const flo
     }
 }
 
-cudaError_t launch_gn_apply(const act_t* x, const float2* ab, const act_t* r, act_t* y, int B,
-                            int HW, int C, int silu, int num_sms, cudaStream_t s) {
+cudaError_t launch_gn_apply(const act_t* x, const gn_sum_t* acc, const float* gamma, const float* beta, const float* film,
+                            float eps, const act_t* r, act_t* y, int B, int HW, int C, int silu, int num_sms, cudaStream_t s) {
     const long long nvec = static_cast<long long>(B) * HW * C / 8;
     const int vpp = C / 8;
     const long long vpi = static_cast<long long>(HW) * vpp;
     long long want = (nvec + 511) / 512;
-    const long long cap = static_cast<long long>(num_sms) * 8;
+    const long long cap = static_cast<long long>(num_sms) * 4;  // one resident wave (__launch_bounds__(256, 4))
     long long grid = want < cap ? want : cap;
     // (grid * 256) % vpp == 0  <=>  the per-thread channel vector is loop-invariant
     const int need = vpp % 3 == 0 ? 3 : 1;  // 256 covers the power-of-two part of vpp (8, 16, 32, 64)
     grid = (grid + need - 1) / need * need;
-    if ((grid * 256) % vpp != 0) return cudaErrorInvalidValue;
+    if ((grid * 256) % vpp != 0 || C % 32 != 0) return cudaErrorInvalidValue;
     const uint4* xv = reinterpret_cast<const uint4*>(x);
     const uint4* rv = reinterpret_cast<const uint4*>(r);
     uint4* yv = reinterpret_cast<uint4*>(y);
-    const int g = static_cast<int>(grid);
-    if (silu && r) return launch_pdl(gn_apply_kernel<true, true>, dim3(g), dim3(256), 0, s, xv, ab, rv, yv, nvec, vpp, vpi);
-    if (silu) return launch_pdl(gn_apply_kernel<true, false>, dim3(g), dim3(256), 0, s, xv, ab, rv, yv, nvec, vpp, vpi);
-    if (r) return launch_pdl(gn_apply_kernel<false, true>, dim3(g), dim3(256), 0, s, xv, ab, rv, yv, nvec, vpp, vpi);
-    return launch_pdl(gn_apply_kernel<false, false>, dim3(g), dim3(256), 0, s, xv, ab, rv, yv, nvec, vpp, vpi);
+    const dim3 g(static_cast<unsigned>(grid)), blk(256);
+    const GnCoef gc{acc, gamma, beta, film, C, HW, eps};
+    const size_t sm = static_cast<size_t>(B) * 32 * sizeof(float2);
+    if (sm > 48 * 1024) return cudaErrorInvalidValue;
+    if (silu && r) return launch_pdl(gn_apply_kernel<true, true>, g, blk, sm, s, xv, rv, yv, nvec, vpp, vpi, gc, B);
+    if (silu) return launch_pdl(gn_apply_kernel<true, false>, g, blk, sm, s, xv, rv, yv, nvec, vpp, vpi, gc, B);
+    if (r) return launch_pdl(gn_apply_kernel<false, true>, g, blk, sm, s, xv, rv, yv, nvec, vpp, vpi, gc, B);
+    return launch_pdl(gn_apply_kernel<false, false>, g, blk, sm, s, xv, rv, yv, nvec, vpp, vpi, gc, B);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1,23 +1,20 @@
 // Launchers of the non-GEMM kernels of the decode hot path (all HBM- or latency-bound).
 #pragma once
 #include "act.cuh"
+#include "gn_sums.cuh"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace cdc {
 
 // ---- GroupNorm (oracle/unet.py RB / Attn) -------------------------------
-// partials: [B][PT][32][2] (sum, sum of squares) per tile and group.
-// ab:       [B][C] float2 = (a, b) with y = a*x + b  (GN affine and FiLM folded).
-cudaError_t launch_gn_stats(const act_t* x, float* partials, int B, int HW, int C, int* PT_out,
-                            cudaStream_t s);
-int gn_stats_num_partials(int HW);
-cudaError_t launch_gn_finalize(const float* partials, int PT, const float* gamma, const float* beta,
-                               const float* film /* [2C] scale|shift or null */, float2* ab, int B, int C, int HW,
-                               float eps, cudaStream_t s);
-// y = act(a*x+b) (+ r); act = SiLU if silu != 0.  In place allowed (y == x).
-cudaError_t launch_gn_apply(const act_t* x, const float2* ab, const act_t* r, act_t* y,
-                            int B, int HW, int C, int silu, int num_sms, cudaStream_t s);
+// Statistics are fixed-point integer accumulators [B][32 groups][2] (gn_sums.cuh), zero on entry, filled by the conv
+// epilogues or by gn_stats (where the producer is not a conv: attention input).
+cudaError_t launch_gn_stats(const act_t* x, gn_sum_t* acc, int B, int HW, int C, cudaStream_t s);
+// y = act(GN(x) * (1 + film_scale) + film_shift) (+ r); act = SiLU if silu != 0; film may be null.  In place allowed.
+// The normalisation coefficients are derived from `acc` inside the kernel (no finalize pass).
+cudaError_t launch_gn_apply(const act_t* x, const gn_sum_t* acc, const float* gamma, const float* beta, const float* film,
+                            float eps, const act_t* r, act_t* y, int B, int HW, int C, int silu, int num_sms, cudaStream_t s);
 
 // ---- time embedding + FiLM (C8; oracle/unet.py TimeEmbed, RB.film) ----------------------------
 struct FilmLayer {

@@ -20,7 +20,6 @@
 
 #include "../../include/cdc_b200.h"
 #include "conv_kf.cuh"
-#include "conv_strip.cuh"
 #include "conv_tc.cuh"
 #include "kernels.cuh"
 
@@ -97,7 +96,7 @@ struct ConvBuild {
     Act out;
     int epi = EPI_STORE;
     int cpg = 1;
-    float* stats = nullptr;
+    gn_sum_t* gn_acc = nullptr;  // EPI_STATS: this GroupNorm's accumulator slot [B][32][2]
     const act_t* residual = nullptr;
     int force_bn = 0;   // > 0: force the N tile of conv_tc.cu; -1: force conv_tc.cu with its own choice
     // DDIM
@@ -271,7 +270,7 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
             kp->ldc = cb.epi == EPI_DDIM ? 3 : cb.out.C;
             kp->out = cb.out.p;
             kp->bias = w.bias;
-            kp->stats = cb.stats;
+            kp->gn_acc = cb.gn_acc;
             kp->x = cb.x;
             kp->xpad = cb.xpad;
             kp->x0_out = cb.x0_out;
@@ -292,66 +291,6 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
                     return launch_conv_kf(q, bn_k, cpg, epi, CHk, xk, s);
                 }
                 return launch_conv_kf(*kp, bn_k, cpg, epi, CHk, xk, s);
-            };
-            return CDC_OK;
-        }
-    }
-
-    // ---- strip variant (conv_strip.cu): 3x3, stride 1, one N tile, image at least one segment wide ----
-    {
-        const int bn_s = cb.epi == EPI_DDIM ? 16 : w.n_pad;
-        const int CH = ctot / 64;
-        int NR = 0, NSW = 0;
-        const bool wide = gw >= 128 && (gw % 128 == 0 || gw >= 512);
-        if (cb.mode == MODE_S1 && cb.ksize == 3 && cb.force_bn == 0 && wide && strip_plan(bn_s, CH, &NR, &NSW) &&
-            strip_inst_ok(bn_s, cb.cpg, cb.epi, CH, NSW == 0)) {
-            auto sp = std::shared_ptr<StripParams>(new StripParams());
-            memset(sp.get(), 0, sizeof(StripParams));
-            for (size_t s = 0; s < cb.srcs.size(); ++s) {
-                const Act& a = cb.srcs[s];
-                if (encode_act_map(&sp->amap[s], a.p, a.C, a.W, a.H, B, static_cast<size_t>(a.C),
-                                   static_cast<size_t>(a.W) * a.C, static_cast<size_t>(a.H) * a.W * a.C, 130, 1))
-                    return fail("cuTensorMapEncodeTiled (strip activation) failed");
-            }
-            if (encode_w_map(&sp->wmap, w.w, w.taps * w.c_pad, w.n_pad, bn_s)) return fail("cuTensorMapEncodeTiled (weights) failed");
-            sp->chunks0 = cb.srcs[0].C / 64;
-            sp->CH = CH;
-            sp->H = gh;
-            sp->W = gw;
-            sp->batch = B;
-            sp->nseg = (gw + 127) / 128;
-            // rows per strip: the fewest strips that still give every SM a unit (halo rows cost 2 / L)
-            int L = 1;
-            while (static_cast<long>(B) * sp->nseg * ((gh + L - 1) / L) > num_sms && L < gh) ++L;
-            sp->L = L;
-            sp->strips_per_col = (gh + L - 1) / L;
-            sp->NR = NR;
-            sp->NSW = NSW;
-            sp->ldc = cb.epi == EPI_DDIM ? 3 : cb.out.C;
-            sp->n_total = w.n_pad;
-            sp->out = cb.out.p;
-            sp->bias = w.bias;
-            sp->residual = cb.residual;
-            sp->stats = cb.stats;
-            sp->x = cb.x;
-            sp->xpad = cb.xpad;
-            sp->x0_out = cb.x0_out;
-            sp->dbg = cb.dbg;
-            const double Ms = static_cast<double>(B) * gh * gw;
-            op->name = cb.name;
-            op->flops = 2.0 * Ms * w.n_true * (9.0 * w.c_true);
-            op->bytes = 2.0 * (Ms * w.c_true + Ms * w.n_true + 9.0 * w.c_true * w.n_true);
-            const int epi = cb.epi, cpg = cb.cpg;
-            const std::vector<float>*c0 = cb.c0, *c1 = cb.c1;
-            op->run = [sp, bn_s, cpg, epi, num_sms, c0, c1](cudaStream_t s, int k) -> cudaError_t {
-                if (epi == EPI_DDIM) {
-                    if (!c0 || k < 0 || k >= static_cast<int>(c0->size())) return cudaErrorInvalidValue;
-                    StripParams q = *sp;
-                    q.c0 = (*c0)[k];
-                    q.c1 = (*c1)[k];
-                    return launch_conv_strip(q, bn_s, cpg, epi, num_sms, s);
-                }
-                return launch_conv_strip(*sp, bn_s, cpg, epi, num_sms, s);
             };
             return CDC_OK;
         }
@@ -475,7 +414,7 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
     cp->out = cb.out.p;
     cp->bias = w.bias;
     cp->residual = cb.residual;
-    cp->stats = cb.stats;
+    cp->gn_acc = cb.gn_acc;
     cp->x = cb.x;
     cp->xpad = cb.xpad;
     cp->x0_out = cb.x0_out;
@@ -500,27 +439,6 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
     return CDC_OK;
 }
 
-static bool conv_uses_strip(const ConvBuild& cb) {
-    int gw, gh, nphase, os, bwl, tw, th;
-    conv_geometry(cb, gw, gh, nphase, os, bwl, tw, th);
-    int ctot = 0;
-    for (const Act& a : cb.srcs) ctot += a.C;
-    const int bn_s = cb.epi == EPI_DDIM ? 16 : cb.w->n_pad;
-    int NR, NSW;
-    const bool wide = gw >= 128 && (gw % 128 == 0 || gw >= 512);
-    return cb.mode == MODE_S1 && cb.ksize == 3 && cb.force_bn == 0 && wide && strip_plan(bn_s, ctot / 64, &NR, &NSW) &&
-           strip_inst_ok(bn_s, cb.cpg, cb.epi, ctot / 64, NSW == 0);
-}
-
-static int conv_num_partials(const ConvBuild& cb, int B, int num_sms) {
-    int gw, gh, nphase, os, bwl, tw, th;
-    conv_geometry(cb, gw, gh, nphase, os, bwl, tw, th);
-    KfGeom kg;
-    if (conv_uses_kf(cb, B, num_sms, &kg)) return kg.nseg * kg.S;
-    if (conv_uses_strip(cb)) return gh * ((gw + 127) / 128);
-    return nphase * tw * th;
-}
-
 }  // namespace cdc
 
 using namespace cdc;
@@ -530,6 +448,8 @@ struct WeightT {
     std::vector<int64_t> shape;
     size_t numel = 0;
 };
+
+constexpr int kMaxGnSlots = 64;  // GroupNorms per sequence (37 in a denoise step, 8 in the context net)
 
 struct cdc_ctx {
     cdc_config cfg;
@@ -555,8 +475,9 @@ struct cdc_ctx {
     int B = 0, H = 0, W = 0;
     std::vector<Op> step_ops, ctx_ops;
     Act cond[4], xpad, latent;
-    float *xs = nullptr, *x0s = nullptr, *partials = nullptr;
-    float2* ab = nullptr;
+    float *xs = nullptr, *x0s = nullptr;
+    gn_sum_t* gn_slots = nullptr;  // [kMaxGnSlots][B][32][2] fixed-point GroupNorm accumulators (gn_sums.cuh)
+    int gn_used_step = 0, gn_used_ctx = 0;
     float *stage_f32 = nullptr;  // NCHW fp32 staging for host-buffer calls
     size_t stage_elems = 0;
     float *pin_in = nullptr, *pin_x = nullptr, *pin_out = nullptr;
@@ -711,8 +632,29 @@ struct PlanB {
         }
         ops->push_back(op);
     }
-    // GN finalize (+FiLM of step k) and apply
-    void gn(const std::string& name, const std::string& gnp, int film_idx, int PT, Act x, const act_t* res, Act y,
+    // Every GroupNorm of the sequence gets its own accumulator slot; one memset (first op of the sequence) clears them.
+    gn_sum_t* slots = nullptr;
+    int next_slot = 0;
+    gn_sum_t* new_gn_slot() {
+        if (next_slot >= kMaxGnSlots) {
+            rc = ctx->fail(CDC_ERR_SHAPE, "too many GroupNorms in one sequence");
+            return slots;
+        }
+        return slots + static_cast<size_t>(next_slot++) * ctx->B * 64;
+    }
+    void clear_slots_op() {  // placeholder op: sized when the sequence is complete (see finish())
+        Op z;
+        z.name = "gn.clear";
+        cdc_ctx* c = ctx;
+        gn_sum_t* base = slots;
+        const int* used = ops == &ctx->step_ops ? &ctx->gn_used_step : &ctx->gn_used_ctx;
+        z.run = [c, base, used](cudaStream_t s, int) {
+            return cudaMemsetAsync(base, 0, static_cast<size_t>(*used) * c->B * 64 * sizeof(gn_sum_t), s);
+        };
+        ops->push_back(z);
+    }
+    // GroupNorm (+FiLM of step k) apply: coefficients come from the accumulator slot inside the kernel
+    void gn(const std::string& name, const std::string& gnp, int film_idx, const gn_sum_t* acc, Act x, const act_t* res, Act y,
             bool silu) {
         if (rc) return;
         cdc_ctx* c = ctx;
@@ -720,22 +662,15 @@ struct PlanB {
         const float* beta = find_w(c, gnp + ".bias")->p;
         const int Cc = x.C, HW = x.H * x.W, B = c->B;
         const int foff = film_idx >= 0 ? c->film_off[film_idx] : -1;
-        Op f;
-        f.name = name + ".finalize";
-        f.bytes = static_cast<double>(B) * PT * 64 * 4;
-        f.run = [c, PT, gamma, beta, foff, Cc, HW, B](cudaStream_t s, int k) {
-            const float* film = foff >= 0 ? c->film + static_cast<size_t>(k) * c->film_total + foff : nullptr;
-            return launch_gn_finalize(c->partials, PT, gamma, beta, film, c->ab, B, Cc, HW, c->cfg.gn_eps, s);
-        };
-        ops->push_back(f);
         Op a;
         a.name = name + (silu ? ".apply_silu" : ".apply") + (res ? "_res" : "");
         a.bytes = static_cast<double>(B) * HW * Cc * 2 * (res ? 3 : 2);
         const act_t *xp = x.p, *rp = res;
         act_t* yp = y.p;
         const int si = silu ? 1 : 0;
-        a.run = [c, xp, rp, yp, B, HW, Cc, si](cudaStream_t s, int) {
-            return launch_gn_apply(xp, c->ab, rp, yp, B, HW, Cc, si, c->num_sms, s);
+        a.run = [c, acc, gamma, beta, foff, xp, rp, yp, B, HW, Cc, si](cudaStream_t s, int k) {
+            const float* film = foff >= 0 ? c->film + static_cast<size_t>(k) * c->film_total + foff : nullptr;
+            return launch_gn_apply(xp, acc, gamma, beta, film, c->cfg.gn_eps, rp, yp, B, HW, Cc, si, c->num_sms, s);
         };
         ops->push_back(a);
     }
@@ -753,9 +688,9 @@ struct PlanB {
         c1.out = t1;
         c1.epi = EPI_STATS;
         c1.cpg = cpg;
-        c1.stats = ctx->partials;
+        c1.gn_acc = new_gn_slot();
         conv(c1);
-        gn(name + ".gn1", wp + ".gn1", film_idx, conv_num_partials(c1, ctx->B, ctx->num_sms), t1, nullptr, t1, true);
+        gn(name + ".gn1", wp + ".gn1", film_idx, c1.gn_acc, t1, nullptr, t1, true);
         ConvBuild c2;
         c2.name = name + ".conv2";
         c2.srcs = {t1};
@@ -763,7 +698,7 @@ struct PlanB {
         c2.out = t2;
         c2.epi = EPI_STATS;
         c2.cpg = cpg;
-        c2.stats = ctx->partials;
+        c2.gn_acc = new_gn_slot();
         conv(c2);
         const act_t* resp = in[0].p;
         if (cin != cout) {
@@ -777,15 +712,9 @@ struct PlanB {
             conv(cr);
             resp = r.p;
         }
-        gn(name + ".gn2", wp + ".gn2", -1, conv_num_partials(c2, ctx->B, ctx->num_sms), t2, resp, out, true);
+        gn(name + ".gn2", wp + ".gn2", -1, c2.gn_acc, t2, resp, out, true);
     }
 };
-
-static size_t max_partials_floats(cdc_ctx* ctx) {
-    // upper bound: one partial row (64 floats) per 128-pixel tile of the largest level, plus slack for ragged tiles
-    const size_t px = static_cast<size_t>(ctx->H) * ctx->W;
-    return static_cast<size_t>(ctx->B) * (px / 64 + 64) * 64;
-}
 
 static int build_plans(cdc_ctx* ctx) {
     const int B = ctx->B, H = ctx->H, W = ctx->W;
@@ -794,14 +723,16 @@ static int build_plans(cdc_ctx* ctx) {
     const size_t px = static_cast<size_t>(B) * H * W;
     CK(ar.alloc(reinterpret_cast<void**>(&ctx->xs), px * 3 * 4));
     CK(ar.alloc(reinterpret_cast<void**>(&ctx->x0s), px * 3 * 4));
-    CK(ar.alloc(reinterpret_cast<void**>(&ctx->partials), max_partials_floats(ctx) * 4));
-    CK(ar.alloc(reinterpret_cast<void**>(&ctx->ab), static_cast<size_t>(B) * 512 * sizeof(float2)));
+    CK(ar.alloc(reinterpret_cast<void**>(&ctx->gn_slots), 2 * static_cast<size_t>(kMaxGnSlots) * B * 64 * sizeof(gn_sum_t)));
+
     ctx->stage_elems = px * 64;  // largest NCHW fp32 tensor crossing the boundary (c0)
     CK(ar.alloc(reinterpret_cast<void**>(&ctx->stage_f32), ctx->stage_elems * 4));
 
     PlanB pb;
     pb.ctx = ctx;
     pb.ops = &ctx->step_ops;
+    pb.slots = ctx->gn_slots;
+    pb.clear_slots_op();
     ctx->xpad = pb.act(64, H, W);
     if (pb.rc) return pb.rc;
     CK(cudaMemset(ctx->xpad.p, 0, px * 64 * 2));
@@ -852,9 +783,10 @@ static int build_plans(cdc_ctx* ctx) {
         st.name = "mid.attn.gn.stats";
         st.bytes = static_cast<double>(B) * HW * Cm * 2;
         const act_t* m1p = m1.p;
-        st.run = [c, m1p, B, HW, Cm](cudaStream_t s, int) { return launch_gn_stats(m1p, c->partials, B, HW, Cm, nullptr, s); };
+        gn_sum_t* aslot = pb.new_gn_slot();
+        st.run = [aslot, m1p, B, HW, Cm](cudaStream_t s, int) { return launch_gn_stats(m1p, aslot, B, HW, Cm, s); };
         ctx->step_ops.push_back(st);
-        pb.gn("mid.attn.gn", "mid.attn.gn", -1, gn_stats_num_partials(HW), m1, nullptr, n, false);
+        pb.gn("mid.attn.gn", "mid.attn.gn", -1, aslot, m1, nullptr, n, false);
         ConvBuild cq;
         cq.name = "mid.attn.qkv";
         cq.srcs = {n};
@@ -912,12 +844,15 @@ static int build_plans(cdc_ctx* ctx) {
         pb.conv(cb);
     }
     if (pb.rc) return pb.rc;
+    ctx->gn_used_step = pb.next_slot;
 
     // ---- context net (oracle/codec.py ContextNet): cond = context_net(y_hat), once per image ----
     if (ctx->has_ctx) {
         PlanB pc;
         pc.ctx = ctx;
         pc.ops = &ctx->ctx_ops;
+        pc.slots = ctx->gn_slots + static_cast<size_t>(kMaxGnSlots) * B * 64;
+        pc.clear_slots_op();
         Act hh = ctx->latent;
         for (int i = 3; i >= 0; --i) {
             const int Hl = H >> i, Wl = W >> i;
@@ -934,6 +869,7 @@ static int build_plans(cdc_ctx* ctx) {
             hh = ctx->cond[i];
         }
         if (pc.rc) return pc.rc;
+        ctx->gn_used_ctx = pc.next_slot;
     }
     return CDC_OK;
 }
@@ -1027,8 +963,7 @@ int cdc_create(const cdc_config* cfg, int device, cdc_ctx** out) {
         g_create_err = "cuTensorMapEncodeTiled entry point not found";
         return CDC_ERR_CUDA;
     }
-    if ((e = configure_conv_kernels()) != cudaSuccess || (e = configure_strip_kernels()) != cudaSuccess ||
-        (e = configure_kf_kernels()) != cudaSuccess) {
+    if ((e = configure_conv_kernels()) != cudaSuccess ||         (e = configure_kf_kernels()) != cudaSuccess) {
         g_create_err = std::string("cudaFuncSetAttribute(conv kernels): ") + cudaGetErrorString(e);
         return CDC_ERR_CUDA;
     }
@@ -1330,8 +1265,13 @@ int cdc_decode_host(cdc_ctx* ctx, const float* latent_host, const float* xT_host
     return CDC_OK;
 }
 
-int cdc_launches_per_step(cdc_ctx* ctx) { return ctx ? static_cast<int>(ctx->step_ops.size()) : 0; }
-int cdc_launches_context(cdc_ctx* ctx) { return ctx ? static_cast<int>(ctx->ctx_ops.size()) + 1 : 0; }
+static int count_kernels(const std::vector<Op>& ops) {  // the GroupNorm-slot memset node is not a kernel of ours
+    int n = 0;
+    for (const Op& op : ops) n += op.name != "gn.clear";
+    return n;
+}
+int cdc_launches_per_step(cdc_ctx* ctx) { return ctx ? count_kernels(ctx->step_ops) : 0; }
+int cdc_launches_context(cdc_ctx* ctx) { return ctx ? count_kernels(ctx->ctx_ops) + 1 : 0; }
 
 double cdc_flops_per_step(cdc_ctx* ctx) {
     if (!ctx) return 0;
@@ -1412,7 +1352,7 @@ int cdc_cdf_lookup(const int32_t* q, const float* sigma, const int32_t* cdf, con
 // ---- single-op entry points for kernel-level parity tests ----
 int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1, int B, int H, int W,
                   const float* w_oihw, const float* bias, int cout, int ksize, int mode, int force_bn,
-                  const void* residual, void* out, float* stats, int* pt_out, cdc_stream s) {
+                  const void* residual, void* out, int64_t* gn_sums, cdc_stream s) {
     cdc_ctx tmp;
     cdc_ctx* ctx = &tmp;
     cudaDeviceProp prop;
@@ -1421,7 +1361,7 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
         g_create_err = "not an sm_100 device";
         return CDC_ERR_ARCH;
     }
-    if (configure_conv_kernels() != cudaSuccess || configure_strip_kernels() != cudaSuccess || configure_kf_kernels() != cudaSuccess) {
+    if (configure_conv_kernels() != cudaSuccess || configure_kf_kernels() != cudaSuccess) {
         g_create_err = "cudaFuncSetAttribute(conv kernels) failed";
         return CDC_ERR_CUDA;
     }
@@ -1457,11 +1397,10 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
     cb.out.W = mode == MODE_S2 ? W / 2 : (mode == MODE_UP2 ? 2 * W : W);
     cb.residual = static_cast<const act_t*>(residual);
     cb.force_bn = force_bn;
-    if (stats) {
+    if (gn_sums) {
         cb.epi = EPI_STATS;
         cb.cpg = cout / 32;
-        cb.stats = stats;
-        if (pt_out) *pt_out = conv_num_partials(cb, B, prop.multiProcessorCount);
+        cb.gn_acc = reinterpret_cast<gn_sum_t*>(gn_sums);
     }
     long long* dbg = nullptr;
     long long* dbg_dev = nullptr;
@@ -1535,22 +1474,6 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
         }
         dbg = nullptr;
     }
-    if (dbg) {
-        printf("strip issuer timeline (CTA 0): row: wait_tempty wait_row mma+commit | since previous row start\n");
-        for (int i = 0; i < 24 && dbg[i * 4 + 3]; ++i)
-            printf("  %2d: %6lld %6lld %6lld | %6lld\n", i, dbg[i * 4 + 1] - dbg[i * 4 + 0], dbg[i * 4 + 2] - dbg[i * 4 + 1],
-                   dbg[i * 4 + 3] - dbg[i * 4 + 2], i ? dbg[i * 4 + 0] - dbg[(i - 1) * 4 + 0] : 0LL);
-        printf("row 10 per-tap issue cycles:");
-        for (int i = 0; i < 9; ++i) printf(" %lld", dbg[384 + i + 1] - dbg[384 + i]);
-        printf("\n");
-        printf("epilogue warp 4 timeline: tile: wait_tfull | ldtm math+store butterfly bar+final | total\n");
-        for (int i = 2; i < 20; ++i) {
-            const long long* e = dbg + 256 + i * 8;
-            printf("  %2d: %6lld | %6lld %6lld %6lld %6lld | %6lld\n", i, e[0] - e[4], e[1] - e[0], e[2] - e[1], e[3] - e[2],
-                   e[5] - e[3], e[5] - e[4]);
-        }
-        
-    }
     ar.release();
     if (ce != cudaSuccess) {
         g_create_err = std::string("test_conv: ") + cudaGetErrorString(ce);
@@ -1568,22 +1491,15 @@ int cdc_test_attention(const void* qkv, void* out, int B, int N, int heads, cdc_
 
 int cdc_test_gn(const void* x, const void* r, void* y, const float* gamma, const float* beta, const float* film, int B,
                 int HW, int C, int silu, float eps, cdc_stream s) {
-    float* partials = nullptr;
-    float2* ab = nullptr;
-    const int PT = gn_stats_num_partials(HW);
-    if (cudaMalloc(&partials, static_cast<size_t>(B) * PT * 64 * 4) != cudaSuccess) return CDC_ERR_CUDA;
-    if (cudaMalloc(&ab, static_cast<size_t>(B) * C * sizeof(float2)) != cudaSuccess) {
-        cudaFree(partials);
-        return CDC_ERR_CUDA;
-    }
-    cudaError_t e = launch_gn_stats(static_cast<const act_t*>(x), partials, B, HW, C, nullptr, S(s));
-    if (e == cudaSuccess) e = launch_gn_finalize(partials, PT, gamma, beta, film, ab, B, C, HW, eps, S(s));
+    gn_sum_t* acc = nullptr;
+    if (cudaMalloc(&acc, static_cast<size_t>(B) * 64 * sizeof(gn_sum_t)) != cudaSuccess) return CDC_ERR_CUDA;
+    cudaError_t e = cudaMemsetAsync(acc, 0, static_cast<size_t>(B) * 64 * sizeof(gn_sum_t), S(s));
+    if (e == cudaSuccess) e = launch_gn_stats(static_cast<const act_t*>(x), acc, B, HW, C, S(s));
     if (e == cudaSuccess)
-        e = launch_gn_apply(static_cast<const act_t*>(x), ab, static_cast<const act_t*>(r),
+        e = launch_gn_apply(static_cast<const act_t*>(x), acc, gamma, beta, film, eps, static_cast<const act_t*>(r),
                             static_cast<act_t*>(y), B, HW, C, silu, dev_sms(), S(s));
     if (e == cudaSuccess) e = cudaStreamSynchronize(S(s));
-    cudaFree(partials);
-    cudaFree(ab);
+    cudaFree(acc);
     return e == cudaSuccess ? CDC_OK : CDC_ERR_CUDA;
 }
 

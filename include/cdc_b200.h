@@ -110,10 +110,11 @@ int cdc_cdf_lookup(const int32_t* q, const float* sigma, const int32_t* cdf, con
 
 /* ---- single-op entry points for kernel-level parity tests -------------------------------------- */
 /* conv: x NHWC 16-bit (cdc_act_dtype) sources (1 or 2), w OIHW fp32 (device), bias fp32; mode 0 = stride 1,
- * 1 = stride 2, 2 = nearest-x2 input; out NHWC 16-bit; stats (optional) [B][PT][32][2]. */
+ * 1 = stride 2, 2 = nearest-x2 input; out NHWC 16-bit; gn_sums (optional, ZERO on entry): GroupNorm statistics of the
+ * output, [B][32 groups][2] = (sum, sum of squares) as 64-bit fixed point with 20 fractional bits. */
 int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1, int B, int H, int W,
                   const float* w_oihw, const float* bias, int cout, int ksize, int mode, int force_bn,
-                  const void* residual, void* out, float* stats, int* pt_out, cdc_stream s);
+                  const void* residual, void* out, int64_t* gn_sums, cdc_stream s);
 int cdc_test_attention(const void* qkv, void* out, int B, int N, int heads, cdc_stream s);
 int cdc_test_gn(const void* x, const void* r, void* y, const float* gamma, const float* beta, const float* film,
                 int B, int HW, int C, int silu, float eps, cdc_stream s);

@@ -42,16 +42,14 @@ def _run_conv(srcs, w, b, ksize, mode, force_bn=0, residual=None, stats=False):
     s = [_nhwc_act(t) for t in srcs]
     out = torch.full((B, OH, OW, n_pad), float("nan"), device=DEV, dtype=_act_dtype())
     res = _nhwc_act(residual) if residual is not None else None
-    st = torch.zeros(B * (OH * OW // 64 + 64) * 64, device=DEV, dtype=torch.float32) if stats else None
-    pt = C.c_int(0)
+    st = torch.zeros(B, 32, 2, device=DEV, dtype=torch.int64) if stats else None  # fixed point, 20 fractional bits
     rc = L.cdc_test_conv(0, _ptr(s[0]), s[0].shape[-1], _ptr(s[1]) if len(s) > 1 else C.c_void_p(0),
                          s[1].shape[-1] if len(s) > 1 else 0, B, H, W, _ptr(w.contiguous()), _ptr(b.contiguous()),
-                         cout, ksize, mode, force_bn, _ptr(res), _ptr(out), _ptr(st), C.byref(pt), C.c_void_p(0))
+                         cout, ksize, mode, force_bn, _ptr(res), _ptr(out), _ptr(st), C.c_void_p(0))
     assert rc == 0, L.cdc_last_error(None).decode()
     torch.cuda.synchronize()
     o = out[..., :cout].float().permute(0, 3, 1, 2).contiguous()
-    part = st[: B * pt.value * 64].reshape(B, pt.value, 32, 2) if stats else None
-    return o, part
+    return o, st
 
 
 def _ref_conv(srcs, w, b, ksize, mode, residual=None):
@@ -150,12 +148,12 @@ def test_conv_groupnorm_partials(cfg):
     o, part = _run_conv(srcs, w, b, 3, 0, fbn, stats=True)
     ref = _ref_conv(srcs, w, b, 3, 0)
     _check(o, ref, "stats-conv output")
-    got = part.double().sum(dim=1)  # [B, 32, 2]
+    got = part.double() / 2.0 ** 20  # [B, 32, 2] (sum, sum of squares) per image and group
     rg = ref.double().reshape(B, 32, -1)
     want = torch.stack([rg.sum(-1), (rg * rg).sum(-1)], dim=-1)
     rel = (got - want).abs() / want.abs().clamp(min=1.0)
     assert rel.max().item() < 2e-3, f"GN partials off: {rel.max().item()}"
-    # bitwise reproducible (fixed-order reduction)
+    # bitwise reproducible (integer accumulation is order-independent)
     o2, part2 = _run_conv(srcs, w, b, 3, 0, fbn, stats=True)
     assert torch.equal(part, part2) and torch.equal(o, o2)
 

@@ -122,7 +122,8 @@ def test_flops_and_launch_accounting():
     dec.set_sample_schedule(17)
     dec.bind(1, 256, 256)
     assert abs(dec.flops_per_step() / unet_flops(ocfg, 1, 256, 256) - 1.0) < 1e-6
-    assert dec.launches_per_step() == len(dec.step_ops()) > 100
+    # every op is one kernel of ours except the memset node that clears the GroupNorm accumulators
+    assert dec.launches_per_step() == len(dec.step_ops()) - 1 > 80
 
 
 def test_wrong_shapes_fail_loudly():

@@ -15,9 +15,8 @@ x = torch.randn(B, H, W, cin, device="cuda").to(dt)
 w = (torch.randn(cout, cin, 3, 3, device="cuda") / 24).float()
 b = torch.zeros(cout, device="cuda")
 out = torch.empty(B, H, W, (cout + 63) // 64 * 64, device="cuda", dtype=dt)
-st = torch.zeros(B * (H * W // 64 + 64) * 64, device="cuda")
-pt = C.c_int(0)
+st = torch.zeros(B, 32, 2, device="cuda", dtype=torch.int64)
 for it in range(2):
     rc = L.cdc_test_conv(0, C.c_void_p(x.data_ptr()), cin, None, 0, B, H, W, C.c_void_p(w.data_ptr()), C.c_void_p(b.data_ptr()),
-                         cout, 3, 0, 0, None, C.c_void_p(out.data_ptr()), C.c_void_p(st.data_ptr()), C.byref(pt), None)
+                         cout, 3, 0, 0, None, C.c_void_p(out.data_ptr()), C.c_void_p(st.data_ptr()), None)
     assert rc == 0, L.cdc_last_error(None)
