@@ -12,7 +12,7 @@ SYMBOLS = [
     "cdc_has_context_net", "cdc_set_schedule", "cdc_schedule_index", "cdc_schedule_coeffs", "cdc_bind_io",
     "cdc_set_cond", "cdc_set_latent", "cdc_set_x", "cdc_get_x", "cdc_get_x0", "cdc_denoise_step", "cdc_decode",
     "cdc_decode_host", "cdc_launches_per_step", "cdc_launches_context", "cdc_flops_per_step", "cdc_num_step_ops",
-    "cdc_step_op_name", "cdc_step_op_flops", "cdc_step_op_bytes", "cdc_run_step_op", "cdc_profile_step", "cdc_quantize",
+    "cdc_step_op_name", "cdc_step_op_flops", "cdc_step_op_bytes", "cdc_run_step_op", "cdc_profile_step", "cdc_debug_graph_skip", "cdc_quantize",
     "cdc_cdf_lookup", "cdc_test_conv", "cdc_test_attention", "cdc_test_gn",
 ]
 
@@ -81,6 +81,7 @@ def lib():
     L.cdc_step_op_bytes.restype = C.c_double
     L.cdc_run_step_op.argtypes = [p, i32, i32, p]
     L.cdc_profile_step.argtypes = [p, i32, i32, C.POINTER(C.c_float), p]
+    L.cdc_debug_graph_skip.argtypes = [p, i32]
     L.cdc_quantize.argtypes = [f32p, f32p, i32p, f32p, i64, i64, i64, p]
     L.cdc_cdf_lookup.argtypes = [i32p, f32p, i32p, i32p, i32p, i32p, f32p, i32, i64, i32p, i32p, i32p, i32p, i32p,
                                  i64, p]

@@ -483,6 +483,7 @@ struct cdc_ctx {
     float *pin_in = nullptr, *pin_x = nullptr, *pin_out = nullptr;
     cudaGraphExec_t graph = nullptr;
     int graph_K = 0;
+    int graph_skip = 0;  // measurement only (cdc_debug_graph_skip): class of ops left out of the captured graph
     cudaStream_t cap_stream = nullptr;
 
     int fail(int code, const char* fmt, ...) {
@@ -903,7 +904,10 @@ static int capture_graph(cdc_ctx* ctx) {
     }
     for (int k = 0; k < ctx->K && e == cudaSuccess; ++k)
         for (Op& op : ctx->step_ops) {
-            bool skipped = false;
+            const bool is_conv = op.flops > 0 && op.name.find("sdpa") == std::string::npos;
+            const bool is_attn = op.name.find("sdpa") != std::string::npos;
+            bool skipped = (ctx->graph_skip == 1 && is_conv) || (ctx->graph_skip == 2 && op.flops == 0 && op.name != "gn.clear") ||
+                           (ctx->graph_skip == 3 && is_attn);
             for (const std::string& w : skip) skipped = skipped || op.name.find(w) != std::string::npos;
             if (skipped) continue;
             e = op.run(ctx->cap_stream, k);
@@ -1297,6 +1301,16 @@ int cdc_run_step_op(cdc_ctx* ctx, int i, int k, cdc_stream s) {
     NEED_PLAN();
     if (i < 0 || i >= static_cast<int>(ctx->step_ops.size()) || k < 0 || k >= ctx->K) return ctx->fail(CDC_ERR_SHAPE, "bad op/step index");
     CK(ctx->step_ops[i].run(S(s), k));
+    return CDC_OK;
+}
+
+// Measurement only: leave a class of ops out of the captured graph (0 = none, 1 = the tcgen05 convs, 2 = the
+// elementwise / GroupNorm kernels, 3 = attention), so that a class's in-graph cost is the difference of two replay
+// times.  The decoded image is garbage while a class is skipped.
+int cdc_debug_graph_skip(cdc_ctx* ctx, int op_class) {
+    if (!ctx || op_class < 0 || op_class > 3) return CDC_ERR_SHAPE;
+    if (op_class != ctx->graph_skip) drop_graph(ctx);
+    ctx->graph_skip = op_class;
     return CDC_OK;
 }
 

@@ -96,6 +96,9 @@ double cdc_step_op_bytes(cdc_ctx* ctx, int i);
 int cdc_run_step_op(cdc_ctx* ctx, int i, int k, cdc_stream s);
 /* in-stream device time (microseconds) of every op of step k, after `warm` untimed steps; us_out[cdc_num_step_ops] */
 int cdc_profile_step(cdc_ctx* ctx, int k, int warm, float* us_out, cdc_stream s);
+/* measurement only: leave a class of ops out of the captured graph (0 none, 1 tcgen05 convs, 2 elementwise/GroupNorm,
+ * 3 attention) so that the class's in-graph cost is a difference of replay times; the image is garbage meanwhile */
+int cdc_debug_graph_skip(cdc_ctx* ctx, int op_class);
 
 /* ---- oracle/entropy.py quantize_symbols / cdf_lookup (stateless) ------------------------------- */
 /* q = rint(y - mu) int32 (half-to-even), y_hat = q + mu.  mu_mod == 0: mu is elementwise;
