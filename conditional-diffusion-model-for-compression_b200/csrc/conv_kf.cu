@@ -43,13 +43,18 @@ constexpr int kKfRowTx = 130 * 128;
 constexpr int kKfAcc = 8;               // accumulator ring
 constexpr int kKfAux = 1024 + 2 * 8 * 16 * 2 * 4;  // barriers + TMEM holder + bias, stats scratch
 
-template <int BN, int CPG, int EPI, int CH, bool STAGE, bool XK16>
+template <int BN, int CPG, int EPI, int CH, bool STAGE, bool XK16, int MODE>
 __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __grid_constant__ KfParams p) {
     constexpr int WB = BN * 128;  // one (tap, chunk) weight block
     constexpr uint32_t WB16 = WB >> 4;
     constexpr int TMEM_COLS = kKfAcc * BN <= 128 ? 128 : kKfAcc * BN <= 256 ? 256 : 512;  // power of two
     constexpr int STAGE_BYTES = STAGE ? 2 * 128 * BN * 2 : 0;
     static_assert(!STAGE || BN == 64, "staged TMA store is built for 128-byte output rows");
+    // MODE 0: 3x3 conv.  MODE 1: nearest-x2 upsample + 3x3 conv as four 2x2 convs on the low-resolution input, one
+    // per output parity (py, px) with pre-summed weights (repack_weight_up2_kernel): N tile nt = (channel tile, parity),
+    // taps kh in {py, py+1}, kw in {px, px+1} of the 3x3 window, output pixel (2h + py, 2w + px).
+    constexpr int NKH = MODE == 1 ? 2 : 3, NKW = MODE == 1 ? 2 : 3;
+    static_assert(MODE == 0 || (!STAGE && EPI == EPI_STORE && !XK16), "UP2 mode: plain scattered store only");
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
@@ -58,7 +63,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
     const int NS = p.NS;
     const uint32_t ring = base;
     const uint32_t wbase = ring + NS * kKfRowBytes;
-    const uint32_t stage = wbase + 9 * CH * WB;
+    const uint32_t stage = wbase + NKH * NKW * CH * WB;
     const uint32_t aux = stage + STAGE_BYTES;
     uint8_t* aux_gen = gen + (aux - base);
     // barriers: row_full[4] row_empty[4] tfull[8] tempty[8] wres
@@ -69,6 +74,8 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nt = blockIdx.x / p.G1, cta = blockIdx.x % p.G1;
+    const int py = MODE == 1 ? (nt & 3) >> 1 : 0, px = MODE == 1 ? nt & 1 : 0;  // output parity (UP2)
+    const int cot = MODE == 1 ? nt >> 2 : nt;                                     // output-channel tile
     const bool kdbg = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 32;
     if (kdbg) {
         p.dbg[500] = clock64();
@@ -99,7 +106,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
         tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_holder)), TMEM_COLS);
         tmem_relinquish();
     }
-    for (int i = threadIdx.x; i < BN; i += 128 + kEpiThreads) bias_s[i] = p.bias[nt * BN + i];
+    for (int i = threadIdx.x; i < BN; i += 128 + kEpiThreads) bias_s[i] = p.bias[cot * BN + i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -109,12 +116,20 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
     if (warp == 3 && lane == 0) {
         // Weights are constants: their load need not wait for the preceding kernel (PDL).
         // smem block order [kw][chunk][2 - kh]: the kh taps of one (kw, chunk) form one contiguous B operand.
-        mbar_expect_tx(bar_wres, 9 * CH * WB);
-        for (int kh = 0; kh < 3; ++kh)
-            for (int kw = 0; kw < 3; ++kw)
-                for (int ch = 0; ch < CH; ++ch)
-                    tma_load_2d(wbase + ((kw * CH + ch) * 3 + (2 - kh)) * WB, &p.wmap, bar_wres,
-                                ((kh * 3 + kw) * CH + ch) * 64, nt * BN);
+        mbar_expect_tx(bar_wres, NKH * NKW * CH * WB);
+        if constexpr (MODE == 0) {
+            for (int kh = 0; kh < 3; ++kh)
+                for (int kw = 0; kw < 3; ++kw)
+                    for (int ch = 0; ch < CH; ++ch)
+                        tma_load_2d(wbase + ((kw * CH + ch) * 3 + (2 - kh)) * WB, &p.wmap, bar_wres,
+                                    ((kh * 3 + kw) * CH + ch) * 64, cot * BN);
+        } else {  // pre-summed parity weights: K index ((parity * 4 + a * 2 + b) * CH + chunk) * 64
+            for (int a2 = 0; a2 < 2; ++a2)
+                for (int b2 = 0; b2 < 2; ++b2)
+                    for (int ch = 0; ch < CH; ++ch)
+                        tma_load_2d(wbase + ((b2 * CH + ch) * 2 + (1 - a2)) * WB, &p.wmap, bar_wres,
+                                    (((nt & 3) * 4 + a2 * 2 + b2) * CH + ch) * 64, cot * BN);
+        }
     }
     pdl_launch_dependents();
     pdl_wait();  // everything below touches activations written by the preceding kernels
@@ -169,7 +184,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
         {
             constexpr uint32_t idesc0 = make_idesc_f16(128, 0);
             constexpr uint32_t NB = static_cast<uint32_t>(BN >> 3) << 17;  // idesc increment per window slot
-            constexpr int T = 12, TH = 6;  // K steps per (input row, chunk); position of the wait for the next chunk
+            constexpr int T = 4 * NKW, TH = T / 2;  // K steps per (input row, chunk); position of the wait for the next chunk
             const uint64_t desc_hi = make_sw128_desc(0) & 0xFFFFFFFF00000000ull;
             const uint32_t wlo = wbase >> 4;
             uint32_t rslot = 0, rpar = 0;
@@ -184,13 +199,15 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
                 tc_fence_after();
                 if (kdbg && u == cta) p.dbg[504] = clock64();
                 for (int i = 0; i < L + 2; ++i) {
-                    const int jlo = i >= 2 ? i - 2 : 0;
-                    const int jhi = i < L ? i : L - 1;
-                    const uint32_t cnt = static_cast<uint32_t>(jhi - jlo + 1);
+                    // input row i feeds output rows j = i - py - e, e = 0 .. NKH-1 (kh = py + e); clipped to the strip
+                    const int jtop = i - py;
+                    const int jlo = jtop - (NKH - 1) > 0 ? jtop - (NKH - 1) : 0;
+                    const int jhi = jtop < L ? jtop : L - 1;
+                    const uint32_t cnt = jhi >= jlo ? static_cast<uint32_t>(jhi - jlo + 1) : 0u;  // 0: nothing to issue (UP2 edge rows)
                     const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && u == cta && i < 40 && lane == 0;
                     if (dbg) p.dbg[i * 4 + 0] = clock64();
                     const uint32_t slo = (g + jlo) & 7;
-                    const uint32_t khp = static_cast<uint32_t>(2 - (i - jlo));  // reversed kh of the first window slot
+                    const uint32_t khp = static_cast<uint32_t>((NKH - 1) - (jtop - jlo));  // reversed kh of the first window slot
                     const uint32_t nA = cnt < 8 - slo ? cnt : 8 - slo, nB = cnt - nA;
                     const uint32_t dA = tmem_base + slo * BN, dB = tmem_base;
                     const uint32_t bA = khp * WB16, bB = (khp + nA) * WB16;
@@ -204,10 +221,10 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
                             constexpr int t0 = decltype(t0c)::value, t1 = decltype(t1c)::value;
 #pragma unroll
                             for (int t = t0; t < t1; ++t) {
-                                const int k = t & 3, kw = t >> 2;
+                                const int k = t & 3, kw = t >> 2;  // kw: index into the NKW horizontal taps
                                 if (XK16 && ch == 0 && k != 0) continue;  // stem: chunk 0 = x_t, channels 16..63 are zero
-                                const uint32_t alo = alo_base + kw * 8 + 2 * k;
-                                const uint32_t blo = wlo + ((kw * CH + ch) * 3) * WB16 + 2 * k;
+                                const uint32_t alo = alo_base + (kw + px) * 8 + 2 * k;
+                                const uint32_t blo = wlo + ((kw * CH + ch) * NKH) * WB16 + 2 * k;
                                 umma_f16_ss(dA, desc_hi | alo, desc_hi | (blo + bA), iA, 1u);
                             }
                             if (nB != 0) {
@@ -215,13 +232,13 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
                                 for (int t = t0; t < t1; ++t) {
                                     const int k = t & 3, kw = t >> 2;
                                     if (XK16 && ch == 0 && k != 0) continue;
-                                    const uint32_t alo = alo_base + kw * 8 + 2 * k;
-                                    const uint32_t blo = wlo + ((kw * CH + ch) * 3) * WB16 + 2 * k;
+                                    const uint32_t alo = alo_base + (kw + px) * 8 + 2 * k;
+                                    const uint32_t blo = wlo + ((kw * CH + ch) * NKH) * WB16 + 2 * k;
                                     umma_f16_ss(dB, desc_hi | alo, desc_hi | (blo + bB), iB, 1u);
                                 }
                             }
                         };
-                        if (elect_one_sync()) steps(std::integral_constant<int, 0>{}, std::integral_constant<int, TH>{});
+                        if (cnt != 0 && elect_one_sync()) steps(std::integral_constant<int, 0>{}, std::integral_constant<int, TH>{});
                         __syncwarp();
                         if (dbg && ch == 0) p.dbg[i * 4 + 1] = clock64();
                         const uint32_t nslot = rslot + 1 == static_cast<uint32_t>(NS) ? 0u : rslot + 1;
@@ -231,7 +248,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
                         }
                         if (dbg && ch == 0) p.dbg[i * 4 + 2] = clock64();
                         if (elect_one_sync()) {
-                            steps(std::integral_constant<int, TH>{}, std::integral_constant<int, T>{});
+                            if (cnt != 0) steps(std::integral_constant<int, TH>{}, std::integral_constant<int, T>{});
                             umma_commit(bar_rempty + 8 * rslot);  // chunk consumed
                             if (ch == CH - 1 && i >= 2) umma_commit(bar_tfull + 8 * ((g + i - 2) & 7));  // output row i-2 complete
                         }
@@ -387,14 +404,22 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
                         named_bar_sync(1, kEpiThreads);
                         if (edbg) edbg[5] = clock64();
                         if (store_leader) {
-                            tma_store_4d(&p.omap, stage + (tile_ctr & 1) * (128 * BN * 2), nt * BN, seg * 128, h0 + j, b);
+                            tma_store_4d(&p.omap, stage + (tile_ctr & 1) * (128 * BN * 2), cot * BN, seg * 128, h0 + j, b);
                             bulk_commit_group();
                         }
                     } else if (valid) {
-                        const size_t pix = (static_cast<size_t>(b) * p.H + (h0 + j)) * p.W + gx;
-                        uint4* dst = reinterpret_cast<uint4*>(p.out + pix * p.ldc + nt * BN + half * HC);
+                        const size_t pix = MODE == 1 ? (static_cast<size_t>(b) * 2 * p.H + 2 * (h0 + j) + py) * (2 * p.W) + 2 * gx + px
+                                                     : (static_cast<size_t>(b) * p.H + (h0 + j)) * p.W + gx;
+                        uint4* dst = reinterpret_cast<uint4*>(p.out + pix * p.ldc + cot * BN + half * HC);
+                        // thread = pixel: its channels are contiguous, lanes are a pixel pitch apart.  32-byte stores fill
+                        // whole sectors and halve the store instructions (each costs ~1 cycle per distinct line)
+                        if constexpr (HC % 16 == 0) {
 #pragma unroll
-                        for (int s4 = 0; s4 < HC / 8; ++s4) dst[s4] = o[s4];
+                            for (int s8 = 0; s8 < HC / 16; ++s8) st_global_v8(dst + 2 * s8, o[2 * s8], o[2 * s8 + 1]);
+                        } else {
+#pragma unroll
+                            for (int s4 = 0; s4 < HC / 8; ++s4) dst[s4] = o[s4];
+                        }
                     }
                     if (edbg) edbg[6] = clock64();
                 }
@@ -417,7 +442,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
                         const float* r0 = red + ((hh * 4) * 16 + gl) * 2;
                         const float s = ((r0[0] + r0[32]) + r0[64]) + r0[96];
                         const float s2 = ((r0[1] + r0[33]) + r0[65]) + r0[97];
-                        gn_sums_add(p.gn_acc + static_cast<size_t>(b) * 64, nt * (BN / CPG) + t, s, s2);
+                        gn_sums_add(p.gn_acc + static_cast<size_t>(b) * 64, cot * (BN / CPG) + t, s, s2);
                     }
                 }
             }
@@ -438,32 +463,34 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
 }
 
 // ------------------------------------------------------------------------------------------------ host
-// (BN, CPG, EPI, CH, STAGED) instantiations: the layer shapes of the UNet / context net this variant serves.
-#define KF_ALL_CASES()                           \
-    KF_CASE(64, 2, EPI_STATS, 1, true, false)    \
-    KF_CASE(64, 2, EPI_STATS, 2, false, false)   \
-    KF_CASE(64, 4, EPI_STATS, 1, true, false)    \
-    KF_CASE(64, 4, EPI_STATS, 2, false, false)   \
-    KF_CASE(64, 1, EPI_STORE, 1, true, false)    \
-    KF_CASE(64, 1, EPI_STORE, 2, false, false)   \
-    KF_CASE(64, 1, EPI_STORE, 2, false, true)    \
-    KF_CASE(32, 4, EPI_STATS, 3, false, false)   \
-    KF_CASE(32, 4, EPI_STATS, 4, false, false)   \
-    KF_CASE(48, 6, EPI_STATS, 3, false, false)   \
-    KF_CASE(32, 8, EPI_STATS, 4, false, false)   \
-    KF_CASE(16, 1, EPI_DDIM, 1, false, false)
+// (BN, CPG, EPI, CH, STAGED, XK16, MODE) instantiations: the layer shapes of the UNet / context net this variant serves.
+#define KF_ALL_CASES()                              \
+    KF_CASE(64, 2, EPI_STATS, 1, true, false, 0)    \
+    KF_CASE(64, 2, EPI_STATS, 2, false, false, 0)   \
+    KF_CASE(64, 4, EPI_STATS, 1, true, false, 0)    \
+    KF_CASE(64, 4, EPI_STATS, 2, false, false, 0)   \
+    KF_CASE(64, 1, EPI_STORE, 1, true, false, 0)    \
+    KF_CASE(64, 1, EPI_STORE, 2, false, false, 0)   \
+    KF_CASE(64, 1, EPI_STORE, 2, false, true, 0)    \
+    KF_CASE(32, 4, EPI_STATS, 3, false, false, 0)   \
+    KF_CASE(32, 4, EPI_STATS, 4, false, false, 0)   \
+    KF_CASE(48, 6, EPI_STATS, 3, false, false, 0)   \
+    KF_CASE(32, 8, EPI_STATS, 4, false, false, 0)   \
+    KF_CASE(16, 1, EPI_DDIM, 1, false, false, 0)    \
+    KF_CASE(64, 1, EPI_STORE, 2, false, false, 1)   \
+    KF_CASE(64, 1, EPI_STORE, 3, false, false, 1)   \
+    KF_CASE(64, 1, EPI_STORE, 4, false, false, 1)
 
-int kf_smem_bytes(int bn, int CH, int NS, bool staged) {
-    return 1024 + NS * kKfRowBytes + 9 * CH * bn * 128 + (staged ? 2 * 128 * bn * 2 : 0) + kKfAux;
+int kf_smem_bytes(int bn, int CH, int NS, bool staged, int mode) {
+    return 1024 + NS * kKfRowBytes + (mode == 1 ? 4 : 9) * CH * bn * 128 + (staged ? 2 * 128 * bn * 2 : 0) + kKfAux;
 }
 
-bool kf_plan(int bn, int CH, int* NS, bool* staged) {
+bool kf_plan(int bn, int CH, int mode, int* NS, bool* staged) {
     const int limit = 227 * 1024;
-    static const bool nostage = getenv("CDC_KF_NOSTAGE") != nullptr;  // experiment switch
-    for (int st = nostage ? 0 : 1; st >= 0; --st) {  // NS = ring slots of one (row, chunk) each
+    for (int st = mode == 1 ? 0 : 1; st >= 0; --st) {  // NS = ring slots of one (row, chunk) each
         if (st && bn != 64) continue;
         for (int ns = 4; ns >= 3; --ns)
-            if (kf_smem_bytes(bn, CH, ns, st != 0) <= limit) {
+            if (kf_smem_bytes(bn, CH, ns, st != 0, mode) <= limit) {
                 *NS = ns;
                 *staged = st != 0;
                 return true;
@@ -472,12 +499,12 @@ bool kf_plan(int bn, int CH, int* NS, bool* staged) {
     return false;
 }
 
-bool kf_inst_ok(int bn, int cpg, int epi, int CH) {
+bool kf_inst_ok(int bn, int cpg, int epi, int CH, int mode) {
     int ns;
     bool st;
-    if (!kf_plan(bn, CH, &ns, &st)) return false;
-#define KF_CASE(BN_, CPG_, EPI_, CH_, ST_, X_) \
-    if (bn == BN_ && (EPI_ != EPI_STATS || cpg == CPG_) && epi == EPI_ && CH == CH_ && st == ST_) return true;
+    if (!kf_plan(bn, CH, mode, &ns, &st)) return false;
+#define KF_CASE(BN_, CPG_, EPI_, CH_, ST_, X_, M_) \
+    if (bn == BN_ && (EPI_ != EPI_STATS || cpg == CPG_) && epi == EPI_ && CH == CH_ && st == ST_ && mode == M_) return true;
     KF_ALL_CASES()
 #undef KF_CASE
     return false;
@@ -485,8 +512,8 @@ bool kf_inst_ok(int bn, int cpg, int epi, int CH) {
 
 cudaError_t configure_kf_kernels() {
     cudaError_t e;
-#define KF_CASE(BN_, CPG_, EPI_, CH_, ST_, X_)                                                              \
-    if ((e = cudaFuncSetAttribute(conv_kf_kernel<BN_, CPG_, EPI_, CH_, ST_, X_>,                              \
+#define KF_CASE(BN_, CPG_, EPI_, CH_, ST_, X_, M_)                                                          \
+    if ((e = cudaFuncSetAttribute(conv_kf_kernel<BN_, CPG_, EPI_, CH_, ST_, X_, M_>,                          \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) \
         return e;
     KF_ALL_CASES()
@@ -494,15 +521,15 @@ cudaError_t configure_kf_kernels() {
     return cudaSuccess;
 }
 
-cudaError_t launch_conv_kf(const KfParams& p, int bn, int cpg, int epi, int CH, bool xk16, cudaStream_t stream) {
+cudaError_t launch_conv_kf(const KfParams& p, int bn, int cpg, int epi, int CH, bool xk16, int mode, cudaStream_t stream) {
     int ns;
     bool st;
-    if (!kf_plan(bn, CH, &ns, &st) || ns != p.NS) return cudaErrorInvalidValue;
+    if (!kf_plan(bn, CH, mode, &ns, &st) || ns != p.NS) return cudaErrorInvalidValue;
     const dim3 grid(p.n_tiles * p.G1), block(128 + kEpiThreads);
-    const size_t smem = kf_smem_bytes(bn, CH, ns, st);
-#define KF_CASE(BN_, CPG_, EPI_, CH_, ST_, X_)                                                                \
-    if (bn == BN_ && (EPI_ != EPI_STATS || cpg == CPG_) && epi == EPI_ && CH == CH_ && st == ST_ && xk16 == X_)   \
-        return launch_pdl(conv_kf_kernel<BN_, CPG_, EPI_, CH_, ST_, X_>, grid, block, smem, stream, p);
+    const size_t smem = kf_smem_bytes(bn, CH, ns, st, mode);
+#define KF_CASE(BN_, CPG_, EPI_, CH_, ST_, X_, M_)                                                                            \
+    if (bn == BN_ && (EPI_ != EPI_STATS || cpg == CPG_) && epi == EPI_ && CH == CH_ && st == ST_ && xk16 == X_ && mode == M_)   \
+        return launch_pdl(conv_kf_kernel<BN_, CPG_, EPI_, CH_, ST_, X_, M_>, grid, block, smem, stream, p);
     KF_ALL_CASES()
 #undef KF_CASE
     return cudaErrorInvalidValue;

@@ -9,11 +9,11 @@ struct alignas(64) KfParams {
     CUtensorMap wmap;     // weights [n_pad][9 * CH * 64] K-major, box {64, BN}
     CUtensorMap omap;     // output, box {BN ch, 128 px, 1 row, 1 image} (staged TMA store only)
     int chunks0;          // 64-channel chunks that come from source 0 (the rest from source 1)
-    int H, W, batch;
+    int H, W, batch;      // INPUT grid (mode 1: the low-resolution tensor; the output is 2H x 2W)
     int nseg;             // ceil(W / 128) column segments
     int S;                // strips per column (rows are spread evenly over them)
     int NS;               // input-row ring slots
-    int n_tiles;          // N tiles of BN output channels; every CTA keeps ONE tile's weights resident
+    int n_tiles;          // N tiles (mode 1: channel tiles x 4 parities); every CTA keeps ONE tile's weights resident
     int G1;               // CTAs per N tile (grid = n_tiles * G1)
     int ldc;              // channels of the output tensor
     act_t* out;
@@ -26,10 +26,12 @@ struct alignas(64) KfParams {
     long long* dbg;       // optional: issuer / epilogue timeline of CTA 0 (clock64 stamps), tools only
 };
 
-bool kf_inst_ok(int bn, int cpg, int epi, int CH);
-bool kf_plan(int bn, int CH, int* NS, bool* staged);  // shared-memory plan; false if the weights do not fit
-int kf_smem_bytes(int bn, int CH, int NS, bool staged);
+// mode 0: 3x3 conv; mode 1: nearest-x2 upsample + 3x3 conv (four parity 2x2 convs on the low-resolution input)
+bool kf_inst_ok(int bn, int cpg, int epi, int CH, int mode);
+bool kf_plan(int bn, int CH, int mode, int* NS, bool* staged);  // shared-memory plan; false if the weights do not fit
+int kf_smem_bytes(int bn, int CH, int NS, bool staged, int mode);
 cudaError_t configure_kf_kernels();
-cudaError_t launch_conv_kf(const KfParams& p, int bn, int cpg, int epi, int CH, bool xk16, cudaStream_t stream);  // xk16: chunk 0 has 16 real channels (stem)
+cudaError_t launch_conv_kf(const KfParams& p, int bn, int cpg, int epi, int CH, bool xk16, int mode,
+                           cudaStream_t stream);  // xk16: chunk 0 has 16 real channels (stem)
 
 }  // namespace cdc

@@ -82,6 +82,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* desc, uint
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// 256-bit global store (sm_100: STG.256): one full 32-byte sector per lane.  p must be 32-byte aligned.
+__device__ __forceinline__ void st_global_v8(void* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+                 "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
 // TMA store of one 4-D box shared -> global (bulk async-group completion).  Pixels of the box that fall
 // outside the tensor are clipped by the hardware.
 __device__ __forceinline__ void tma_store_4d(const void* desc, uint32_t src, int c0, int c1, int c2, int c3) {

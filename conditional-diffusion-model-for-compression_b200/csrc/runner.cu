@@ -173,7 +173,7 @@ static void conv_geometry(const ConvBuild& cb, int& gw, int& gh, int& nphase, in
 
 // ---- kh-fused strip variant (conv_kf.cu): 3x3, stride 1, resident weights, N tiles of 64 (16 for the final conv) ----
 struct KfGeom {
-    int bn, CH, n_tiles, nseg, S, G1, NS;
+    int bn, CH, n_tiles, nseg, S, G1, NS, mode;
     bool staged;
 };
 static bool kf_disabled() {
@@ -182,10 +182,14 @@ static bool kf_disabled() {
     return v == 1;
 }
 static bool conv_uses_kf(const ConvBuild& cb, int B, int num_sms, KfGeom* g) {
-    if (kf_disabled() || cb.mode != MODE_S1 || cb.ksize != 3 || cb.force_bn != 0 || cb.residual) return false;
+    if (kf_disabled() || cb.mode == MODE_S2 || cb.ksize != 3 || cb.force_bn != 0 || cb.residual) return false;
+    g->mode = cb.mode == MODE_UP2 ? 1 : 0;
+    if (g->mode == 1 && (!cb.w->up2 || cb.epi != EPI_STORE)) return false;
     const int gw = cb.srcs[0].W, gh = cb.srcs[0].H;
     g->nseg = (gw + 127) / 128;
-    if (gw * 100 < g->nseg * 128 * 35) return false;  // segments are 128 pixels wide: too much of the tile would be padding
+    // segments are 128 pixels wide: too much of the tile would be padding (measured break-even against conv_tc.cu:
+    // 3x3 convs down to 48 of 128 columns; the upsampling convs need 96)
+    if (gw * 100 < g->nseg * 128 * (cb.mode == MODE_UP2 ? 50 : 35)) return false;
     int ctot = 0;
     for (const Act& a : cb.srcs) ctot += a.C;
     g->CH = ctot / 64;
@@ -195,12 +199,12 @@ static bool conv_uses_kf(const ConvBuild& cb, int B, int num_sms, KfGeom* g) {
     for (int c : cands) {
         const int bn = cb.epi == EPI_DDIM ? 16 : c;
         if (cb.w->n_pad % bn || (cb.epi == EPI_STATS && bn % cb.cpg)) continue;
-        if (!kf_inst_ok(bn, cb.cpg, cb.epi, g->CH) || !kf_plan(bn, g->CH, &g->NS, &g->staged)) continue;
+        if (!kf_inst_ok(bn, cb.cpg, cb.epi, g->CH, g->mode) || !kf_plan(bn, g->CH, g->mode, &g->NS, &g->staged)) continue;
         g->bn = bn;
         break;
     }
     if (!g->bn) return false;
-    g->n_tiles = cb.w->n_pad / g->bn;
+    g->n_tiles = cb.w->n_pad / g->bn * (g->mode == 1 ? 4 : 1);
     if (cb.epi == EPI_DDIM && g->n_tiles != 1) return false;
     g->nseg = (gw + 127) / 128;
     const int cols = B * g->nseg;  // independent strip columns per N tile
@@ -277,20 +281,22 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
             kp->dbg = cb.dbg;
             const double Ms = static_cast<double>(B) * gh * gw;
             op->name = cb.name;
-            op->flops = 2.0 * Ms * w.n_true * (9.0 * w.c_true);
-            op->bytes = 2.0 * (Ms * w.c_true + Ms * w.n_true + 9.0 * w.c_true * w.n_true);
+            const double Mout = Ms * (kg.mode == 1 ? 4.0 : 1.0);  // algorithmic: the 3x3 conv on the upsampled grid
+            op->flops = 2.0 * Mout * w.n_true * (9.0 * w.c_true);
+            op->bytes = 2.0 * (Ms * w.c_true + Mout * w.n_true + 9.0 * w.c_true * w.n_true);
             const int epi = cb.epi, cpg = cb.cpg, bn_k = kg.bn, CHk = kg.CH;
-            const bool xk = cb.x16 && cb.epi == EPI_STORE && kg.bn == 64 && kg.CH == 2 && cb.srcs[0].C == 64;
+            const bool xk = cb.x16 && cb.epi == EPI_STORE && kg.bn == 64 && kg.CH == 2 && cb.srcs[0].C == 64 && kg.mode == 0;
+            const int kmode = kg.mode;
             const std::vector<float>*c0 = cb.c0, *c1 = cb.c1;
-            op->run = [kp, bn_k, cpg, epi, CHk, xk, c0, c1](cudaStream_t s, int k) -> cudaError_t {
+            op->run = [kp, bn_k, cpg, epi, CHk, xk, kmode, c0, c1](cudaStream_t s, int k) -> cudaError_t {
                 if (epi == EPI_DDIM) {
                     if (!c0 || k < 0 || k >= static_cast<int>(c0->size())) return cudaErrorInvalidValue;
                     KfParams q = *kp;
                     q.c0 = (*c0)[k];
                     q.c1 = (*c1)[k];
-                    return launch_conv_kf(q, bn_k, cpg, epi, CHk, xk, s);
+                    return launch_conv_kf(q, bn_k, cpg, epi, CHk, xk, kmode, s);
                 }
-                return launch_conv_kf(*kp, bn_k, cpg, epi, CHk, xk, s);
+                return launch_conv_kf(*kp, bn_k, cpg, epi, CHk, xk, kmode, s);
             };
             return CDC_OK;
         }

@@ -109,6 +109,12 @@ CONV_CASES = [
     ("kf_units_gt_ctas", 40, 16, 512, [64], 64, 3, 0, 0),
     ("kf_c128_n128_two_tiles", 1, 96, 384, [128], 128, 3, 0, 0),
     ("kf_dual_64+64_long", 2, 130, 256, [64, 64], 64, 3, 0, 0),
+    # nearest-x2 + conv3x3 through the kh-fused kernel (four parity 2x2 convs, scattered store)
+    ("kf_up2_c128_n64", 1, 40, 128, [128], 64, 3, 2, 0),
+    ("kf_up2_c192_n128_ragged", 2, 21, 192, [192], 128, 3, 2, 0),
+    ("kf_up2_c256_n192", 1, 16, 96, [256], 192, 3, 2, 0),
+    ("kf_up2_c256_n256_w48", 1, 10, 48, [256], 256, 3, 2, 0),
+    ("kf_up2_one_row", 1, 1, 128, [128], 64, 3, 2, 0),
 ]
 
 

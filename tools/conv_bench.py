@@ -17,7 +17,7 @@ def bench(H, W, cin, cout, ks, mode, fbn, stats=1, cin2=0, B=1):
     OH, OW = (H // 2, W // 2) if mode == 1 else ((2 * H, 2 * W) if mode == 2 else (H, W))
     out = torch.empty(B, OH, OW, (cout + 63) // 64 * 64, device="cuda", dtype=dt)
     st = torch.zeros(B, 32, 2, device="cuda", dtype=torch.int64) if stats else None
-        print(f"H{H} W{W} cin{cin}+{cin2} cout{cout} k{ks} mode{mode} force_bn{fbn}: ", end="", flush=True)
+    print(f"H{H} W{W} cin{cin}+{cin2} cout{cout} k{ks} mode{mode} force_bn{fbn}: ", end="", flush=True)
     rc = L.cdc_test_conv(0, C.c_void_p(x.data_ptr()), cin, C.c_void_p(x2.data_ptr()) if cin2 else None, cin2, B, H, W,
                          C.c_void_p(w.data_ptr()), C.c_void_p(b.data_ptr()), cout, ks, mode, fbn, None,
                          C.c_void_p(out.data_ptr()), C.c_void_p(st.data_ptr()) if stats else None, None)
