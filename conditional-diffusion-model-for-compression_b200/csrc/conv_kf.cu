@@ -12,8 +12,8 @@
 //   A operand : ring of input-row chunks in shared memory (TMA box {64 ch, 130 px, 1, 1}, zero fill = conv
 //               padding); every (row, 64-channel chunk) is loaded once, consumed by its own 12 MMAs and released
 //   B operand : the N tile's whole [kw][chunk][kh reversed][BN][64] weight block, resident in shared memory
-//   D         : ring of 8 accumulators (BN TMEM columns each); output row j of the running row counter g
-//               lives in slot (g + j) & 7, so the window {r-1, r, r+1} is contiguous except when it wraps
+//   D         : ring of 512 / BN (at most 16) accumulators (BN TMEM columns each); output row j of the running row counter g
+//               lives in slot (g + j) % ring, so the window {r-1, r, r+1} is contiguous except when it wraps
 //               (then the MMA is split in two)
 //   first use : every MMA accumulates; the epilogue re-zeroes an accumulator (tcgen05.st) right after draining it,
 //               so the issue stream has no special first K step
@@ -40,14 +40,17 @@ namespace cdc {
 
 constexpr int kKfRowBytes = 17 * 1024;  // 130 pixels x 128 B = 16640, padded to a 1024 B multiple
 constexpr int kKfRowTx = 130 * 128;
-constexpr int kKfAcc = 8;               // accumulator ring
+constexpr int kKfAccMax = 16;           // accumulator-ring barriers (the ring holds min(16, 512 / BN) output rows)
 constexpr int kKfAux = 1024 + 2 * 8 * 16 * 2 * 4;  // barriers + TMEM holder + bias, stats scratch
 
 template <int BN, int CPG, int EPI, int CH, bool STAGE, bool XK16, int MODE>
 __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __grid_constant__ KfParams p) {
     constexpr int WB = BN * 128;  // one (tap, chunk) weight block
     constexpr uint32_t WB16 = WB >> 4;
-    constexpr int TMEM_COLS = kKfAcc * BN <= 128 ? 128 : kKfAcc * BN <= 256 ? 256 : 512;  // power of two
+    // accumulator ring: as many output rows as TMEM holds (a window that wraps costs split MMAs: the longer the ring,
+    // the rarer) -- 8 rows of 64 columns, 10 of 48, 16 of 32 or 16
+    constexpr uint32_t NACC = 512 / BN < kKfAccMax ? 512 / BN : kKfAccMax;
+    constexpr int TMEM_COLS = NACC * BN <= 128 ? 128 : NACC * BN <= 256 ? 256 : 512;  // power of two
     constexpr int STAGE_BYTES = STAGE ? 2 * 128 * BN * 2 : 0;
     static_assert(!STAGE || BN == 64, "staged TMA store is built for 128-byte output rows");
     // MODE 0: 3x3 conv.  MODE 1: nearest-x2 upsample + 3x3 conv as four 2x2 convs on the low-resolution input, one
@@ -66,10 +69,10 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
     const uint32_t stage = wbase + NKH * NKW * CH * WB;
     const uint32_t aux = stage + STAGE_BYTES;
     uint8_t* aux_gen = gen + (aux - base);
-    // barriers: row_full[4] row_empty[4] tfull[8] tempty[8] wres
-    const uint32_t bar_rfull = aux, bar_rempty = aux + 32, bar_tfull = aux + 64, bar_tempty = aux + 128, bar_wres = aux + 192;
-    volatile uint32_t* tmem_holder = reinterpret_cast<volatile uint32_t*>(aux_gen + 200);
-    float* bias_s = reinterpret_cast<float*>(aux_gen + 256);
+    // barriers: row_full[4] row_empty[4] tfull[16] tempty[16] wres
+    const uint32_t bar_rfull = aux, bar_rempty = aux + 32, bar_tfull = aux + 64, bar_tempty = aux + 192, bar_wres = aux + 320;
+    volatile uint32_t* tmem_holder = reinterpret_cast<volatile uint32_t*>(aux_gen + 328);
+    float* bias_s = reinterpret_cast<float*>(aux_gen + 512);
     float* red_s = reinterpret_cast<float*>(aux_gen + 1024);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
             mbar_init(bar_rfull + 8 * s, 1);
             mbar_init(bar_rempty + 8 * s, 1);
         }
-        for (int s = 0; s < kKfAcc; ++s) {
+        for (int s = 0; s < static_cast<int>(NACC); ++s) {
             mbar_init(bar_tfull + 8 * s, 1);
             mbar_init(bar_tempty + 8 * s, EPI == EPI_DDIM ? 128 : kEpiThreads);
         }
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
                 for (int i = 0; i < L + 2; ++i) {
                     if (i < L) {  // input row i opens the accumulator of output row i: drained and re-zeroed?
                         const uint32_t gi = g + i;
-                        mbar_wait(bar_tempty + 8 * (gi & 7), (gi >> 3) & 1);
+                        mbar_wait(bar_tempty + 8 * (gi % NACC), (gi / NACC) & 1);
                     }
 #pragma unroll
                     for (int ch = 0; ch < CH; ++ch) {  // one ring slot per (row, 64-channel chunk)
@@ -188,7 +191,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
             const uint64_t desc_hi = make_sw128_desc(0) & 0xFFFFFFFF00000000ull;
             const uint32_t wlo = wbase >> 4;
             uint32_t rslot = 0, rpar = 0;
-            uint32_t g = 0;  // running output-row counter: row j of the current strip uses accumulator (g + j) & 7
+            uint32_t g = 0;  // running output-row counter: row j of the current strip uses accumulator (g + j) % NACC
             if (kdbg) p.dbg[502] = clock64();
             mbar_wait(bar_wres, 0);
             if (kdbg) p.dbg[503] = clock64();
@@ -206,9 +209,9 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
                     const uint32_t cnt = jhi >= jlo ? static_cast<uint32_t>(jhi - jlo + 1) : 0u;  // 0: nothing to issue (UP2 edge rows)
                     const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && u == cta && i < 40 && lane == 0;
                     if (dbg) p.dbg[i * 4 + 0] = clock64();
-                    const uint32_t slo = (g + jlo) & 7;
+                    const uint32_t slo = (g + jlo) % NACC;
                     const uint32_t khp = static_cast<uint32_t>((NKH - 1) - (jtop - jlo));  // reversed kh of the first window slot
-                    const uint32_t nA = cnt < 8 - slo ? cnt : 8 - slo, nB = cnt - nA;
+                    const uint32_t nA = cnt < NACC - slo ? cnt : NACC - slo, nB = cnt - nA;
                     const uint32_t dA = tmem_base + slo * BN, dB = tmem_base;
                     const uint32_t bA = khp * WB16, bB = (khp + nA) * WB16;
                     const uint32_t iA = idesc0 + nA * NB, iB = idesc0 + nB * NB;
@@ -238,19 +241,21 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
                                 }
                             }
                         };
+                        // probe the next chunk's barrier now, use the answer after the first half of the MMAs
+                        const uint32_t nslot = rslot + 1 == static_cast<uint32_t>(NS) ? 0u : rslot + 1;
+                        const bool more = ch + 1 < CH || i + 1 < L + 2;  // (a new row's first chunk also certifies its accumulator)
+                        const uint32_t npar = nslot == 0 ? rpar ^ 1 : rpar;
+                        const uint32_t ready = more ? mbar_test_wait(bar_rfull + 8 * nslot, npar) : 1u;
                         if (cnt != 0 && elect_one_sync()) steps(std::integral_constant<int, 0>{}, std::integral_constant<int, TH>{});
                         __syncwarp();
                         if (dbg && ch == 0) p.dbg[i * 4 + 1] = clock64();
-                        const uint32_t nslot = rslot + 1 == static_cast<uint32_t>(NS) ? 0u : rslot + 1;
-                        if (ch + 1 < CH || i + 1 < L + 2) {  // next chunk (a new row's first chunk also certifies its accumulator)
-                            mbar_wait(bar_rfull + 8 * nslot, nslot == 0 ? rpar ^ 1 : rpar);
-                            tc_fence_after();
-                        }
+                        if (!ready) mbar_wait(bar_rfull + 8 * nslot, npar);
+                        if (more) tc_fence_after();
                         if (dbg && ch == 0) p.dbg[i * 4 + 2] = clock64();
                         if (elect_one_sync()) {
                             if (cnt != 0) steps(std::integral_constant<int, TH>{}, std::integral_constant<int, T>{});
                             umma_commit(bar_rempty + 8 * rslot);  // chunk consumed
-                            if (ch == CH - 1 && i >= 2) umma_commit(bar_tfull + 8 * ((g + i - 2) & 7));  // output row i-2 complete
+                            if (ch == CH - 1 && i >= 2) umma_commit(bar_tfull + 8 * ((g + i - 2) % NACC));  // output row i-2 complete
                         }
                         __syncwarp();
                         rslot = nslot;
@@ -274,7 +279,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
             const float b0 = bias_s[0], b1 = bias_s[1], b2 = bias_s[2];
             const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
             if (half == 0) {
-                for (int s_ = 0; s_ < kKfAcc; ++s_) {  // arm every accumulator: zero, then the first "drained" arrive
+                for (int s_ = 0; s_ < static_cast<int>(NACC); ++s_) {  // arm every accumulator: zero, then the first "drained" arrive
                     tmem_zero<16>(tq + s_ * BN);
                     tmem_st_wait();
                     tc_fence_before();
@@ -287,14 +292,14 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
                 const int gx = seg * 128 + row;
                 const bool valid = gx < p.W;
                 for (int j = half; j < L; j += 2) {
-                    const uint32_t gj = g + j, slot = gj & 7;
+                    const uint32_t gj = g + j, slot = gj % NACC;
                     const size_t pix = (static_cast<size_t>(b) * p.H + (h0 + j)) * p.W + gx;
                     float xt[3] = {0.f, 0.f, 0.f};
                     if (valid) {
 #pragma unroll
                         for (int c = 0; c < 3; ++c) xt[c] = p.x[pix * 3 + c];
                     }
-                    mbar_wait(bar_tfull + 8 * slot, (gj >> 3) & 1);
+                    mbar_wait(bar_tfull + 8 * slot, (gj / NACC) & 1);
                     tc_fence_after();
                     uint32_t v[16];
                     tmem_ld16(tq + slot * BN, v);
@@ -330,7 +335,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
 #pragma unroll
             for (int c = 0; c < HC; ++c) bias_r[c] = bias_s[half * HC + c];
             const bool store_leader = warp == 4 && lane == 0;
-            for (int s_ = 0; s_ < kKfAcc; ++s_) {  // arm every accumulator: zero, then the first "drained" arrive
+            for (int s_ = 0; s_ < static_cast<int>(NACC); ++s_) {  // arm every accumulator: zero, then the first "drained" arrive
                 tmem_zero<HC>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + s_ * BN + half * HC);
                 tmem_st_wait();
                 tc_fence_before();
@@ -346,10 +351,10 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
 #pragma unroll
                 for (int i = 0; i < GH; ++i) gs[i] = gq[i] = 0.0f;
                 for (int j = 0; j < L; ++j, ++tile_ctr) {
-                    const uint32_t gj = g + j, slot = gj & 7;
+                    const uint32_t gj = g + j, slot = gj % NACC;
                     long long* edbg = (p.dbg != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0 && u == cta && j < 30) ? p.dbg + 256 + j * 8 : nullptr;
                     if (edbg) edbg[0] = clock64();
-                    mbar_wait(bar_tfull + 8 * slot, (gj >> 3) & 1);
+                    mbar_wait(bar_tfull + 8 * slot, (gj / NACC) & 1);
                     tc_fence_after();
                     if (edbg) edbg[1] = clock64();
                     if (p.dbg != nullptr && p.dbg[511] == 1) {  // tools only: MMA phase without epilogue work

@@ -50,6 +50,19 @@ __device__ __forceinline__ bool mbar_try_wait_suspend(uint32_t bar, uint32_t par
         : "memory");
     return ok != 0;
 }
+// Non-blocking probe.  Issued EARLY and consumed late, its ~140-cycle latency overlaps whatever is issued in between
+// (the kf conv issuer puts half a chunk's MMAs there).
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
 // Bounded wait: a protocol bug must trap (sticky launch failure), never hang the GPU box.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
