@@ -43,14 +43,18 @@ constexpr int kKfRowTx = 130 * 128;
 constexpr int kKfAccMax = 16;           // accumulator-ring barriers (the ring holds min(16, 512 / BN) output rows)
 constexpr int kKfAux = 1024 + 2 * 8 * 16 * 2 * 4;  // barriers + TMEM holder + bias, stats scratch
 
-template <int BN, int CPG, int EPI, int CH, bool STAGE, bool XK16, int MODE>
+template <int BN, int CPG, int EPI, int CH, bool STAGE, bool XK16, int MODE, bool RES1>
 __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __grid_constant__ KfParams p) {
     constexpr int WB = BN * 128;  // one (tap, chunk) weight block
     constexpr uint32_t WB16 = WB >> 4;
     // accumulator ring: as many output rows as TMEM holds (a window that wraps costs split MMAs: the longer the ring,
     // the rarer) -- 8 rows of 64 columns, 10 of 48, 16 of 32 or 16
-    constexpr uint32_t NACC = 512 / BN < kKfAccMax ? 512 / BN : kKfAccMax;
-    constexpr int TMEM_COLS = NACC * BN <= 128 ? 128 : NACC * BN <= 256 ? 256 : 512;  // power of two
+    // RES1: the ResBlock's 1x1 residual conv of the same input rides along -- centre-tap MMAs into a second, short
+    // ring of accumulators (its output row is complete one input row earlier than the 3x3's)
+    constexpr uint32_t NRES = RES1 ? (BN == 64 ? 2 : 8) : 0;
+    constexpr uint32_t NACC = RES1 ? (BN == 64 ? 6 : 8) : (512 / BN < kKfAccMax ? 512 / BN : kKfAccMax);
+    constexpr int TMEM_COLS = (NACC + NRES) * BN <= 128 ? 128 : (NACC + NRES) * BN <= 256 ? 256 : 512;  // power of two
+    static_assert(!RES1 || (MODE == 0 && !STAGE && EPI != EPI_DDIM && (BN == 64 || BN == 32)), "fused residual conv: 3x3 stats/store convs");
     constexpr int STAGE_BYTES = STAGE ? 2 * 128 * BN * 2 : 0;
     static_assert(!STAGE || BN == 64, "staged TMA store is built for 128-byte output rows");
     // MODE 0: 3x3 conv.  MODE 1: nearest-x2 upsample + 3x3 conv as four 2x2 convs on the low-resolution input, one
@@ -66,13 +70,15 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
     const int NS = p.NS;
     const uint32_t ring = base;
     const uint32_t wbase = ring + NS * kKfRowBytes;
-    const uint32_t stage = wbase + NKH * NKW * CH * WB;
+    const uint32_t wres1 = wbase + NKH * NKW * CH * WB;  // fused 1x1 weights [chunk][BN][64]
+    const uint32_t stage = wres1 + (RES1 ? CH * WB : 0);
     const uint32_t aux = stage + STAGE_BYTES;
     uint8_t* aux_gen = gen + (aux - base);
-    // barriers: row_full[4] row_empty[4] tfull[16] tempty[16] wres
+    // barriers: row_full[4] row_empty[4] tfull[16] tempty[16] wres xfull[8] xempty[8] (x = fused residual conv)
     const uint32_t bar_rfull = aux, bar_rempty = aux + 32, bar_tfull = aux + 64, bar_tempty = aux + 192, bar_wres = aux + 320;
-    volatile uint32_t* tmem_holder = reinterpret_cast<volatile uint32_t*>(aux_gen + 328);
-    float* bias_s = reinterpret_cast<float*>(aux_gen + 512);
+    const uint32_t bar_xfull = aux + 328, bar_xempty = aux + 392;
+    volatile uint32_t* tmem_holder = reinterpret_cast<volatile uint32_t*>(aux_gen + 456);
+    float* bias_s = reinterpret_cast<float*>(aux_gen + 512);  // [BN] conv bias, then [BN] residual-conv bias
     float* red_s = reinterpret_cast<float*>(aux_gen + 1024);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -103,13 +109,20 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
             mbar_init(bar_tempty + 8 * s, EPI == EPI_DDIM ? 128 : kEpiThreads);
         }
         mbar_init(bar_wres, 1);
+        for (int s = 0; s < static_cast<int>(NRES); ++s) {
+            mbar_init(bar_xfull + 8 * s, 1);
+            mbar_init(bar_xempty + 8 * s, kEpiThreads);
+        }
         fence_mbar_init();
     }
     if (warp == 2) {  // (warp-collective)
         tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_holder)), TMEM_COLS);
         tmem_relinquish();
     }
-    for (int i = threadIdx.x; i < BN; i += 128 + kEpiThreads) bias_s[i] = p.bias[cot * BN + i];
+    for (int i = threadIdx.x; i < BN; i += 128 + kEpiThreads) {
+        bias_s[i] = p.bias[cot * BN + i];
+        if (RES1) bias_s[BN + i] = p.res_bias[cot * BN + i];
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -119,7 +132,9 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
     if (warp == 3 && lane == 0) {
         // Weights are constants: their load need not wait for the preceding kernel (PDL).
         // smem block order [kw][chunk][2 - kh]: the kh taps of one (kw, chunk) form one contiguous B operand.
-        mbar_expect_tx(bar_wres, NKH * NKW * CH * WB);
+        mbar_expect_tx(bar_wres, (NKH * NKW + (RES1 ? 1 : 0)) * CH * WB);
+        if constexpr (RES1)
+            for (int ch = 0; ch < CH; ++ch) tma_load_2d(wres1 + ch * WB, &p.rmap, bar_wres, ch * 64, cot * BN);
         if constexpr (MODE == 0) {
             for (int kh = 0; kh < 3; ++kh)
                 for (int kw = 0; kw < 3; ++kw)
@@ -159,6 +174,10 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
                     if (i < L) {  // input row i opens the accumulator of output row i: drained and re-zeroed?
                         const uint32_t gi = g + i;
                         mbar_wait(bar_tempty + 8 * (gi % NACC), (gi / NACC) & 1);
+                    }
+                    if (RES1 && i >= 1 && i <= L) {  // input row i is the centre row of output row i-1 of the fused 1x1 conv
+                        const uint32_t gr = g + i - 1;
+                        mbar_wait(bar_xempty + 8 * (gr % NRES), (gr / NRES) & 1);
                     }
 #pragma unroll
                     for (int ch = 0; ch < CH; ++ch) {  // one ring slot per (row, 64-channel chunk)
@@ -254,6 +273,14 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
                         if (dbg && ch == 0) p.dbg[i * 4 + 2] = clock64();
                         if (elect_one_sync()) {
                             if (cnt != 0) steps(std::integral_constant<int, TH>{}, std::integral_constant<int, T>{});
+                            if (RES1 && i >= 1 && i <= L) {  // fused 1x1 residual conv: centre tap, its own accumulator ring
+                                const uint32_t gr = g + i - 1;
+                                const uint32_t dR = tmem_base + (NACC + gr % NRES) * BN;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    umma_f16_ss(dR, desc_hi | (alo_base + 8 + 2 * k), desc_hi | ((wres1 >> 4) + ch * WB16 + 2 * k), idesc0 + NB, 1u);
+                                if (ch == CH - 1) umma_commit(bar_xfull + 8 * (gr % NRES));
+                            }
                             umma_commit(bar_rempty + 8 * rslot);  // chunk consumed
                             if (ch == CH - 1 && i >= 2) umma_commit(bar_tfull + 8 * ((g + i - 2) % NACC));  // output row i-2 complete
                         }
@@ -335,11 +362,16 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
 #pragma unroll
             for (int c = 0; c < HC; ++c) bias_r[c] = bias_s[half * HC + c];
             const bool store_leader = warp == 4 && lane == 0;
-            for (int s_ = 0; s_ < static_cast<int>(NACC); ++s_) {  // arm every accumulator: zero, then the first "drained" arrive
+            for (int s_ = 0; s_ < static_cast<int>(NACC + NRES); ++s_) {  // arm every accumulator: zero, then the first "drained" arrive
                 tmem_zero<HC>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + s_ * BN + half * HC);
                 tmem_st_wait();
                 tc_fence_before();
-                mbar_arrive(bar_tempty + 8 * s_);
+                mbar_arrive(s_ < static_cast<int>(NACC) ? bar_tempty + 8 * s_ : bar_xempty + 8 * (s_ - NACC));
+            }
+            float rbias_r[RES1 ? HC : 1];
+            if constexpr (RES1) {
+#pragma unroll
+                for (int c = 0; c < HC; ++c) rbias_r[c] = bias_s[BN + half * HC + c];
             }
             for (int u = cta; u < units; u += p.G1, ++unit_ctr) {
                 int b, seg, si, h0, L;
@@ -352,6 +384,33 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
                 for (int i = 0; i < GH; ++i) gs[i] = gq[i] = 0.0f;
                 for (int j = 0; j < L; ++j, ++tile_ctr) {
                     const uint32_t gj = g + j, slot = gj % NACC;
+                    if constexpr (RES1) {  // the fused 1x1 conv's row j (complete one input row before the 3x3's)
+                        const uint32_t xs = gj % NRES;
+                        mbar_wait(bar_xfull + 8 * xs, (gj / NRES) & 1);
+                        tc_fence_after();
+                        const uint32_t xaddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (NACC + xs) * BN + half * HC;
+                        uint32_t xv[HC];
+                        tmem_ld_cols<HC>(xaddr, xv);
+                        tmem_ld_wait();
+                        tmem_zero<HC>(xaddr);
+                        tmem_st_wait();
+                        tc_fence_before();
+                        mbar_arrive(bar_xempty + 8 * xs);
+                        if (valid) {
+                            uint4 xo[HC / 8];
+#pragma unroll
+                            for (int s4 = 0; s4 < HC / 8; ++s4) {
+                                xo[s4].x = pack_act2(__uint_as_float(xv[s4 * 8 + 0]) + rbias_r[s4 * 8 + 0], __uint_as_float(xv[s4 * 8 + 1]) + rbias_r[s4 * 8 + 1]);
+                                xo[s4].y = pack_act2(__uint_as_float(xv[s4 * 8 + 2]) + rbias_r[s4 * 8 + 2], __uint_as_float(xv[s4 * 8 + 3]) + rbias_r[s4 * 8 + 3]);
+                                xo[s4].z = pack_act2(__uint_as_float(xv[s4 * 8 + 4]) + rbias_r[s4 * 8 + 4], __uint_as_float(xv[s4 * 8 + 5]) + rbias_r[s4 * 8 + 5]);
+                                xo[s4].w = pack_act2(__uint_as_float(xv[s4 * 8 + 6]) + rbias_r[s4 * 8 + 6], __uint_as_float(xv[s4 * 8 + 7]) + rbias_r[s4 * 8 + 7]);
+                            }
+                            const size_t rpix = (static_cast<size_t>(b) * p.H + (h0 + j)) * p.W + gx;
+                            uint4* rdst = reinterpret_cast<uint4*>(p.res_out + rpix * p.res_ldc + cot * BN + half * HC);
+#pragma unroll
+                            for (int s8 = 0; s8 < HC / 16; ++s8) st_global_v8(rdst + 2 * s8, xo[2 * s8], xo[2 * s8 + 1]);
+                        }
+                    }
                     long long* edbg = (p.dbg != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0 && u == cta && j < 30) ? p.dbg + 256 + j * 8 : nullptr;
                     if (edbg) edbg[0] = clock64();
                     mbar_wait(bar_tfull + 8 * slot, (gj / NACC) & 1);
@@ -468,34 +527,37 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
 }
 
 // ------------------------------------------------------------------------------------------------ host
-// (BN, CPG, EPI, CH, STAGED, XK16, MODE) instantiations: the layer shapes of the UNet / context net this variant serves.
-#define KF_ALL_CASES()                              \
-    KF_CASE(64, 2, EPI_STATS, 1, true, false, 0)    \
-    KF_CASE(64, 2, EPI_STATS, 2, false, false, 0)   \
-    KF_CASE(64, 4, EPI_STATS, 1, true, false, 0)    \
-    KF_CASE(64, 4, EPI_STATS, 2, false, false, 0)   \
-    KF_CASE(64, 1, EPI_STORE, 1, true, false, 0)    \
-    KF_CASE(64, 1, EPI_STORE, 2, false, false, 0)   \
-    KF_CASE(64, 1, EPI_STORE, 2, false, true, 0)    \
-    KF_CASE(32, 4, EPI_STATS, 3, false, false, 0)   \
-    KF_CASE(32, 4, EPI_STATS, 4, false, false, 0)   \
-    KF_CASE(48, 6, EPI_STATS, 3, false, false, 0)   \
-    KF_CASE(32, 8, EPI_STATS, 4, false, false, 0)   \
-    KF_CASE(16, 1, EPI_DDIM, 1, false, false, 0)    \
-    KF_CASE(64, 1, EPI_STORE, 2, false, false, 1)   \
-    KF_CASE(64, 1, EPI_STORE, 3, false, false, 1)   \
-    KF_CASE(64, 1, EPI_STORE, 4, false, false, 1)
+// (BN, CPG, EPI, CH, STAGED, XK16, MODE, RES1) instantiations: the layer shapes of the UNet / context net this variant serves.
+#define KF_ALL_CASES()                                     \
+    KF_CASE(64, 2, EPI_STATS, 1, true, false, 0, false)    \
+    KF_CASE(64, 2, EPI_STATS, 2, false, false, 0, false)   \
+    KF_CASE(64, 4, EPI_STATS, 1, true, false, 0, false)    \
+    KF_CASE(64, 4, EPI_STATS, 2, false, false, 0, false)   \
+    KF_CASE(64, 1, EPI_STORE, 1, true, false, 0, false)    \
+    KF_CASE(64, 1, EPI_STORE, 2, false, false, 0, false)   \
+    KF_CASE(64, 1, EPI_STORE, 2, false, true, 0, false)    \
+    KF_CASE(32, 4, EPI_STATS, 3, false, false, 0, false)   \
+    KF_CASE(32, 4, EPI_STATS, 4, false, false, 0, false)   \
+    KF_CASE(48, 6, EPI_STATS, 3, false, false, 0, false)   \
+    KF_CASE(32, 8, EPI_STATS, 4, false, false, 0, false)   \
+    KF_CASE(16, 1, EPI_DDIM, 1, false, false, 0, false)    \
+    KF_CASE(64, 1, EPI_STORE, 2, false, false, 1, false)   \
+    KF_CASE(64, 1, EPI_STORE, 3, false, false, 1, false)   \
+    KF_CASE(64, 1, EPI_STORE, 4, false, false, 1, false)   \
+    KF_CASE(64, 2, EPI_STATS, 2, false, false, 0, true)    \
+    KF_CASE(32, 4, EPI_STATS, 3, false, false, 0, true)    \
+    KF_CASE(32, 4, EPI_STATS, 4, false, false, 0, true)
 
-int kf_smem_bytes(int bn, int CH, int NS, bool staged, int mode) {
-    return 1024 + NS * kKfRowBytes + (mode == 1 ? 4 : 9) * CH * bn * 128 + (staged ? 2 * 128 * bn * 2 : 0) + kKfAux;
+int kf_smem_bytes(int bn, int CH, int NS, bool staged, int mode, bool res) {
+    return 1024 + NS * kKfRowBytes + ((mode == 1 ? 4 : 9) + (res ? 1 : 0)) * CH * bn * 128 + (staged ? 2 * 128 * bn * 2 : 0) + kKfAux;
 }
 
-bool kf_plan(int bn, int CH, int mode, int* NS, bool* staged) {
+bool kf_plan(int bn, int CH, int mode, bool res, int* NS, bool* staged) {
     const int limit = 227 * 1024;
-    for (int st = mode == 1 ? 0 : 1; st >= 0; --st) {  // NS = ring slots of one (row, chunk) each
+    for (int st = (mode == 1 || res) ? 0 : 1; st >= 0; --st) {  // NS = ring slots of one (row, chunk) each
         if (st && bn != 64) continue;
         for (int ns = 4; ns >= 3; --ns)
-            if (kf_smem_bytes(bn, CH, ns, st != 0, mode) <= limit) {
+            if (kf_smem_bytes(bn, CH, ns, st != 0, mode, res) <= limit) {
                 *NS = ns;
                 *staged = st != 0;
                 return true;
@@ -504,12 +566,12 @@ bool kf_plan(int bn, int CH, int mode, int* NS, bool* staged) {
     return false;
 }
 
-bool kf_inst_ok(int bn, int cpg, int epi, int CH, int mode) {
+bool kf_inst_ok(int bn, int cpg, int epi, int CH, int mode, bool res) {
     int ns;
     bool st;
-    if (!kf_plan(bn, CH, mode, &ns, &st)) return false;
-#define KF_CASE(BN_, CPG_, EPI_, CH_, ST_, X_, M_) \
-    if (bn == BN_ && (EPI_ != EPI_STATS || cpg == CPG_) && epi == EPI_ && CH == CH_ && st == ST_ && mode == M_) return true;
+    if (!kf_plan(bn, CH, mode, res, &ns, &st)) return false;
+#define KF_CASE(BN_, CPG_, EPI_, CH_, ST_, X_, M_, R_) \
+    if (bn == BN_ && (EPI_ != EPI_STATS || cpg == CPG_) && epi == EPI_ && CH == CH_ && st == ST_ && mode == M_ && res == R_) return true;
     KF_ALL_CASES()
 #undef KF_CASE
     return false;
@@ -517,8 +579,8 @@ bool kf_inst_ok(int bn, int cpg, int epi, int CH, int mode) {
 
 cudaError_t configure_kf_kernels() {
     cudaError_t e;
-#define KF_CASE(BN_, CPG_, EPI_, CH_, ST_, X_, M_)                                                          \
-    if ((e = cudaFuncSetAttribute(conv_kf_kernel<BN_, CPG_, EPI_, CH_, ST_, X_, M_>,                          \
+#define KF_CASE(BN_, CPG_, EPI_, CH_, ST_, X_, M_, R_)                                                      \
+    if ((e = cudaFuncSetAttribute(conv_kf_kernel<BN_, CPG_, EPI_, CH_, ST_, X_, M_, R_>,                      \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) \
         return e;
     KF_ALL_CASES()
@@ -526,15 +588,15 @@ cudaError_t configure_kf_kernels() {
     return cudaSuccess;
 }
 
-cudaError_t launch_conv_kf(const KfParams& p, int bn, int cpg, int epi, int CH, bool xk16, int mode, cudaStream_t stream) {
+cudaError_t launch_conv_kf(const KfParams& p, int bn, int cpg, int epi, int CH, bool xk16, int mode, bool res, cudaStream_t stream) {
     int ns;
     bool st;
-    if (!kf_plan(bn, CH, mode, &ns, &st) || ns != p.NS) return cudaErrorInvalidValue;
+    if (!kf_plan(bn, CH, mode, res, &ns, &st) || ns != p.NS) return cudaErrorInvalidValue;
     const dim3 grid(p.n_tiles * p.G1), block(128 + kEpiThreads);
-    const size_t smem = kf_smem_bytes(bn, CH, ns, st, mode);
-#define KF_CASE(BN_, CPG_, EPI_, CH_, ST_, X_, M_)                                                                            \
-    if (bn == BN_ && (EPI_ != EPI_STATS || cpg == CPG_) && epi == EPI_ && CH == CH_ && st == ST_ && xk16 == X_ && mode == M_)   \
-        return launch_pdl(conv_kf_kernel<BN_, CPG_, EPI_, CH_, ST_, X_, M_>, grid, block, smem, stream, p);
+    const size_t smem = kf_smem_bytes(bn, CH, ns, st, mode, res);
+#define KF_CASE(BN_, CPG_, EPI_, CH_, ST_, X_, M_, R_)                                                                                     \
+    if (bn == BN_ && (EPI_ != EPI_STATS || cpg == CPG_) && epi == EPI_ && CH == CH_ && st == ST_ && xk16 == X_ && mode == M_ && res == R_)   \
+        return launch_pdl(conv_kf_kernel<BN_, CPG_, EPI_, CH_, ST_, X_, M_, R_>, grid, block, smem, stream, p);
     KF_ALL_CASES()
 #undef KF_CASE
     return cudaErrorInvalidValue;

@@ -8,6 +8,7 @@ struct alignas(64) KfParams {
     CUtensorMap amap[2];  // activation sources, box {64 ch, 130 px, 1 row, 1 image}
     CUtensorMap wmap;     // weights [n_pad][9 * CH * 64] K-major, box {64, BN}
     CUtensorMap omap;     // output, box {BN ch, 128 px, 1 row, 1 image} (staged TMA store only)
+    CUtensorMap rmap;     // fused 1x1 residual conv: its weights [n_pad][CH * 64] K-major, box {64, BN}
     int chunks0;          // 64-channel chunks that come from source 0 (the rest from source 1)
     int H, W, batch;      // INPUT grid (mode 1: the low-resolution tensor; the output is 2H x 2W)
     int nseg;             // ceil(W / 128) column segments
@@ -18,6 +19,9 @@ struct alignas(64) KfParams {
     int ldc;              // channels of the output tensor
     act_t* out;
     const float* bias;    // [n_tiles * BN]
+    act_t* res_out;       // fused 1x1 residual conv (same input, centre tap only): output tensor, channels, bias
+    int res_ldc;
+    const float* res_bias;
     gn_sum_t* gn_acc;     // EPI_STATS: [batch][32][2] fixed-point accumulators (gn_sums.cuh), zero on entry
     float* x;             // EPI_DDIM (see ConvParams)
     act_t* xpad;
@@ -27,11 +31,12 @@ struct alignas(64) KfParams {
 };
 
 // mode 0: 3x3 conv; mode 1: nearest-x2 upsample + 3x3 conv (four parity 2x2 convs on the low-resolution input)
-bool kf_inst_ok(int bn, int cpg, int epi, int CH, int mode);
-bool kf_plan(int bn, int CH, int mode, int* NS, bool* staged);  // shared-memory plan; false if the weights do not fit
-int kf_smem_bytes(int bn, int CH, int NS, bool staged, int mode);
+// res: the ResBlock's 1x1 residual conv rides along (its weights are resident too, its accumulators share TMEM)
+bool kf_inst_ok(int bn, int cpg, int epi, int CH, int mode, bool res);
+bool kf_plan(int bn, int CH, int mode, bool res, int* NS, bool* staged);  // shared-memory plan; false if the weights do not fit
+int kf_smem_bytes(int bn, int CH, int NS, bool staged, int mode, bool res);
 cudaError_t configure_kf_kernels();
-cudaError_t launch_conv_kf(const KfParams& p, int bn, int cpg, int epi, int CH, bool xk16, int mode,
+cudaError_t launch_conv_kf(const KfParams& p, int bn, int cpg, int epi, int CH, bool xk16, int mode, bool res,
                            cudaStream_t stream);  // xk16: chunk 0 has 16 real channels (stem)
 
 }  // namespace cdc

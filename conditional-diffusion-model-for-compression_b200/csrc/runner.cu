@@ -106,6 +106,9 @@ struct ConvBuild {
     const std::vector<float>* c0 = nullptr;  // per-step sampler coefficients (host)
     const std::vector<float>* c1 = nullptr;
     long long* dbg = nullptr;  // strip kernel issuer timeline (tools)
+    // fused 1x1 residual conv of the same input (kf path only; build_conv reports whether it was taken)
+    const ConvW* res_w = nullptr;
+    Act res_out;
     bool x16 = false;          // source 0 carries at most 16 non-zero channels (the stem's x_t copy)
 };
 
@@ -174,7 +177,7 @@ static void conv_geometry(const ConvBuild& cb, int& gw, int& gh, int& nphase, in
 // ---- kh-fused strip variant (conv_kf.cu): 3x3, stride 1, resident weights, N tiles of 64 (16 for the final conv) ----
 struct KfGeom {
     int bn, CH, n_tiles, nseg, S, G1, NS, mode;
-    bool staged;
+    bool staged, res;
 };
 static bool kf_disabled() {
     static int v = -1;
@@ -199,7 +202,12 @@ static bool conv_uses_kf(const ConvBuild& cb, int B, int num_sms, KfGeom* g) {
     for (int c : cands) {
         const int bn = cb.epi == EPI_DDIM ? 16 : c;
         if (cb.w->n_pad % bn || (cb.epi == EPI_STATS && bn % cb.cpg)) continue;
-        if (!kf_inst_ok(bn, cb.cpg, cb.epi, g->CH, g->mode) || !kf_plan(bn, g->CH, g->mode, &g->NS, &g->staged)) continue;
+        // with the ResBlock's 1x1 residual conv riding along when that fits, else without
+        g->res = cb.res_w != nullptr && g->mode == 0 && cb.res_w->n_pad == cb.w->n_pad && cb.res_w->taps == 1 &&
+                 cb.res_w->c_pad == ctot && kf_inst_ok(bn, cb.cpg, cb.epi, g->CH, g->mode, true) &&
+                 kf_plan(bn, g->CH, g->mode, true, &g->NS, &g->staged);
+        if (!g->res && (!kf_inst_ok(bn, cb.cpg, cb.epi, g->CH, g->mode, false) || !kf_plan(bn, g->CH, g->mode, false, &g->NS, &g->staged)))
+            continue;
         g->bn = bn;
         break;
     }
@@ -258,6 +266,13 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
                     return fail("cuTensorMapEncodeTiled (kf activation) failed");
             }
             if (encode_w_map(&kp->wmap, w.w, w.taps * w.c_pad, w.n_pad, kg.bn)) return fail("cuTensorMapEncodeTiled (weights) failed");
+            if (kg.res) {
+                if (encode_w_map(&kp->rmap, cb.res_w->w, cb.res_w->c_pad, cb.res_w->n_pad, kg.bn))
+                    return fail("cuTensorMapEncodeTiled (residual-conv weights) failed");
+                kp->res_out = cb.res_out.p;
+                kp->res_ldc = cb.res_out.C;
+                kp->res_bias = cb.res_w->bias;
+            }
             if (kg.staged &&
                 encode_act_map(&kp->omap, cb.out.p, cb.out.C, cb.out.W, cb.out.H, B, static_cast<size_t>(cb.out.C),
                                static_cast<size_t>(cb.out.W) * cb.out.C, static_cast<size_t>(cb.out.H) * cb.out.W * cb.out.C, 128, 1))
@@ -284,19 +299,25 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
             const double Mout = Ms * (kg.mode == 1 ? 4.0 : 1.0);  // algorithmic: the 3x3 conv on the upsampled grid
             op->flops = 2.0 * Mout * w.n_true * (9.0 * w.c_true);
             op->bytes = 2.0 * (Ms * w.c_true + Mout * w.n_true + 9.0 * w.c_true * w.n_true);
+            if (kg.res) {  // the 1x1 residual conv's algorithmic work moves into this launch
+                op->flops += 2.0 * Ms * cb.res_w->n_true * cb.res_w->c_true;
+                op->bytes += 2.0 * (Ms * cb.res_w->n_true + static_cast<double>(cb.res_w->c_true) * cb.res_w->n_true);
+                op->name += "+res";
+            }
             const int epi = cb.epi, cpg = cb.cpg, bn_k = kg.bn, CHk = kg.CH;
             const bool xk = cb.x16 && cb.epi == EPI_STORE && kg.bn == 64 && kg.CH == 2 && cb.srcs[0].C == 64 && kg.mode == 0;
             const int kmode = kg.mode;
+            const bool kres = kg.res;
             const std::vector<float>*c0 = cb.c0, *c1 = cb.c1;
-            op->run = [kp, bn_k, cpg, epi, CHk, xk, kmode, c0, c1](cudaStream_t s, int k) -> cudaError_t {
+            op->run = [kp, bn_k, cpg, epi, CHk, xk, kmode, kres, c0, c1](cudaStream_t s, int k) -> cudaError_t {
                 if (epi == EPI_DDIM) {
                     if (!c0 || k < 0 || k >= static_cast<int>(c0->size())) return cudaErrorInvalidValue;
                     KfParams q = *kp;
                     q.c0 = (*c0)[k];
                     q.c1 = (*c1)[k];
-                    return launch_conv_kf(q, bn_k, cpg, epi, CHk, xk, kmode, s);
+                    return launch_conv_kf(q, bn_k, cpg, epi, CHk, xk, kmode, kres, s);
                 }
-                return launch_conv_kf(*kp, bn_k, cpg, epi, CHk, xk, kmode, s);
+                return launch_conv_kf(*kp, bn_k, cpg, epi, CHk, xk, kmode, kres, s);
             };
             return CDC_OK;
         }
@@ -696,6 +717,16 @@ struct PlanB {
         c1.epi = EPI_STATS;
         c1.cpg = cpg;
         c1.gn_acc = new_gn_slot();
+        bool res_fused = false;
+        Act rbuf;
+        if (cin != cout) {  // the 1x1 residual conv reads the same input: let it ride along in the kh-fused kernel if it fits
+            rbuf = shared("res", cout, H, W);
+            c1.res_w = &ctx->convs[wp + ".res"];
+            c1.res_out = rbuf;
+            KfGeom kg;
+            res_fused = conv_uses_kf(c1, ctx->B, ctx->num_sms, &kg) && kg.res;
+            if (!res_fused) c1.res_w = nullptr;
+        }
         conv(c1);
         gn(name + ".gn1", wp + ".gn1", film_idx, c1.gn_acc, t1, nullptr, t1, true);
         ConvBuild c2;
@@ -709,15 +740,16 @@ struct PlanB {
         conv(c2);
         const act_t* resp = in[0].p;
         if (cin != cout) {
-            Act r = shared("res", cout, H, W);
-            ConvBuild cr;
-            cr.name = name + ".res";
-            cr.srcs = in;
-            cr.w = &ctx->convs[wp + ".res"];
-            cr.ksize = 1;
-            cr.out = r;
-            conv(cr);
-            resp = r.p;
+            if (!res_fused) {
+                ConvBuild cr;
+                cr.name = name + ".res";
+                cr.srcs = in;
+                cr.w = &ctx->convs[wp + ".res"];
+                cr.ksize = 1;
+                cr.out = rbuf;
+                conv(cr);
+            }
+            resp = rbuf.p;
         }
         gn(name + ".gn2", wp + ".gn2", -1, c2.gn_acc, t2, resp, out, true);
     }
