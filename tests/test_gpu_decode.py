@@ -34,7 +34,7 @@ def _setup(with_context=False):
     return _cache[key]
 
 
-@pytest.mark.parametrize("shape", [(1, 256, 256), (2, 128, 192)])
+@pytest.mark.parametrize("shape", [(1, 256, 256), (2, 128, 192), (1, 64, 64), (1, 128, 384), (3, 64, 128)])
 def test_teacher_forced_step_parity(shape):
     from oracle.weights import synthetic_cond, synthetic_init
     dec, orc, ocfg = _setup()
