@@ -1,5 +1,5 @@
 // Shared epilogue of the tcgen05 conv kernels: one 128-pixel x BN accumulator tile
-// TMEM -> registers -> (+bias, GroupNorm partials, residual, DDIM update) -> global.
+// TMEM -> registers -> (+bias, GroupNorm sums, residual, DDIM update) -> global.
 // Called by the 4 epilogue warps (128 threads); thread = TMEM lane = output pixel.
 #pragma once
 #include "conv_tc.cuh"
@@ -144,7 +144,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const EpiArgs& e, uint32_t ta
         }
         if (dbg) dbg[2] = clock64();
         if constexpr (EPI == EPI_STATS) {
-            // warp butterfly -> 8 warps through smem -> one fixed-order partial per (tile, group)
+            // warp butterfly -> 8 warps through smem -> one (sum, sum of squares) per (tile, group) -> integer atomics
             const float ws = warp_group_reduce<GH>(gs, lane);
             const float wq = warp_group_reduce<GH>(gq, lane);
             constexpr int REP = 32 / GH;

@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
                 }
                 g += L;
                 if constexpr (EPI == EPI_STATS) {
-                    // one fixed-order partial per (strip, group): warp butterfly -> 4 lane quarters through smem
+                    // one (sum, sum of squares) per (strip, group): warp butterfly -> 4 lane quarters through smem -> integer atomics
                     const float ws = warp_group_reduce<GH>(gs, lane);
                     const float wq = warp_group_reduce<GH>(gq, lane);
                     constexpr int REP = 32 / GH;

@@ -10,7 +10,7 @@
 //   warp 0 : TMA producer (one elected lane)        smem ring: full[] / empty[] mbarriers
 //   warp 1 : tcgen05.mma issuer (one elected lane)  TMEM ring: tfull[] / tempty[] (2 accumulators)
 //   warp 2 : TMEM allocator
-//   warps 4-11 : epilogue (tcgen05.ld -> +bias -> GroupNorm partials / residual / DDIM -> global)
+//   warps 4-11 : epilogue (tcgen05.ld -> +bias -> GroupNorm sums / residual / DDIM -> global)
 //
 // Oracle counterpart: oracle/unet.py `conv`, `Up`, `RB` (the reference ships no code).
 #include <stdio.h>
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
                 tc_fence_after();
                 const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
                 const uint32_t alo = (sa >> 4) & 0x3FFFu, blo = ((sa + Cfg::A_BYTES) >> 4) & 0x3FFFu;
-                if (leader) {  // elected-lane region, 32-bit descriptor math (see conv_strip.cu)
+                if (leader) {  // elected-lane region, 32-bit descriptor math (see conv_kf.cu)
                     umma_f16_ss(d_tmem, desc_hi | alo, desc_hi | blo, idesc, i != 0 ? 1u : 0u);
 #pragma unroll
                     for (int k = 1; k < 4; ++k)  // 4 x (K = 16): +32 B inside the 128 B swizzle row

@@ -1,4 +1,4 @@
-// HBM-/latency-bound kernels around K-conv: GroupNorm statistics / finalize / apply(+SiLU,+residual),
+// HBM-/latency-bound kernels around K-conv: GroupNorm statistics / apply(+SiLU,+residual),
 // time-embedding MLP + FiLM vectors, layout conversion at the API boundary, weight repack.
 // Oracle counterparts: oracle/unet.py RB, Attn.gn, TimeEmbed; SURVEY.md 2.2 C5, C6, C8.
 #include "gn_sums.cuh"
@@ -76,9 +76,6 @@ cudaError_t launch_gn_stats(const act_t* x, gn_sum_t* acc, int B, int HW, int C,
     return launch_pdl(gn_stats_kernel, dim3(PT, B), dim3(256), 0, s, x, acc, HW, C);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Finalize: one CTA per (group, image).  Thread t sums partials t, t+256, ... in order, then a fixed
-// shared-memory tree; double accumulation.  The CTA then writes (a, b) for its C/32 channels.
 // ------------------------------------------------------------------------------------------------
 // Apply: y = SiLU(a*x + b) (+ r), 8 channels (16 B) per thread, grid-stride.
 // x * sigmoid(x) = x * (0.5 + 0.5 * tanh(x / 2)): ONE MUFU op (tanh.approx.f32, max relative error 2^-11, below the

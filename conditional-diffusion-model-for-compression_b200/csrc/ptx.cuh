@@ -121,7 +121,7 @@ __device__ __forceinline__ void bulk_wait_group() {
 // Programmatic dependent launch: wait for the preceding kernel's memory to be visible / let the next
 // kernel's CTAs start their prologue.  Both are no-ops when the launch carries no PDL attribute.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-// Early trigger: only kernels whose dependents are small (GroupNorm finalize / apply, or a conv that cannot become
+// Early trigger: only kernels whose dependents are small (GroupNorm apply, or a conv that cannot become
 // resident before this one's CTAs exit anyway) call this.  gn_apply does NOT: its dependent is a conv whose CTAs would
 // claim most of the register file next to the still-running apply CTAs (measured: -1.7 % when every kernel triggered).
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

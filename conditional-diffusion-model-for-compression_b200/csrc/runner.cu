@@ -105,7 +105,7 @@ struct ConvBuild {
     float* x0_out = nullptr;
     const std::vector<float>* c0 = nullptr;  // per-step sampler coefficients (host)
     const std::vector<float>* c1 = nullptr;
-    long long* dbg = nullptr;  // strip kernel issuer timeline (tools)
+    long long* dbg = nullptr;  // kf kernel issuer / epilogue timeline (tools)
     // fused 1x1 residual conv of the same input (kf path only; build_conv reports whether it was taken)
     const ConvW* res_w = nullptr;
     Act res_out;
@@ -140,7 +140,7 @@ static int encode_w_map(CUtensorMap* m, const act_t* w, int K, int N, int BN) {
     return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
 }
 
-// Number of GroupNorm partial rows a stats-conv writes per image (must match conv_tc.cu).
+// Tile geometry of the general conv kernel (conv_tc.cu).
 static void conv_geometry(const ConvBuild& cb, int& gw, int& gh, int& nphase, int& os, int& bwl, int& tiles_w,
                           int& tiles_h) {
     const Act& a = cb.srcs[0];

@@ -33,7 +33,7 @@ def _nhwc_act(t):
 
 
 def _run_conv(srcs, w, b, ksize, mode, force_bn=0, residual=None, stats=False):
-    """srcs: list of NCHW fp32 cuda tensors (bf16-exact).  Returns (out NCHW fp32, partials or None)."""
+    """srcs: list of NCHW fp32 cuda tensors (bf16-exact).  Returns (out NCHW fp32, GroupNorm sums or None)."""
     L = _lib()
     B, _, H, W = srcs[0].shape
     cout = w.shape[0]
@@ -94,7 +94,7 @@ CONV_CASES = [
     ("ragged_s2_24x40", 1, 24, 40, [64], 128, 3, 1, 0),
     ("big_k4608_n256", 1, 16, 32, [256, 256], 256, 3, 0, 0),
     ("multi_tile_persistent", 4, 64, 128, [64], 64, 3, 0, 0),
-    # strip variant (conv_strip.cu): W a multiple of 128, one N tile; resident and streamed weights
+    # kh-fused strip variant (conv_kf.cu): W a multiple of 128; one or two N tiles, one to three input chunks
     ("strip_c64_n64_256x256", 1, 256, 256, [64], 64, 3, 0, 0),
     ("strip_rows_not_multiple_of_L", 3, 50, 256, [64], 64, 3, 0, 0),
     ("strip_dual_64+64_n64", 1, 64, 384, [64, 64], 64, 3, 0, 0),

@@ -33,7 +33,7 @@ def _nhwc_act(t):
 
 
 def _run_conv(srcs, w, b, ksize, mode, force_bn=0, residual=None, stats=False):
-    """srcs: list of NCHW fp32 cuda tensors (bf16-exact).  Returns (out NCHW fp32, partials or None)."""
+    """srcs: list of NCHW fp32 cuda tensors (bf16-exact).  Returns (out NCHW fp32, GroupNorm sums or None)."""
     L = _lib()
     B, _, H, W = srcs[0].shape
     cout = w.shape[0]

@@ -1,5 +1,5 @@
 // Micro-benchmark for the kh-fused strip conv: cycles per tcgen05.mma (M=128, K=16, fp16 SS) by N, issued as
-// straight-line code from an elected lane (the form conv_strip.cu uses), with an optional tcgen05.commit every
+// straight-line code from an elected lane (the form conv_kf.cu uses), with an optional tcgen05.commit every
 // CE MMAs.  Operands are resident in shared memory; A descriptors walk the (kw, k) offsets of a 3x3 strip row.
 // Answers: (1) does one N=192 MMA (three kh taps stacked along N) cost ~96 cycles, i.e. half of three N=64
 // MMAs; (2) what does a commit cost the issue stream.

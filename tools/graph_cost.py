@@ -21,7 +21,7 @@ for _ in range(8):
 ts.sort()
 print("GRAPH_MS", ts[len(ts)//2])
 ''' % ROOT
-variants = [("full", ""), ("no finalize", "finalize"), ("no apply", "apply"), ("no finalize+apply", "finalize,apply"),
+variants = [("full", ""), ("no apply", "apply"),
             ("no attention", "sdpa,attn.gn.stats"), ("no res 1x1", ".res"), ("no up convs", ".up"), ("no down convs", ".down"),
             ("no level-0 3x3", "stem,down.0.rb,up.0.rb1.conv,up.0.rb2.conv,final"), ("no level-1 3x3", "down.1.rb1.conv,down.1.rb2.conv,up.1.rb1.conv,up.1.rb2.conv"),
             ("no level-2 3x3", "down.2.rb1.conv,down.2.rb2.conv,up.2.rb1.conv,up.2.rb2.conv"),

@@ -1,4 +1,4 @@
-"""Print the strip kernels' issuer / epilogue timeline for one conv (CDC_STRIP_DEBUG=1) and time the launch with CUDA
+"""Print the kh-fused conv kernel's issuer / epilogue timeline for one conv (CDC_STRIP_DEBUG=1) and time the launch with CUDA
 events (second, warm call).  Usage: strip_timeline.py [cin] [cout] [H] [W] [mode]   (mode 2 = nearest-x2 input)"""
 import ctypes as C, os, sys
 os.environ.setdefault("CDC_STRIP_DEBUG", "1")
