@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
     // RES1: the ResBlock's 1x1 residual conv of the same input rides along -- centre-tap MMAs into a second, short
     // ring of accumulators (its output row is complete one input row earlier than the 3x3's)
     constexpr uint32_t NRES = RES1 ? (BN == 64 ? 2 : 8) : 0;
+    constexpr uint32_t NRESD = NRES ? NRES : 1;  // divisor (the fused-residual code is dead when NRES == 0)
     constexpr uint32_t NACC = RES1 ? (BN == 64 ? 6 : 8) : (512 / BN < kKfAccMax ? 512 / BN : kKfAccMax);
     constexpr int TMEM_COLS = (NACC + NRES) * BN <= 128 ? 128 : (NACC + NRES) * BN <= 256 ? 256 : 512;  // power of two
     static_assert(!RES1 || (MODE == 0 && !STAGE && EPI != EPI_DDIM && (BN == 64 || BN == 32)), "fused residual conv: 3x3 stats/store convs");
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
                     }
                     if (RES1 && i >= 1 && i <= L) {  // input row i is the centre row of output row i-1 of the fused 1x1 conv
                         const uint32_t gr = g + i - 1;
-                        mbar_wait(bar_xempty + 8 * (gr % NRES), (gr / NRES) & 1);
+                        mbar_wait(bar_xempty + 8 * (gr % NRESD), (gr / NRESD) & 1);
                     }
 #pragma unroll
                     for (int ch = 0; ch < CH; ++ch) {  // one ring slot per (row, 64-channel chunk)
@@ -275,11 +276,11 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
                             if (cnt != 0) steps(std::integral_constant<int, TH>{}, std::integral_constant<int, T>{});
                             if (RES1 && i >= 1 && i <= L) {  // fused 1x1 residual conv: centre tap, its own accumulator ring
                                 const uint32_t gr = g + i - 1;
-                                const uint32_t dR = tmem_base + (NACC + gr % NRES) * BN;
+                                const uint32_t dR = tmem_base + (NACC + gr % NRESD) * BN;
 #pragma unroll
                                 for (int k = 0; k < 4; ++k)
                                     umma_f16_ss(dR, desc_hi | (alo_base + 8 + 2 * k), desc_hi | ((wres1 >> 4) + ch * WB16 + 2 * k), idesc0 + NB, 1u);
-                                if (ch == CH - 1) umma_commit(bar_xfull + 8 * (gr % NRES));
+                                if (ch == CH - 1) umma_commit(bar_xfull + 8 * (gr % NRESD));
                             }
                             umma_commit(bar_rempty + 8 * rslot);  // chunk consumed
                             if (ch == CH - 1 && i >= 2) umma_commit(bar_tfull + 8 * ((g + i - 2) % NACC));  // output row i-2 complete
