@@ -51,6 +51,7 @@ cudaError_t launch_repack_weight_up2(const float* src, act_t* dst, int O, int I,
 // ---- attention (C7; oracle/unet.py Attn) --------------------------------------------------------
 // qkv [B*N][768] act_t (q | k | v, head h = channels 64h..64h+63) -> o [B*N][256] bf16
 cudaError_t launch_attention(const act_t* qkv, act_t* o, int B, int N, int heads, cudaStream_t s);
+cudaError_t configure_attention();  // dynamic shared-memory limit (call once, outside graph capture)
 
 // ---- integer path (C10; oracle/entropy.py) ------------------------------------------------------
 cudaError_t launch_quantize(const float* y, const float* mu, int32_t* q, float* yhat, int64_t n, int64_t mu_inner,

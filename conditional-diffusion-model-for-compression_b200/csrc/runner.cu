@@ -817,7 +817,6 @@ static int build_plans(cdc_ctx* ctx) {
         // attention: GN -> qkv 1x1 -> flash attention -> proj 1x1 + residual
         Act n = pb.act(Cm, Hm, Wm), qkv = pb.act(3 * Cm, Hm, Wm), o = pb.act(Cm, Hm, Wm);
         if (pb.rc) return pb.rc;
-        cdc_ctx* c = ctx;
         Op st;
         st.name = "mid.attn.gn.stats";
         st.bytes = static_cast<double>(B) * HW * Cm * 2;
@@ -1005,7 +1004,7 @@ int cdc_create(const cdc_config* cfg, int device, cdc_ctx** out) {
         g_create_err = "cuTensorMapEncodeTiled entry point not found";
         return CDC_ERR_CUDA;
     }
-    if ((e = configure_conv_kernels()) != cudaSuccess ||         (e = configure_kf_kernels()) != cudaSuccess) {
+    if ((e = configure_attention()) != cudaSuccess || (e = configure_conv_kernels()) != cudaSuccess ||         (e = configure_kf_kernels()) != cudaSuccess) {
         g_create_err = std::string("cudaFuncSetAttribute(conv kernels): ") + cudaGetErrorString(e);
         return CDC_ERR_CUDA;
     }
