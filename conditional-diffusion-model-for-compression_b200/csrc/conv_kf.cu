@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
                 for (int kw = 0; kw < 3; ++kw)
                     for (int ch = 0; ch < CH; ++ch)
                         tma_load_2d(wbase + ((kw * CH + ch) * 3 + (2 - kh)) * WB, &p.wmap, bar_wres,
-                                    ((kh * 3 + kw) * CH + ch) * 64, cot * BN);
+                                    ((p.tr ? kw * 3 + kh : kh * 3 + kw) * CH + ch) * 64, cot * BN);  // transposed walk: taps swap roles
         } else {  // pre-summed parity weights: K index ((parity * 4 + a * 2 + b) * CH + chunk) * 64
             for (int a2 = 0; a2 < 2; ++a2)
                 for (int b2 = 0; b2 < 2; ++b2)
@@ -406,7 +406,8 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
                                 xo[s4].z = pack_act2(__uint_as_float(xv[s4 * 8 + 4]) + rbias_r[s4 * 8 + 4], __uint_as_float(xv[s4 * 8 + 5]) + rbias_r[s4 * 8 + 5]);
                                 xo[s4].w = pack_act2(__uint_as_float(xv[s4 * 8 + 6]) + rbias_r[s4 * 8 + 6], __uint_as_float(xv[s4 * 8 + 7]) + rbias_r[s4 * 8 + 7]);
                             }
-                            const size_t rpix = (static_cast<size_t>(b) * p.H + (h0 + j)) * p.W + gx;
+                            const size_t rpix = p.tr ? (static_cast<size_t>(b) * p.W + gx) * p.H + (h0 + j)
+                                                     : (static_cast<size_t>(b) * p.H + (h0 + j)) * p.W + gx;
                             uint4* rdst = reinterpret_cast<uint4*>(p.res_out + rpix * p.res_ldc + cot * BN + half * HC);
 #pragma unroll
                             for (int s8 = 0; s8 < HC / 16; ++s8) st_global_v8(rdst + 2 * s8, xo[2 * s8], xo[2 * s8 + 1]);
@@ -474,7 +475,8 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
                         }
                     } else if (valid) {
                         const size_t pix = MODE == 1 ? (static_cast<size_t>(b) * 2 * p.H + 2 * (h0 + j) + py) * (2 * p.W) + 2 * gx + px
-                                                     : (static_cast<size_t>(b) * p.H + (h0 + j)) * p.W + gx;
+                                           : p.tr ? (static_cast<size_t>(b) * p.W + gx) * p.H + (h0 + j)
+                                                  : (static_cast<size_t>(b) * p.H + (h0 + j)) * p.W + gx;
                         uint4* dst = reinterpret_cast<uint4*>(p.out + pix * p.ldc + cot * BN + half * HC);
                         // thread = pixel: its channels are contiguous, lanes are a pixel pitch apart.  32-byte stores fill
                         // whole sectors and halve the store instructions (each costs ~1 cycle per distinct line)

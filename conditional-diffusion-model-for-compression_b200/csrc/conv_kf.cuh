@@ -10,6 +10,8 @@ struct alignas(64) KfParams {
     CUtensorMap omap;     // output, box {BN ch, 128 px, 1 row, 1 image} (staged TMA store only)
     CUtensorMap rmap;     // fused 1x1 residual conv: its weights [n_pad][CH * 64] K-major, box {64, BN}
     int chunks0;          // 64-channel chunks that come from source 0 (the rest from source 1)
+    int tr;               // 1: transposed walk -- kernel rows = image columns, kernel pixels = image rows (H, W below are
+                          // the kernel-space extents); tensor maps, weight taps and output addressing are swapped to match
     int H, W, batch;      // INPUT grid (mode 1: the low-resolution tensor; the output is 2H x 2W)
     int nseg;             // ceil(W / 128) column segments
     int S;                // strips per column (rows are spread evenly over them)

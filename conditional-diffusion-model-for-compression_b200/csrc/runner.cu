@@ -178,6 +178,7 @@ static void conv_geometry(const ConvBuild& cb, int& gw, int& gh, int& nphase, in
 struct KfGeom {
     int bn, CH, n_tiles, nseg, S, G1, NS, mode;
     bool staged, res;
+    bool tr;  // transposed walk: strips run along image columns (less padding / halo for e.g. a 128 x 192 level)
 };
 static bool kf_disabled() {
     static int v = -1;
@@ -188,11 +189,14 @@ static bool conv_uses_kf(const ConvBuild& cb, int B, int num_sms, KfGeom* g) {
     if (kf_disabled() || cb.mode == MODE_S2 || cb.ksize != 3 || cb.force_bn != 0 || cb.residual) return false;
     g->mode = cb.mode == MODE_UP2 ? 1 : 0;
     if (g->mode == 1 && (!cb.w->up2 || cb.epi != EPI_STORE)) return false;
-    const int gw = cb.srcs[0].W, gh = cb.srcs[0].H;
+    int gw = cb.srcs[0].W, gh = cb.srcs[0].H;
+    g->tr = false;
     g->nseg = (gw + 127) / 128;
     // segments are 128 pixels wide: too much of the tile would be padding (measured break-even against conv_tc.cu:
     // 3x3 convs down to 48 of 128 columns; the upsampling convs need 96)
-    if (gw * 100 < g->nseg * 128 * (cb.mode == MODE_UP2 ? 50 : 35)) return false;
+    const bool wide_ok = gw * 100 >= g->nseg * 128 * (cb.mode == MODE_UP2 ? 50 : 35);
+    const bool tall_ok = cb.mode == MODE_S1 && cb.epi != EPI_DDIM && gh * 100 >= ((gh + 127) / 128) * 128 * 35;
+    if (!wide_ok && !tall_ok) return false;
     int ctot = 0;
     for (const Act& a : cb.srcs) ctot += a.C;
     g->CH = ctot / 64;
@@ -214,15 +218,32 @@ static bool conv_uses_kf(const ConvBuild& cb, int B, int num_sms, KfGeom* g) {
     if (!g->bn) return false;
     g->n_tiles = cb.w->n_pad / g->bn * (g->mode == 1 ? 4 : 1);
     if (cb.epi == EPI_DDIM && g->n_tiles != 1) return false;
-    g->nseg = (gw + 127) / 128;
-    const int cols = B * g->nseg;  // independent strip columns per N tile
-    int G1 = num_sms / g->n_tiles;
-    if (G1 < 1) G1 = 1;
-    int S = G1 / cols;
-    if (S < 1) S = 1;
-    if (S > gh) S = gh;
-    g->S = S;
-    g->G1 = cols * S < G1 ? cols * S : G1;
+    // strip geometry for a walk along image rows (tr = 0) or image columns (tr = 1): relative cost = padding of the
+    // 128-pixel segments x halo rows per strip; the transposed walk is used for unstaged kernels when it is >10 % cheaper
+    auto plan = [&](int w_, int h_, int* nseg, int* S, int* G1) {
+        *nseg = (w_ + 127) / 128;
+        const int cols = B * *nseg;  // independent strip columns per N tile
+        int g1 = num_sms / g->n_tiles;
+        if (g1 < 1) g1 = 1;
+        int s_ = g1 / cols;
+        if (s_ < 1) s_ = 1;
+        if (s_ > h_) s_ = h_;
+        *S = s_;
+        *G1 = cols * s_ < g1 ? cols * s_ : g1;
+        const double L = static_cast<double>(h_) / s_;
+        return (*nseg * 128.0 / w_) * (L + 2.0) / L;
+    };
+    int nsegT, ST, G1T;
+    const double c0 = wide_ok ? plan(gw, gh, &g->nseg, &g->S, &g->G1) : 1e30;
+    const double c1 = (tall_ok && !g->staged && g->mode == 0) ? plan(gh, gw, &nsegT, &ST, &G1T) : 1e30;
+    if (c1 < 0.9 * c0) {
+        g->tr = true;
+        g->nseg = nsegT;
+        g->S = ST;
+        g->G1 = G1T;
+    } else if (!wide_ok) {
+        return false;
+    }
     return true;
 }
 
@@ -261,9 +282,11 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
             memset(kp.get(), 0, sizeof(KfParams));
             for (size_t s = 0; s < cb.srcs.size(); ++s) {
                 const Act& a = cb.srcs[s];
-                if (encode_act_map(&kp->amap[s], a.p, a.C, a.W, a.H, B, static_cast<size_t>(a.C),
-                                   static_cast<size_t>(a.W) * a.C, static_cast<size_t>(a.H) * a.W * a.C, 130, 1))
-                    return fail("cuTensorMapEncodeTiled (kf activation) failed");
+                const int rc_map = kg.tr ? encode_act_map(&kp->amap[s], a.p, a.C, a.H, a.W, B, static_cast<size_t>(a.W) * a.C,
+                                                          static_cast<size_t>(a.C), static_cast<size_t>(a.H) * a.W * a.C, 130, 1)
+                                         : encode_act_map(&kp->amap[s], a.p, a.C, a.W, a.H, B, static_cast<size_t>(a.C),
+                                                          static_cast<size_t>(a.W) * a.C, static_cast<size_t>(a.H) * a.W * a.C, 130, 1);
+                if (rc_map) return fail("cuTensorMapEncodeTiled (kf activation) failed");
             }
             if (encode_w_map(&kp->wmap, w.w, w.taps * w.c_pad, w.n_pad, kg.bn)) return fail("cuTensorMapEncodeTiled (weights) failed");
             if (kg.res) {
@@ -278,8 +301,9 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
                                static_cast<size_t>(cb.out.W) * cb.out.C, static_cast<size_t>(cb.out.H) * cb.out.W * cb.out.C, 128, 1))
                 return fail("cuTensorMapEncodeTiled (kf output) failed");
             kp->chunks0 = cb.srcs[0].C / 64;
-            kp->H = gh;
-            kp->W = gw;
+            kp->tr = kg.tr ? 1 : 0;
+            kp->H = kg.tr ? gw : gh;  // kernel-space rows / pixels per row
+            kp->W = kg.tr ? gh : gw;
             kp->batch = B;
             kp->nseg = kg.nseg;
             kp->S = kg.S;

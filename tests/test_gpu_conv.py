@@ -142,7 +142,9 @@ def test_conv_residual_epilogue():
                                  (64, 1, 50, 640, 0, 128),
                                  # kh-fused variant with N tiles of 32 / 48 channels (weights of wider layers stay resident)
                                  (128, 1, 64, 384, 0, 192), (128, 1, 40, 256, 0, 256), (192, 1, 64, 192, 0, 192),
-                                 (256, 1, 32, 96, 0, 256), (256, 2, 16, 48, 0, 256), (64, 1, 64, 128, -1), (64, 1, 64, 128, 0), (128, 2, 32, 64, 0), (128, 1, 16, 16, 64), (192, 1, 32, 32, 0),
+                                 (256, 1, 32, 96, 0, 256), (256, 2, 16, 48, 0, 256),
+                                 # transposed walk (strips along image columns): a 128 x 192 level, a tall narrow image
+                                 (192, 1, 128, 192, 0, 192), (128, 2, 256, 40, 0, 128), (64, 1, 64, 128, -1), (64, 1, 64, 128, 0), (128, 2, 32, 64, 0), (128, 1, 16, 16, 64), (192, 1, 32, 32, 0),
                                  (256, 1, 16, 32, 256), (256, 1, 16, 16, 128), (256, 1, 16, 16, 64),
                                  (64, 1, 24, 48, 0)])
 def test_conv_groupnorm_partials(cfg):
