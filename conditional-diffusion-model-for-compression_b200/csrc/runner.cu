@@ -532,6 +532,9 @@ struct cdc_ctx {
     float *stage_f32 = nullptr;  // NCHW fp32 staging for host-buffer calls
     size_t stage_elems = 0;
     float *pin_in = nullptr, *pin_x = nullptr, *pin_out = nullptr;
+    size_t pin_nl = 0, pin_nx = 0;  // elements the pinned staging buffers hold
+    cudaStream_t copy_stream = nullptr;  // cdc_decode_host: x_T upload overlaps the context net
+    cudaEvent_t ev_x = nullptr, ev_fork = nullptr;
     cudaGraphExec_t graph = nullptr;
     int graph_K = 0;
     int graph_skip = 0;  // measurement only (cdc_debug_graph_skip): class of ops left out of the captured graph
@@ -1054,6 +1057,9 @@ void cdc_destroy(cdc_ctx* ctx) {
     if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
     if (ctx->pin_x) cudaFreeHost(ctx->pin_x);
     if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->ev_x) cudaEventDestroy(ctx->ev_x);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     delete ctx;
 }
 
@@ -1303,30 +1309,66 @@ int cdc_decode(cdc_ctx* ctx, cdc_stream s) {
     return CDC_OK;
 }
 
+static bool host_ptr_is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();  // (unregistered host memory reports an error on old drivers)
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
 int cdc_decode_host(cdc_ctx* ctx, const float* latent_host, const float* xT_host, float* image_host, cdc_stream s) {
     NEED_PLAN();
     const size_t nl = static_cast<size_t>(ctx->B) * ctx->cfg.latent_ch * (ctx->H / 16) * (ctx->W / 16);
     const size_t nx = static_cast<size_t>(ctx->B) * 3 * ctx->H * ctx->W;
-    if (!ctx->pin_in) {
+    if (nl > ctx->pin_nl || nx > ctx->pin_nx) {  // (re)size the pinned staging buffers for this shape
+        CK(cudaStreamSynchronize(S(s)));
+        if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
+        if (ctx->pin_x) cudaFreeHost(ctx->pin_x);
+        if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
+        ctx->pin_in = ctx->pin_x = ctx->pin_out = nullptr;
         CK(cudaMallocHost(&ctx->pin_in, nl * 4));
         CK(cudaMallocHost(&ctx->pin_x, nx * 4));
         CK(cudaMallocHost(&ctx->pin_out, nx * 4));
+        ctx->pin_nl = nl;
+        ctx->pin_nx = nx;
     }
-    memcpy(ctx->pin_in, latent_host, nl * 4);
-    memcpy(ctx->pin_x, xT_host, nx * 4);
+    if (!ctx->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->ev_x, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    }
+    // page-locked caller buffers are copied from / to directly; pageable ones go through the pinned staging buffers
+    const float* lat_src = latent_host;
+    const float* x_src = xT_host;
+    if (!host_ptr_is_pinned(latent_host)) {
+        memcpy(ctx->pin_in, latent_host, nl * 4);
+        lat_src = ctx->pin_in;
+    }
+    if (!host_ptr_is_pinned(xT_host)) {
+        memcpy(ctx->pin_x, xT_host, nx * 4);
+        x_src = ctx->pin_x;
+    }
     float* d_lat = ctx->stage_f32;
     float* d_x = ctx->stage_f32 + nl;
     if (nl + nx > ctx->stage_elems) return ctx->fail(CDC_ERR_SHAPE, "staging buffer too small");
-    CK(cudaMemcpyAsync(d_lat, ctx->pin_in, nl * 4, cudaMemcpyHostToDevice, S(s)));
-    CK(cudaMemcpyAsync(d_x, ctx->pin_x, nx * 4, cudaMemcpyHostToDevice, S(s)));
+    // x_T (4.7 MB at 768x512) rides a second stream while the context net runs on the latent
+    CK(cudaEventRecord(ctx->ev_fork, S(s)));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
+    CK(cudaMemcpyAsync(d_x, x_src, nx * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->ev_x, ctx->copy_stream));
+    CK(cudaMemcpyAsync(d_lat, lat_src, nl * 4, cudaMemcpyHostToDevice, S(s)));
     int r;
     if ((r = cdc_set_latent(ctx, d_lat, s))) return r;
+    CK(cudaStreamWaitEvent(S(s), ctx->ev_x, 0));
     if ((r = cdc_set_x(ctx, d_x, s))) return r;
     if ((r = cdc_decode(ctx, s))) return r;
     if ((r = cdc_get_x(ctx, d_x, 1, s))) return r;
-    CK(cudaMemcpyAsync(ctx->pin_out, d_x, nx * 4, cudaMemcpyDeviceToHost, S(s)));
+    const bool out_pinned = host_ptr_is_pinned(image_host);
+    CK(cudaMemcpyAsync(out_pinned ? image_host : ctx->pin_out, d_x, nx * 4, cudaMemcpyDeviceToHost, S(s)));
     CK(cudaStreamSynchronize(S(s)));
-    memcpy(image_host, ctx->pin_out, nx * 4);
+    if (!out_pinned) memcpy(image_host, ctx->pin_out, nx * 4);
     return CDC_OK;
 }
 

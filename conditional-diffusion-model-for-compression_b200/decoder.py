@@ -138,8 +138,10 @@ class Decoder:
             return self._get_x0()
 
     @torch.no_grad()
-    def decode(self, latent, steps, *, init=None, gamma=0.8, seed=0, cond=None):
-        """latent y_hat fp32 [B,256,H/16,W/16] -> image fp32 [B,3,H,W] in [0,1] (K steps = one graph launch)."""
+    def decode(self, latent, steps, *, init=None, gamma=0.8, seed=0, cond=None, out=None):
+        """latent y_hat fp32 [B,256,H/16,W/16] -> image fp32 [B,3,H,W] in [0,1] (K steps = one graph launch).
+        Host tensors take the cdc_decode_host path (H2D + decode + D2H inside the library); page-locked inputs and a
+        page-locked `out` (optional, host path only: fp32 [B,3,H,W], returned) are copied from / to directly."""
         if steps != self.steps:
             self.set_sample_schedule(steps)
         B, _, h, w = latent.shape
@@ -153,7 +155,10 @@ class Decoder:
                 # host buffers: pinned staging + H2D/D2H inside the library
                 lat = latent.float().contiguous()
                 x0 = init.float().contiguous()
-                out = torch.empty(B, 3, H, W, dtype=torch.float32)
+                if out is None:
+                    out = torch.empty(B, 3, H, W, dtype=torch.float32)
+                elif out.shape != (B, 3, H, W) or out.dtype != torch.float32 or out.is_cuda or not out.is_contiguous():
+                    raise ValueError("out must be a contiguous fp32 host tensor of shape [B,3,H,W]")
                 _ffi.check(self.ctx, self.L.cdc_decode_host(self.ctx, C.c_void_p(lat.data_ptr()),
                                                             C.c_void_p(x0.data_ptr()), C.c_void_p(out.data_ptr()),
                                                             _stream_ptr()), "cdc_decode_host")

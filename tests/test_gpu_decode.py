@@ -114,6 +114,10 @@ def test_context_net_and_host_decode():
     assert e < 0.1
     img2 = dec.decode(lat.to(DEV), K, init=x.to(DEV)).cpu()
     assert torch.equal(img, img2)
+    # page-locked caller buffers are copied from / to directly (no staging copies): same result, returned in `out`
+    out = torch.empty_like(img).pin_memory()
+    img3 = dec.decode(lat.pin_memory(), K, init=x.pin_memory(), out=out)
+    assert img3 is out and torch.equal(img, img3)
 
 
 def test_flops_and_launch_accounting():
