@@ -2,6 +2,7 @@
 #pragma once
 #include "act.cuh"
 #include "gn_sums.cuh"
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -52,6 +53,15 @@ cudaError_t launch_repack_weight_up2(const float* src, act_t* dst, int O, int I,
 // qkv [B*N][768] act_t (q | k | v, head h = channels 64h..64h+63) -> o [B*N][256] bf16
 cudaError_t launch_attention(const act_t* qkv, act_t* o, int B, int N, int heads, cudaStream_t s);
 cudaError_t configure_attention();  // dynamic shared-memory limit (call once, outside graph capture)
+// tcgen05 version (attention.cu): qkv_map = 3-D tensor map {768 cols, N rows, B} of the qkv tensor, box {64, 128, 1},
+// 128-byte swizzle (built by the host runtime)
+struct alignas(64) AttnTcParams {
+    CUtensorMap qkv_map;
+    act_t* out;  // [B*N][heads * 64]
+    int N, heads;
+};
+cudaError_t configure_attention_tc();
+cudaError_t launch_attention_tc(const AttnTcParams& p, int B, cudaStream_t s);
 
 // ---- integer path (C10; oracle/entropy.py) ------------------------------------------------------
 cudaError_t launch_quantize(const float* y, const float* mu, int32_t* q, float* yhat, int64_t n, int64_t mu_inner,

@@ -127,6 +127,23 @@ static int encode_act_map(CUtensorMap* m, const act_t* base, int C, int Wd, int 
     return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
 }
 
+// qkv [B][N][cols] viewed as a 3-D tensor {cols, N, B}, box {64, 128, 1}: one head's Q / K / V slice of 128 tokens
+static int encode_qkv_map(CUtensorMap* m, const act_t* qkv, int cols, int N, int B) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return -1;
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(B)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(cols) * 2, static_cast<cuuint64_t>(N) * cols * 2};
+    cuuint32_t box[3] = {64, 128, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(m, CDC_TMA_DTYPE, 3, const_cast<act_t*>(qkv), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
+}
+static bool attention_legacy() {  // A/B switch: the mma.sync kernel
+    static const bool v = getenv("CDC_ATTN_LEGACY") != nullptr;
+    return v;
+}
+
 static int encode_w_map(CUtensorMap* m, const act_t* w, int K, int N, int BN) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return -1;
@@ -866,7 +883,15 @@ static int build_plans(cdc_ctx* ctx) {
         const act_t* qp = qkv.p;
         act_t* op_ = o.p;
         const int heads = ctx->cfg.heads;
-        at.run = [qp, op_, B, HW, heads](cudaStream_t s, int) { return launch_attention(qp, op_, B, HW, heads, s); };
+        auto ap = std::shared_ptr<AttnTcParams>(new AttnTcParams());
+        memset(ap.get(), 0, sizeof(AttnTcParams));
+        if (encode_qkv_map(&ap->qkv_map, qp, 3 * Cm, HW, B)) return ctx->fail(CDC_ERR_CUDA, "cuTensorMapEncodeTiled (qkv) failed");
+        ap->out = op_;
+        ap->N = HW;
+        ap->heads = heads;
+        at.run = [ap, qp, op_, B, HW, heads](cudaStream_t s, int) {
+            return attention_legacy() ? launch_attention(qp, op_, B, HW, heads, s) : launch_attention_tc(*ap, B, s);
+        };
         ctx->step_ops.push_back(at);
         ConvBuild cpj;
         cpj.name = "mid.attn.proj";
@@ -1031,7 +1056,8 @@ int cdc_create(const cdc_config* cfg, int device, cdc_ctx** out) {
         g_create_err = "cuTensorMapEncodeTiled entry point not found";
         return CDC_ERR_CUDA;
     }
-    if ((e = configure_attention()) != cudaSuccess || (e = configure_conv_kernels()) != cudaSuccess ||         (e = configure_kf_kernels()) != cudaSuccess) {
+    if ((e = configure_attention()) != cudaSuccess || (e = configure_attention_tc()) != cudaSuccess ||
+        (e = configure_conv_kernels()) != cudaSuccess ||         (e = configure_kf_kernels()) != cudaSuccess) {
         g_create_err = std::string("cudaFuncSetAttribute(conv kernels): ") + cudaGetErrorString(e);
         return CDC_ERR_CUDA;
     }
@@ -1600,10 +1626,17 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
 }
 
 int cdc_test_attention(const void* qkv, void* out, int B, int N, int heads, cdc_stream s) {
-    return launch_attention(static_cast<const act_t*>(qkv), static_cast<act_t*>(out), B, N, heads, S(s)) ==
-                   cudaSuccess
-               ? CDC_OK
-               : CDC_ERR_CUDA;
+    if (attention_legacy())
+        return launch_attention(static_cast<const act_t*>(qkv), static_cast<act_t*>(out), B, N, heads, S(s)) == cudaSuccess
+                   ? CDC_OK
+                   : CDC_ERR_CUDA;
+    AttnTcParams ap;
+    memset(&ap, 0, sizeof ap);
+    if (encode_qkv_map(&ap.qkv_map, static_cast<const act_t*>(qkv), 3 * heads * 64, N, B)) return CDC_ERR_CUDA;
+    ap.out = static_cast<act_t*>(out);
+    ap.N = N;
+    ap.heads = heads;
+    return launch_attention_tc(ap, B, S(s)) == cudaSuccess ? CDC_OK : CDC_ERR_CUDA;
 }
 
 int cdc_test_gn(const void* x, const void* r, void* y, const float* gamma, const float* beta, const float* film, int B,
