@@ -48,7 +48,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -57,16 +57,21 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summarise the samples taken inside the host-time window [t0, t1] (the timed region); nvidia-smi is started
+        before the warm-up so that it is already polling when the window opens."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        inside = [l for (t, l) in self.samples if (t0 is None or t >= t0) and (t1 is None or t <= t1 + 0.12)]
+        if not inside:  # window shorter than the polling period: the nearest samples
+            inside = [l for (_, l) in self.samples[-2:]]
+        for s in inside:
             f = [x.strip() for x in s.split(",")]
             try:
                 sm.append(float(f[0]))
@@ -179,11 +184,12 @@ def main():
         torch.cuda.synchronize()
 
     def timed(fn):
+        sampler = ClockSampler(local)
+        sampler.start()  # before the warm-up: nvidia-smi needs ~0.1-0.5 s to deliver its first sample
         for i in range(args.warmup):
             fn(i)
         barrier()
-        sampler = ClockSampler(local)
-        sampler.start()
+        t_begin = time.perf_counter()
         evs = []
         for i in range(args.warmup, n_img):
             flush.fill_(i & 0xFF)
@@ -193,7 +199,7 @@ def main():
             e.record()
             evs.append((s, e))
         barrier()
-        clocks = sampler.stop()
+        clocks = sampler.stop(t_begin, time.perf_counter())
         ms = sum(s.elapsed_time(e) for s, e in evs)
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if world > 1:
