@@ -18,12 +18,13 @@
 //   first use : every MMA accumulates; the epilogue re-zeroes an accumulator (tcgen05.st) right after draining it,
 //               so the issue stream has no special first K step
 //
-//   warp 0 : input-row producer (TMA)   warp 1 : tcgen05.mma issuer   warp 2 : TMEM allocator
-//   warp 3 : weight loader (TMA, once)  warps 4-11 : epilogue
+//   warp 0 : input-row producer (TMA)   warp 1 : barrier init + weight load (TMA, once), then tcgen05.mma issuer
+//   warp 2 : TMEM allocator             warps 4-11 : epilogue
 //
 // Epilogue: +bias, GroupNorm sums kept in registers over the whole strip and added once per strip to the
-// fixed-point accumulators of gn_sums.cuh (integer atomics: bitwise reproducible), fp16 pack, then either a swizzled shared-memory tile + one TMA store per
-// output row (coalesced 16 KB writes) or direct 16-byte stores; EPI_DDIM applies the sampler update.
+// fixed-point accumulators of gn_sums.cuh (integer atomics: bitwise reproducible), fp16 pack, then either a
+// swizzled shared-memory tile + one TMA store per output row (coalesced 16 KB writes) or direct 32-byte stores;
+// EPI_DDIM applies the sampler update.
 //
 // Oracle counterpart: oracle/unet.py `conv(k=3)` inside RB / stem / final (the reference ships no code).
 #include <stdio.h>
@@ -115,23 +116,8 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
             mbar_init(bar_xempty + 8 * s, kEpiThreads);
         }
         fence_mbar_init();
-    }
-    if (warp == 2) {  // (warp-collective)
-        tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_holder)), TMEM_COLS);
-        tmem_relinquish();
-    }
-    for (int i = threadIdx.x; i < BN; i += 128 + kEpiThreads) {
-        bias_s[i] = p.bias[cot * BN + i];
-        if (RES1) bias_s[BN + i] = p.res_bias[cot * BN + i];
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_holder;
-    if (kdbg) p.dbg[501] = clock64();
-
-    if (warp == 3 && lane == 0) {
-        // Weights are constants: their load need not wait for the preceding kernel (PDL).
+        // The weight block starts loading right away -- before the TMEM allocation and the CTA-wide sync (its barrier
+        // was initialised by this thread), and before griddepcontrol.wait: weights are constants.
         // smem block order [kw][chunk][2 - kh]: the kh taps of one (kw, chunk) form one contiguous B operand.
         mbar_expect_tx(bar_wres, (NKH * NKW + (RES1 ? 1 : 0)) * CH * WB);
         if constexpr (RES1)
@@ -150,6 +136,20 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
                                     (((nt & 3) * 4 + a2 * 2 + b2) * CH + ch) * 64, cot * BN);
         }
     }
+    if (warp == 2) {  // (warp-collective)
+        tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_holder)), TMEM_COLS);
+        tmem_relinquish();
+    }
+    for (int i = threadIdx.x; i < BN; i += 128 + kEpiThreads) {
+        bias_s[i] = p.bias[cot * BN + i];
+        if (RES1) bias_s[BN + i] = p.res_bias[cot * BN + i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    if (kdbg) p.dbg[501] = clock64();
+
     pdl_launch_dependents();
     pdl_wait();  // everything below touches activations written by the preceding kernels
 
