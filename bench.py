@@ -273,6 +273,7 @@ def main():
         ew_ms = (g_full - g_noew) / K_DDIM
         conv = [(n, f, b) for (n, f, b) in ops if f > 0 and "sdpa" not in n]
         conv_fl = sum(f for _, f, _ in conv)
+        n_gn_in = sum(1 for n, _, _ in conv if "+gn_in" in n)
         peak_tf, peak_gbs, which = peaks()
         ach = conv_fl / (conv_ms / 1e3) / 1e12
         traffic, traffic_of = None, None
@@ -283,7 +284,9 @@ def main():
         out["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                            "traffic": traffic, "traffic_of": traffic_of,
                            "kernel": f"conv_kf_kernel + conv_tc_kernel: the {len(conv)} tcgen05 conv launches of one denoise step "
-                                     f"({conv_fl / 1e9:.1f} GFLOP algorithmic, {conv_ms * 1e3:.0f} us in-graph)",
+                                     f"({conv_fl / 1e9:.1f} GFLOP algorithmic, {conv_ms * 1e3:.0f} us in-graph"
+                                     + (f"; {n_gn_in} of them also apply GroupNorm+FiLM+SiLU to their input rows in shared memory, "
+                                        "replacing elementwise passes)" if n_gn_in else ")"),
                            "peak_source": which, "how": "graph replay time minus replay time of the graph captured without the convs, / 17 steps",
                            "graph_ms": g_full, "conv_ms_per_step": conv_ms,
                            "step_tflops": dec.flops_per_step() / (g_full / K_DDIM / 1e3) / 1e12}

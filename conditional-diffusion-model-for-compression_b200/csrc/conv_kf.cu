@@ -34,6 +34,7 @@
 
 #include "conv_epilogue.cuh"
 #include "conv_kf.cuh"
+#include "gn_apply.cuh"
 #include "launch.cuh"
 #include "ptx.cuh"
 
@@ -42,10 +43,13 @@ namespace cdc {
 constexpr int kKfRowBytes = 17 * 1024;  // 130 pixels x 128 B = 16640, padded to a 1024 B multiple
 constexpr int kKfRowTx = 130 * 128;
 constexpr int kKfAccMax = 16;           // accumulator-ring barriers (the ring holds min(16, 512 / BN) output rows)
-constexpr int kKfAux = 1024 + 2 * 8 * 16 * 2 * 4;  // barriers + TMEM holder + bias, stats scratch
+constexpr int kKfAux = 1024 + 2 * 8 * 16 * 2 * 4 + 2048 + 256;  // barriers + TMEM holder + bias, stats scratch, APPLY coefficients
+constexpr int kKfXfThreads = 128;       // APPLY: input-transform threads (warps 2, 3, 12, 13: one per SM sub-partition)
 
-template <int BN, int CPG, int EPI, int CH, bool STAGE, bool XK16, int MODE, bool RES1>
-__global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __grid_constant__ KfParams p) {
+template <int BN, int CPG, int EPI, int CH, bool STAGE, bool XK16, int MODE, bool RES1, bool APPLY>
+__global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? 64 : 0), 1) conv_kf_kernel(const __grid_constant__ KfParams p) {
+    constexpr int kThreads = 128 + kEpiThreads + (APPLY ? 64 : 0);
+    static_assert(!APPLY || (MODE == 0 && !XK16 && !RES1 && EPI == EPI_STATS), "input GroupNorm: the ResBlock's second conv");
     constexpr int WB = BN * 128;  // one (tap, chunk) weight block
     constexpr uint32_t WB16 = WB >> 4;
     // accumulator ring: as many output rows as TMEM holds (a window that wraps costs split MMAs: the longer the ring,
@@ -79,9 +83,13 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
     // barriers: row_full[4] row_empty[4] tfull[16] tempty[16] wres xfull[8] xempty[8] (x = fused residual conv)
     const uint32_t bar_rfull = aux, bar_rempty = aux + 32, bar_tfull = aux + 64, bar_tempty = aux + 192, bar_wres = aux + 320;
     const uint32_t bar_xfull = aux + 328, bar_xempty = aux + 392;
+    const uint32_t bar_rready = aux + 464;  // APPLY: [4] row chunk transformed (one arrive per transform warp)
+    const uint32_t bar_afull = APPLY ? bar_rready : bar_rfull;  // what the MMA issuer waits for
     volatile uint32_t* tmem_holder = reinterpret_cast<volatile uint32_t*>(aux_gen + 456);
     float* bias_s = reinterpret_cast<float*>(aux_gen + 512);  // [BN] conv bias, then [BN] residual-conv bias
     float* red_s = reinterpret_cast<float*>(aux_gen + 1024);
+    float2* coef_s = reinterpret_cast<float2*>(aux_gen + 3072);      // APPLY: [CH * 64] (a, b) of the current image
+    float2* mr_s = reinterpret_cast<float2*>(aux_gen + 3072 + 2048);  // APPLY: [32] (mean, rstd)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nt = blockIdx.x / p.G1, cta = blockIdx.x % p.G1;
@@ -94,6 +102,14 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         p.dbg[508] = static_cast<long long>(gt);
     }
+    if (p.dbg != nullptr && threadIdx.x == 32 && blockIdx.x < 160) {  // every CTA: lifetime in globaltimer ns, SM id
+        unsigned long long gt;
+        uint32_t smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        p.dbg[512 + 3 * blockIdx.x] = static_cast<long long>(gt);
+        p.dbg[514 + 3 * blockIdx.x] = smid;
+    }
     const int units = p.batch * p.nseg * p.S;
 
     if (warp == 0 && lane == 0) {
@@ -105,6 +121,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
         for (int s = 0; s < 4; ++s) {
             mbar_init(bar_rfull + 8 * s, 1);
             mbar_init(bar_rempty + 8 * s, 1);
+            if (APPLY) mbar_init(bar_rready + 8 * s, kKfXfThreads / 32);
         }
         for (int s = 0; s < static_cast<int>(NACC); ++s) {
             mbar_init(bar_tfull + 8 * s, 1);
@@ -140,7 +157,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
         tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_holder)), TMEM_COLS);
         tmem_relinquish();
     }
-    for (int i = threadIdx.x; i < BN; i += 128 + kEpiThreads) {
+    for (int i = threadIdx.x; i < BN; i += kThreads) {
         bias_s[i] = p.bias[cot * BN + i];
         if (RES1) bias_s[BN + i] = p.res_bias[cot * BN + i];
     }
@@ -218,7 +235,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
             for (int u = cta; u < units; u += p.G1) {
                 int b, seg, si, h0, L;
                 decode(u, b, seg, si, h0, L);
-                mbar_wait(bar_rfull + 8 * rslot, rpar);  // first chunk of the strip
+                mbar_wait(bar_afull + 8 * rslot, rpar);  // first chunk of the strip
                 tc_fence_after();
                 if (kdbg && u == cta) p.dbg[504] = clock64();
                 for (int i = 0; i < L + 2; ++i) {
@@ -265,11 +282,11 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
                         const uint32_t nslot = rslot + 1 == static_cast<uint32_t>(NS) ? 0u : rslot + 1;
                         const bool more = ch + 1 < CH || i + 1 < L + 2;  // (a new row's first chunk also certifies its accumulator)
                         const uint32_t npar = nslot == 0 ? rpar ^ 1 : rpar;
-                        const uint32_t ready = more ? mbar_test_wait(bar_rfull + 8 * nslot, npar) : 1u;
+                        const uint32_t ready = more ? mbar_test_wait(bar_afull + 8 * nslot, npar) : 1u;
                         if (cnt != 0 && elect_one_sync()) steps(std::integral_constant<int, 0>{}, std::integral_constant<int, TH>{});
                         __syncwarp();
                         if (dbg && ch == 0) p.dbg[i * 4 + 1] = clock64();
-                        if (!ready) mbar_wait(bar_rfull + 8 * nslot, npar);
+                        if (!ready) mbar_wait(bar_afull + 8 * nslot, npar);
                         if (more) tc_fence_after();
                         if (dbg && ch == 0) p.dbg[i * 4 + 2] = clock64();
                         if (elect_one_sync()) {
@@ -295,7 +312,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
             }
             if (kdbg) p.dbg[505] = clock64();
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 12) {
         // ------------------------------------------------------------ epilogue (8 warps)
         const int q = warp & 3;            // TMEM sub-partition: lanes 32q .. 32q+31
         const int half = (warp - 4) >> 2;  // column half of the accumulator
@@ -516,6 +533,103 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
             if (STAGE && store_leader) bulk_wait_group<0>();
 
         }
+    } else if constexpr (APPLY) {
+        // ------------------------------------------------------------ input transform (warps 2, 3, 12, 13)
+        // y = SiLU(a*x + b) on every landed row chunk, in place, before the MMAs read it: the arithmetic of
+        // gn_apply_kernel (gn_apply.cuh), bit for bit.  Thread = (16-byte channel vector c, pixel lane pl): its 8 channels'
+        // (a, b) pairs stay in registers across the pixels of a chunk.  Pixels and rows outside the image are left as
+        // TMA zero-filled them: the conv pads with zeros AFTER the activation.
+        const int xt = (warp < 4 ? warp - 2 : warp - 10) * 32 + lane;
+        const int c = xt & 7, pl = xt >> 3;
+        const uint32_t toff = static_cast<uint32_t>(pl) * 128u + (static_cast<uint32_t>(c ^ (pl & 7)) << 4);  // 128-byte swizzle
+        constexpr int NIT = (130 + 15) / 16;
+        const int cpg_in = CH * 2;  // channels per group of the input (C_in / 32)
+        const double inv_n = kGnFixInv / (static_cast<double>(cpg_in) * p.H * p.W);
+        uint32_t slot = 0, par = 0;
+        int cur_b = -1;
+        float4 cf[4];
+        const bool xf_copy_only = p.dbg != nullptr && p.dbg[511] == 3;  // tools only: rows through registers, no arithmetic
+        for (int u = cta; u < units; u += p.G1) {
+            int b, seg, si, h0, L;
+            decode(u, b, seg, si, h0, L);
+            if (b != cur_b) {  // coefficient table of image b (once per CTA when the batch is 1)
+                named_bar_sync(3, kKfXfThreads);
+                if (xt < 32) mr_s[xt] = gn_mean_rstd(p.in_acc + (static_cast<size_t>(b) * 32 + xt) * 2, inv_n, p.in_eps);
+                named_bar_sync(3, kKfXfThreads);
+                for (int ci = xt; ci < CH * 64; ci += kKfXfThreads) {
+                    const float sc = p.in_film ? 1.0f + p.in_film[ci] : 1.0f, sh = p.in_film ? p.in_film[CH * 64 + ci] : 0.0f;
+                    const float2 ab = gn_fold(p.in_gamma[ci], p.in_beta[ci], sc, sh, mr_s[ci / cpg_in]);
+                    coef_s[ci] = make_float2(0.5f * ab.x, 0.5f * ab.y);  // (a/2, b/2): see silu_h
+                }
+                named_bar_sync(3, kKfXfThreads);
+                cur_b = b;
+                if constexpr (CH == 1) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) cf[j] = reinterpret_cast<const float4*>(coef_s + c * 8)[j];
+                }
+            }
+            const int w0 = seg * 128 - 1;
+            for (int i = 0; i < L + 2; ++i) {
+                const int h = h0 - 1 + i;
+                const bool row_in = h >= 0 && h < p.H;
+#pragma unroll
+                for (int ch = 0; ch < CH; ++ch) {
+                    if constexpr (CH > 1) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) cf[j] = reinterpret_cast<const float4*>(coef_s + ch * 64 + c * 8)[j];
+                    }
+                    long long* xdbg = (p.dbg != nullptr && blockIdx.x == 0 && xt == 0 && u == cta && i * CH + ch < 48) ? p.dbg + 1024 + (i * CH + ch) * 8 : nullptr;
+                    if (xdbg) xdbg[0] = clock64();
+                    mbar_wait(bar_rfull + 8 * slot, par);
+                    if (xdbg) xdbg[1] = clock64();
+                    if (row_in) {
+                        const uint32_t sb = ring + slot * kKfRowBytes + toff;
+                        // three phases with distinct registers per vector: all loads, all arithmetic, all stores -- a store
+                        // that has to leave the (busy) shared-memory queue before its registers are reused costs ~150 cycles
+                        uint4 v[NIT];
+                        bool ok[NIT];
+#pragma unroll
+                        for (int k = 0; k < NIT; ++k) {
+                            const int pxl = pl + 16 * k, gx = w0 + pxl;
+                            ok[k] = pxl < 130 && gx >= 0 && gx < p.W;
+                            v[k] = make_uint4(0u, 0u, 0u, 0u);
+                            if (ok[k])
+                                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                             : "=r"(v[k].x), "=r"(v[k].y), "=r"(v[k].z), "=r"(v[k].w)
+                                             : "r"(sb + k * 2048));
+                        }
+                        if (xdbg) {  // (tools) loads returned: the clock read depends on every loaded vector
+                            uint32_t accx = 0;
+#pragma unroll
+                            for (int k = 0; k < NIT; ++k) accx ^= v[k].x ^ v[k].w;
+                            long long tl;
+                            asm volatile("mov.u64 %0, %%clock64;" : "=l"(tl) : "r"(accx));
+                            xdbg[3] = tl;
+                        }
+                        if (!xf_copy_only) {
+#pragma unroll
+                            for (int k = 0; k < NIT; ++k) v[k] = gn_apply_vec<true, false, true>(v[k], v[k], cf);
+                        }
+#pragma unroll
+                        for (int k = 0; k < NIT; ++k) {
+                            if (ok[k])
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + k * 2048), "r"(v[k].x), "r"(v[k].y), "r"(v[k].z),
+                                             "r"(v[k].w)
+                                             : "memory");
+                        }
+                    }
+                    if (xdbg) xdbg[4] = clock64();
+                    fence_proxy_async_smem();  // generic-proxy writes -> visible to the MMA's async-proxy reads
+                    if (xdbg) xdbg[2] = clock64();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_rready + 8 * slot);
+                    if (++slot == static_cast<uint32_t>(NS)) {
+                        slot = 0;
+                        par ^= 1;
+                    }
+                }
+            }
+        }
     }
 
     tc_fence_before();
@@ -526,30 +640,39 @@ __global__ void __launch_bounds__(128 + kEpiThreads, 1) conv_kf_kernel(const __g
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         p.dbg[509] = static_cast<long long>(gt);
     }
+    if (p.dbg != nullptr && threadIdx.x == 32 && blockIdx.x < 160) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        p.dbg[513 + 3 * blockIdx.x] = static_cast<long long>(gt);
+    }
     if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------ host
 // (BN, CPG, EPI, CH, STAGED, XK16, MODE, RES1) instantiations: the layer shapes of the UNet / context net this variant serves.
-#define KF_ALL_CASES()                                     \
-    KF_CASE(64, 2, EPI_STATS, 1, true, false, 0, false)    \
-    KF_CASE(64, 2, EPI_STATS, 2, false, false, 0, false)   \
-    KF_CASE(64, 4, EPI_STATS, 1, true, false, 0, false)    \
-    KF_CASE(64, 4, EPI_STATS, 2, false, false, 0, false)   \
-    KF_CASE(64, 1, EPI_STORE, 1, true, false, 0, false)    \
-    KF_CASE(64, 1, EPI_STORE, 2, false, false, 0, false)   \
-    KF_CASE(64, 1, EPI_STORE, 2, false, true, 0, false)    \
-    KF_CASE(32, 4, EPI_STATS, 3, false, false, 0, false)   \
-    KF_CASE(32, 4, EPI_STATS, 4, false, false, 0, false)   \
-    KF_CASE(48, 6, EPI_STATS, 3, false, false, 0, false)   \
-    KF_CASE(32, 8, EPI_STATS, 4, false, false, 0, false)   \
-    KF_CASE(16, 1, EPI_DDIM, 1, false, false, 0, false)    \
-    KF_CASE(64, 1, EPI_STORE, 2, false, false, 1, false)   \
-    KF_CASE(64, 1, EPI_STORE, 3, false, false, 1, false)   \
-    KF_CASE(64, 1, EPI_STORE, 4, false, false, 1, false)   \
-    KF_CASE(64, 2, EPI_STATS, 2, false, false, 0, true)    \
-    KF_CASE(32, 4, EPI_STATS, 3, false, false, 0, true)    \
-    KF_CASE(32, 4, EPI_STATS, 4, false, false, 0, true)
+#define KF_ALL_CASES()                                            \
+    KF_CASE(64, 2, EPI_STATS, 1, true, false, 0, false, false)    \
+    KF_CASE(64, 2, EPI_STATS, 2, false, false, 0, false, false)   \
+    KF_CASE(64, 4, EPI_STATS, 1, true, false, 0, false, false)    \
+    KF_CASE(64, 4, EPI_STATS, 2, false, false, 0, false, false)   \
+    KF_CASE(64, 1, EPI_STORE, 1, true, false, 0, false, false)    \
+    KF_CASE(64, 1, EPI_STORE, 2, false, false, 0, false, false)   \
+    KF_CASE(64, 1, EPI_STORE, 2, false, true, 0, false, false)    \
+    KF_CASE(32, 4, EPI_STATS, 3, false, false, 0, false, false)   \
+    KF_CASE(32, 4, EPI_STATS, 4, false, false, 0, false, false)   \
+    KF_CASE(48, 6, EPI_STATS, 3, false, false, 0, false, false)   \
+    KF_CASE(32, 8, EPI_STATS, 4, false, false, 0, false, false)   \
+    KF_CASE(16, 1, EPI_DDIM, 1, false, false, 0, false, false)    \
+    KF_CASE(64, 1, EPI_STORE, 2, false, false, 1, false, false)   \
+    KF_CASE(64, 1, EPI_STORE, 3, false, false, 1, false, false)   \
+    KF_CASE(64, 1, EPI_STORE, 4, false, false, 1, false, false)   \
+    KF_CASE(64, 2, EPI_STATS, 2, false, false, 0, true, false)    \
+    KF_CASE(32, 4, EPI_STATS, 3, false, false, 0, true, false)    \
+    KF_CASE(32, 4, EPI_STATS, 4, false, false, 0, true, false)    \
+    KF_CASE(64, 2, EPI_STATS, 1, true, false, 0, false, true)     \
+    KF_CASE(64, 4, EPI_STATS, 2, false, false, 0, false, true)    \
+    KF_CASE(48, 6, EPI_STATS, 3, false, false, 0, false, true)    \
+    KF_CASE(32, 8, EPI_STATS, 4, false, false, 0, false, true)
 
 int kf_smem_bytes(int bn, int CH, int NS, bool staged, int mode, bool res) {
     return 1024 + NS * kKfRowBytes + ((mode == 1 ? 4 : 9) + (res ? 1 : 0)) * CH * bn * 128 + (staged ? 2 * 128 * bn * 2 : 0) + kKfAux;
@@ -569,12 +692,12 @@ bool kf_plan(int bn, int CH, int mode, bool res, int* NS, bool* staged) {
     return false;
 }
 
-bool kf_inst_ok(int bn, int cpg, int epi, int CH, int mode, bool res) {
+bool kf_inst_ok(int bn, int cpg, int epi, int CH, int mode, bool res, bool apply) {
     int ns;
     bool st;
     if (!kf_plan(bn, CH, mode, res, &ns, &st)) return false;
-#define KF_CASE(BN_, CPG_, EPI_, CH_, ST_, X_, M_, R_) \
-    if (bn == BN_ && (EPI_ != EPI_STATS || cpg == CPG_) && epi == EPI_ && CH == CH_ && st == ST_ && mode == M_ && res == R_) return true;
+#define KF_CASE(BN_, CPG_, EPI_, CH_, ST_, X_, M_, R_, A_) \
+    if (bn == BN_ && (EPI_ != EPI_STATS || cpg == CPG_) && epi == EPI_ && CH == CH_ && st == ST_ && mode == M_ && res == R_ && apply == A_) return true;
     KF_ALL_CASES()
 #undef KF_CASE
     return false;
@@ -582,8 +705,8 @@ bool kf_inst_ok(int bn, int cpg, int epi, int CH, int mode, bool res) {
 
 cudaError_t configure_kf_kernels() {
     cudaError_t e;
-#define KF_CASE(BN_, CPG_, EPI_, CH_, ST_, X_, M_, R_)                                                      \
-    if ((e = cudaFuncSetAttribute(conv_kf_kernel<BN_, CPG_, EPI_, CH_, ST_, X_, M_, R_>,                      \
+#define KF_CASE(BN_, CPG_, EPI_, CH_, ST_, X_, M_, R_, A_)                                                  \
+    if ((e = cudaFuncSetAttribute(conv_kf_kernel<BN_, CPG_, EPI_, CH_, ST_, X_, M_, R_, A_>,                  \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) \
         return e;
     KF_ALL_CASES()
@@ -591,15 +714,17 @@ cudaError_t configure_kf_kernels() {
     return cudaSuccess;
 }
 
-cudaError_t launch_conv_kf(const KfParams& p, int bn, int cpg, int epi, int CH, bool xk16, int mode, bool res, cudaStream_t stream) {
+cudaError_t launch_conv_kf(const KfParams& p, int bn, int cpg, int epi, int CH, bool xk16, int mode, bool res, bool apply,
+                           cudaStream_t stream) {
     int ns;
     bool st;
     if (!kf_plan(bn, CH, mode, res, &ns, &st) || ns != p.NS) return cudaErrorInvalidValue;
-    const dim3 grid(p.n_tiles * p.G1), block(128 + kEpiThreads);
+    const dim3 grid(p.n_tiles * p.G1), block(128 + kEpiThreads + (apply ? 64 : 0));
     const size_t smem = kf_smem_bytes(bn, CH, ns, st, mode, res);
-#define KF_CASE(BN_, CPG_, EPI_, CH_, ST_, X_, M_, R_)                                                                                     \
-    if (bn == BN_ && (EPI_ != EPI_STATS || cpg == CPG_) && epi == EPI_ && CH == CH_ && st == ST_ && xk16 == X_ && mode == M_ && res == R_)   \
-        return launch_pdl(conv_kf_kernel<BN_, CPG_, EPI_, CH_, ST_, X_, M_, R_>, grid, block, smem, stream, p);
+#define KF_CASE(BN_, CPG_, EPI_, CH_, ST_, X_, M_, R_, A_)                                                                                \
+    if (bn == BN_ && (EPI_ != EPI_STATS || cpg == CPG_) && epi == EPI_ && CH == CH_ && st == ST_ && xk16 == X_ && mode == M_ && res == R_ && \
+        apply == A_)                                                                                                                         \
+        return launch_pdl(conv_kf_kernel<BN_, CPG_, EPI_, CH_, ST_, X_, M_, R_, A_>, grid, block, smem, stream, p);
     KF_ALL_CASES()
 #undef KF_CASE
     return cudaErrorInvalidValue;

@@ -25,6 +25,13 @@ struct alignas(64) KfParams {
     int res_ldc;
     const float* res_bias;
     gn_sum_t* gn_acc;     // EPI_STATS: [batch][32][2] fixed-point accumulators (gn_sums.cuh), zero on entry
+    // APPLY: the input is the raw output of the preceding conv; GroupNorm (+ FiLM) + SiLU of THAT conv's statistics is
+    // applied to every input row in shared memory before the MMAs read it (replaces a gn_apply_kernel pass over HBM)
+    const gn_sum_t* in_acc;   // [batch][32][2] totals of the input tensor (complete: written by the preceding kernel)
+    const float* in_gamma;    // [C_in]
+    const float* in_beta;
+    const float* in_film;     // [2 * C_in] (scale | shift) of this step, or null
+    float in_eps;
     float* x;             // EPI_DDIM (see ConvParams)
     act_t* xpad;
     float* x0_out;
@@ -34,11 +41,12 @@ struct alignas(64) KfParams {
 
 // mode 0: 3x3 conv; mode 1: nearest-x2 upsample + 3x3 conv (four parity 2x2 convs on the low-resolution input)
 // res: the ResBlock's 1x1 residual conv rides along (its weights are resident too, its accumulators share TMEM)
-bool kf_inst_ok(int bn, int cpg, int epi, int CH, int mode, bool res);
+// apply: GroupNorm + SiLU of the input applied in shared memory (see in_acc)
+bool kf_inst_ok(int bn, int cpg, int epi, int CH, int mode, bool res, bool apply = false);
 bool kf_plan(int bn, int CH, int mode, bool res, int* NS, bool* staged);  // shared-memory plan; false if the weights do not fit
 int kf_smem_bytes(int bn, int CH, int NS, bool staged, int mode, bool res);
 cudaError_t configure_kf_kernels();
-cudaError_t launch_conv_kf(const KfParams& p, int bn, int cpg, int epi, int CH, bool xk16, int mode, bool res,
+cudaError_t launch_conv_kf(const KfParams& p, int bn, int cpg, int epi, int CH, bool xk16, int mode, bool res, bool apply,
                            cudaStream_t stream);  // xk16: chunk 0 has 16 real channels (stem)
 
 }  // namespace cdc

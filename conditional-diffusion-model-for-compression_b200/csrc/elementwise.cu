@@ -1,6 +1,7 @@
 // HBM-/latency-bound kernels around K-conv: GroupNorm statistics / apply(+SiLU,+residual),
 // time-embedding MLP + FiLM vectors, layout conversion at the API boundary, weight repack.
 // Oracle counterparts: oracle/unet.py RB, Attn.gn, TimeEmbed; SURVEY.md 2.2 C5, C6, C8.
+#include "gn_apply.cuh"
 #include "gn_sums.cuh"
 #include "kernels.cuh"
 #include "launch.cuh"
@@ -78,38 +79,6 @@ cudaError_t launch_gn_stats(const act_t* x, gn_sum_t* acc, int B, int HW, int C,
 
 // ------------------------------------------------------------------------------------------------
 // Apply: y = SiLU(a*x + b) (+ r), 8 channels (16 B) per thread, grid-stride.
-// x * sigmoid(x) = x * (0.5 + 0.5 * tanh(x / 2)): ONE MUFU op (tanh.approx.f32, max relative error 2^-11, below the
-// fp16 rounding of the stored result) instead of ex2 + rcp -- a 25 M-element level-0 tensor costs 13 us of MUFU time
-// chip-wide with two ops per element, which made the apply pass MUFU-bound rather than HBM-bound.
-__device__ __forceinline__ float silu_f(float v) {
-    float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * v));
-    const float h = 0.5f * v;
-    return fmaf(h, t, h);
-}
-
-template <bool SILU, bool RES>
-__device__ __forceinline__ uint4 gn_apply_vec(const uint4 u, const uint4 rr, const float4 (&c)[4]) {
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-    const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
-    uint32_t o[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float v0 = c[j].x * act_lo(w[j]) + c[j].y;  // c = (a0, b0, a1, b1)
-        float v1 = c[j].z * act_hi(w[j]) + c[j].w;
-        if (SILU) {
-            v0 = silu_f(v0);
-            v1 = silu_f(v1);
-        }
-        if (RES) {
-            v0 += act_lo(rw[j]);
-            v1 += act_hi(rw[j]);
-        }
-        o[j] = pack_act2_nosat(v0, v1);  // |SiLU(GN(x))| (+ residual) cannot reach the fp16 limit
-    }
-    return make_uint4(o[0], o[1], o[2], o[3]);
-}
-
 // GroupNorm coefficients of this thread's 8 channels, y = a*x + b with the affine and FiLM (1 + s, sh) folded in, from
 // the fixed-point (sum, sum of squares) accumulators of the image (gn_sums.cuh).  Same arithmetic as the oracle's
 // F.group_norm + FiLM (oracle/unet.py RB): mean / variance in double, rstd = 1 / sqrt(var + eps).
@@ -127,13 +96,7 @@ __device__ __forceinline__ void gn_group_stats(const GnCoef& g, int B, float2* s
     const int cpg = g.C / 32;
     const double inv_n = kGnFixInv / (static_cast<double>(cpg) * g.HW);
     for (int i = threadIdx.x; i < B * 32; i += blockDim.x) {
-        const gn_sum_t* a = g.acc + static_cast<size_t>(i) * 2;
-        const double m = static_cast<double>(a[0]) * inv_n;
-        double var = static_cast<double>(a[1]) * inv_n - m * m;
-        const float v = fmaxf(static_cast<float>(var), 0.0f) + g.eps;
-        float r = rsqrtf(v);
-        r = r * (1.5f - 0.5f * v * r * r);
-        s_mr[i] = make_float2(static_cast<float>(m), r);
+        s_mr[i] = gn_mean_rstd(g.acc + static_cast<size_t>(i) * 2, inv_n, g.eps);
     }
     __syncthreads();
 }
@@ -166,11 +129,9 @@ __device__ __forceinline__ void gn_coef(const GnChan& k, const float2* s_mr, int
     float ab[16];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const float2 mr = s_mr[b * 32 + (c0 + j) / cpg];
-        const float a = k.gamma[j] * mr.y;
-        const float bb = k.beta[j] - mr.x * a;
-        ab[2 * j] = a * k.sc[j];               // FiLM: (a*x + b) * (1 + s) + sh   (s = sh = 0 without FiLM)
-        ab[2 * j + 1] = bb * k.sc[j] + k.sh[j];
+        const float2 f = gn_fold(k.gamma[j], k.beta[j], k.sc[j], k.sh[j], s_mr[b * 32 + (c0 + j) / cpg]);  // (s = sh = 0 without FiLM)
+        ab[2 * j] = f.x;
+        ab[2 * j + 1] = f.y;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) c[j] = make_float4(ab[4 * j], ab[4 * j + 1], ab[4 * j + 2], ab[4 * j + 3]);

@@ -110,6 +110,15 @@ struct ConvBuild {
     const ConvW* res_w = nullptr;
     Act res_out;
     bool x16 = false;          // source 0 carries at most 16 non-zero channels (the stem's x_t copy)
+    // input GroupNorm (+FiLM) + SiLU applied inside the conv (kf path only; conv_uses_kf reports whether it is taken):
+    // the source is the RAW output of the preceding conv, in_acc that conv's statistics slot
+    const gn_sum_t* in_acc = nullptr;
+    const float* in_gamma = nullptr;
+    const float* in_beta = nullptr;
+    int in_film_off = -1;      // offset into the step's FiLM vector, or -1
+    float in_eps = 1e-5f;
+    float* const* film_base = nullptr;  // -> ctx->film: [steps][*film_total] FiLM vectors of the schedule (set later)
+    const int* film_total = nullptr;
 };
 
 static int encode_act_map(CUtensorMap* m, const act_t* base, int C, int Wd, int Hd, int B, size_t sW, size_t sH,
@@ -195,8 +204,17 @@ static void conv_geometry(const ConvBuild& cb, int& gw, int& gh, int& nphase, in
 struct KfGeom {
     int bn, CH, n_tiles, nseg, S, G1, NS, mode;
     bool staged, res;
+    bool apply;  // the input GroupNorm + SiLU runs inside the kernel
     bool tr;  // transposed walk: strips run along image columns (less padding / halo for e.g. a 128 x 192 level)
 };
+static bool fuse_apply_enabled() {  // CDC_FUSE_APPLY=0: GroupNorm 1 of every ResBlock as a pass of its own (A/B, tests)
+    const char* e = getenv("CDC_FUSE_APPLY");
+    return !(e && atoi(e) == 0);
+}
+static int fuse_apply_max_tiles() {  // CDC_FUSE_APPLY=n > 1: fuse into convs with up to n N tiles (experiments)
+    const char* e = getenv("CDC_FUSE_APPLY");
+    return e && atoi(e) > 1 ? atoi(e) : 1;
+}
 static bool kf_disabled() {
     static int v = -1;
     if (v < 0) v = getenv("CDC_NO_KF") ? 1 : 0;
@@ -233,6 +251,10 @@ static bool conv_uses_kf(const ConvBuild& cb, int B, int num_sms, KfGeom* g) {
         break;
     }
     if (!g->bn) return false;
+    // (every N tile's CTAs transform the same rows: with more than fuse_apply_max_tiles() tiles the redundant MUFU work
+    // costs more than the pass it replaces -- measured: fusing levels 1-3 as well made the step 17 % slower)
+    g->apply = cb.in_acc != nullptr && !g->res && cb.srcs.size() == 1 && cb.cpg == g->CH * 2 &&
+               cb.w->n_pad / g->bn <= fuse_apply_max_tiles() && kf_inst_ok(g->bn, cb.cpg, cb.epi, g->CH, g->mode, false, true);
     g->n_tiles = cb.w->n_pad / g->bn * (g->mode == 1 ? 4 : 1);
     if (cb.epi == EPI_DDIM && g->n_tiles != 1) return false;
     // strip geometry for a walk along image rows (tr = 0) or image columns (tr = 1): relative cost = padding of the
@@ -331,6 +353,13 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
             kp->out = cb.out.p;
             kp->bias = w.bias;
             kp->gn_acc = cb.gn_acc;
+            if (cb.in_acc && !kg.apply) return fail("input GroupNorm requested but this conv cannot apply it (caller must check)");
+            if (kg.apply) {
+                kp->in_acc = cb.in_acc;
+                kp->in_gamma = cb.in_gamma;
+                kp->in_beta = cb.in_beta;
+                kp->in_eps = cb.in_eps;
+            }
             kp->x = cb.x;
             kp->xpad = cb.xpad;
             kp->x0_out = cb.x0_out;
@@ -340,6 +369,9 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
             const double Mout = Ms * (kg.mode == 1 ? 4.0 : 1.0);  // algorithmic: the 3x3 conv on the upsampled grid
             op->flops = 2.0 * Mout * w.n_true * (9.0 * w.c_true);
             op->bytes = 2.0 * (Ms * w.c_true + Mout * w.n_true + 9.0 * w.c_true * w.n_true);
+            if (kg.apply) {  // the GroupNorm apply pass no longer touches HBM; its arithmetic rides along
+                op->name += "+gn_in";
+            }
             if (kg.res) {  // the 1x1 residual conv's algorithmic work moves into this launch
                 op->flops += 2.0 * Ms * cb.res_w->n_true * cb.res_w->c_true;
                 op->bytes += 2.0 * (Ms * cb.res_w->n_true + static_cast<double>(cb.res_w->c_true) * cb.res_w->n_true);
@@ -348,17 +380,26 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
             const int epi = cb.epi, cpg = cb.cpg, bn_k = kg.bn, CHk = kg.CH;
             const bool xk = cb.x16 && cb.epi == EPI_STORE && kg.bn == 64 && kg.CH == 2 && cb.srcs[0].C == 64 && kg.mode == 0;
             const int kmode = kg.mode;
-            const bool kres = kg.res;
+            const bool kres = kg.res, kapply = kg.apply;
             const std::vector<float>*c0 = cb.c0, *c1 = cb.c1;
-            op->run = [kp, bn_k, cpg, epi, CHk, xk, kmode, kres, c0, c1](cudaStream_t s, int k) -> cudaError_t {
+            float* const* film_base = cb.film_base;
+            const int* film_total = cb.film_total;
+            const int film_off = cb.in_film_off;
+            op->run = [kp, bn_k, cpg, epi, CHk, xk, kmode, kres, kapply, c0, c1, film_base, film_total, film_off](cudaStream_t s,
+                                                                                                                 int k) -> cudaError_t {
                 if (epi == EPI_DDIM) {
                     if (!c0 || k < 0 || k >= static_cast<int>(c0->size())) return cudaErrorInvalidValue;
                     KfParams q = *kp;
                     q.c0 = (*c0)[k];
                     q.c1 = (*c1)[k];
-                    return launch_conv_kf(q, bn_k, cpg, epi, CHk, xk, kmode, kres, s);
+                    return launch_conv_kf(q, bn_k, cpg, epi, CHk, xk, kmode, kres, false, s);
                 }
-                return launch_conv_kf(*kp, bn_k, cpg, epi, CHk, xk, kmode, kres, s);
+                if (kapply && film_off >= 0) {  // this step's FiLM (scale | shift) of the input GroupNorm
+                    KfParams q = *kp;
+                    q.in_film = *film_base + static_cast<size_t>(k) * *film_total + film_off;
+                    return launch_conv_kf(q, bn_k, cpg, epi, CHk, xk, kmode, kres, true, s);
+                }
+                return launch_conv_kf(*kp, bn_k, cpg, epi, CHk, xk, kmode, kres, kapply, s);
             };
             return CDC_OK;
         }
@@ -772,7 +813,6 @@ struct PlanB {
             if (!res_fused) c1.res_w = nullptr;
         }
         conv(c1);
-        gn(name + ".gn1", wp + ".gn1", film_idx, c1.gn_acc, t1, nullptr, t1, true);
         ConvBuild c2;
         c2.name = name + ".conv2";
         c2.srcs = {t1};
@@ -781,6 +821,23 @@ struct PlanB {
         c2.epi = EPI_STATS;
         c2.cpg = cpg;
         c2.gn_acc = new_gn_slot();
+        // GroupNorm 1 (+FiLM) + SiLU: applied by conv2 to its own input rows in shared memory when the kh-fused kernel has
+        // that instantiation (saves a read + write of the tensor in HBM and a launch), else as a pass of its own
+        if (rc) return;
+        c2.in_acc = c1.gn_acc;
+        c2.in_gamma = find_w(ctx, wp + ".gn1.weight")->p;
+        c2.in_beta = find_w(ctx, wp + ".gn1.bias")->p;
+        c2.in_eps = ctx->cfg.gn_eps;
+        if (film_idx >= 0) {
+            c2.in_film_off = ctx->film_off[film_idx];
+            c2.film_base = &ctx->film;
+            c2.film_total = &ctx->film_total;
+        }
+        KfGeom kg2;
+        if (!(fuse_apply_enabled() && conv_uses_kf(c2, ctx->B, ctx->num_sms, &kg2) && kg2.apply)) {
+            c2.in_acc = nullptr;
+            gn(name + ".gn1", wp + ".gn1", film_idx, c1.gn_acc, t1, nullptr, t1, true);
+        }
         conv(c2);
         const act_t* resp = in[0].p;
         if (cin != cout) {
@@ -1545,15 +1602,36 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
         cb.cpg = cout / 32;
         cb.gn_acc = reinterpret_cast<gn_sum_t*>(gn_sums);
     }
+    void* in_gn = nullptr;  // tools (CDC_TEST_CONV_APPLY=1): time the conv with the input GroupNorm fused -- unit statistics
+    if (getenv("CDC_TEST_CONV_APPLY") && gn_sums && c1 == 0 && cout == cin) {
+        const int cpg_in = cin / 32;
+        std::vector<long long> acc(static_cast<size_t>(B) * 64);
+        for (size_t i = 0; i < acc.size(); i += 2) {
+            acc[i] = 0;
+            acc[i + 1] = static_cast<long long>(cpg_in) * H * W * (1LL << 20);  // mean 0, variance 1
+        }
+        std::vector<float> gb(2 * cin, 0.0f);
+        for (int i = 0; i < cin; ++i) gb[i] = 1.0f;
+        CK(cudaMalloc(&in_gn, acc.size() * 8 + gb.size() * 4));
+        CK(cudaMemcpy(in_gn, acc.data(), acc.size() * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(static_cast<char*>(in_gn) + acc.size() * 8, gb.data(), gb.size() * 4, cudaMemcpyHostToDevice));
+        cb.in_acc = static_cast<const gn_sum_t*>(in_gn);
+        cb.in_gamma = reinterpret_cast<const float*>(static_cast<char*>(in_gn) + acc.size() * 8);
+        cb.in_beta = cb.in_gamma + cin;
+        KfGeom kga;
+        if (!(conv_uses_kf(cb, B, prop.multiProcessorCount, &kga) && kga.apply)) cb.in_acc = nullptr;
+        printf("test_conv: input GroupNorm fused: %s\n", cb.in_acc ? "yes" : "no");
+    }
     long long* dbg = nullptr;
     long long* dbg_dev = nullptr;
-    std::vector<long long> dbg_host(512, 0);
+    std::vector<long long> dbg_host(2048, 0);
     if (getenv("CDC_STRIP_DEBUG")) {
         // plain device memory (managed memory would page-fault inside the timed regions)
-        cudaMalloc(&dbg_dev, 512 * sizeof(long long));
-        std::vector<long long> init(512, 0);
+        cudaMalloc(&dbg_dev, 2048 * sizeof(long long));
+        std::vector<long long> init(2048, 0);
         if (atoi(getenv("CDC_STRIP_DEBUG")) == 2) init[511] = 1;
-        cudaMemcpy(dbg_dev, init.data(), 512 * sizeof(long long), cudaMemcpyHostToDevice);
+        if (atoi(getenv("CDC_STRIP_DEBUG")) == 3) init[511] = 3;  // APPLY: move the rows through registers without the arithmetic
+        cudaMemcpy(dbg_dev, init.data(), 2048 * sizeof(long long), cudaMemcpyHostToDevice);
         cb.dbg = dbg_dev;
     }
     Op op;
@@ -1594,7 +1672,7 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
         cudaEventDestroy(e1);
     }
     if (dbg_dev) {
-        cudaMemcpy(dbg_host.data(), dbg_dev, 512 * sizeof(long long), cudaMemcpyDeviceToHost);
+        cudaMemcpy(dbg_host.data(), dbg_dev, 2048 * sizeof(long long), cudaMemcpyDeviceToHost);
         cudaFree(dbg_dev);
         dbg = dbg_host.data();
     }
@@ -1615,9 +1693,30 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
             printf("  %2d: %6lld %6lld %6lld %6lld %6lld %6lld | %6lld %6lld\n", i, e[1] - e[0], e[2] - e[1], e[3] - e[2], e[4] - e[3],
                    e[5] - e[4], e[6] - e[5], e[6] - e[0], i ? e[0] - (e - 8)[0] : 0LL);
         }
+        if (dbg[1024 + 2]) {
+            printf("kf input-transform warp 2 timeline (CTA 0): chunk: wait_row loads math+stores fence | since previous\n");
+            for (int i = 0; i < 48 && dbg[1024 + i * 8 + 2]; ++i) {
+                const long long* e = dbg + 1024 + i * 8;
+                printf("  %2d: %6lld %6lld %6lld %6lld | %6lld\n", i, e[1] - e[0], e[3] ? e[3] - e[1] : 0LL, e[3] ? e[4] - e[3] : e[4] - e[1],
+                       e[2] - e[4], i ? e[0] - (e - 8)[0] : 0LL);
+            }
+        }
+        {  // lifetimes of all CTAs relative to the earliest start
+            long long t0 = 0, t1 = 0;
+            int n = 0;
+            for (int c = 0; c < 160 && dbg[512 + 3 * c]; ++c, ++n) {
+                t0 = n == 0 ? dbg[512 + 3 * c] : std::min(t0, dbg[512 + 3 * c]);
+                t1 = std::max(t1, dbg[513 + 3 * c]);
+            }
+            printf("kf CTAs: %d, first start -> last end %lld ns; per CTA (start, end, SM):", n, t1 - t0);
+            for (int c = 0; c < n; ++c)
+                printf("%s %lld-%lld@%lld", c % 8 == 0 ? "\n " : "", dbg[512 + 3 * c] - t0, dbg[513 + 3 * c] - t0, dbg[514 + 3 * c]);
+            printf("\n");
+        }
         dbg = nullptr;
     }
     ar.release();
+    if (in_gn) cudaFree(in_gn);
     if (ce != cudaSuccess) {
         g_create_err = std::string("test_conv: ") + cudaGetErrorString(ce);
         return CDC_ERR_CUDA;

@@ -1,0 +1,49 @@
+// MUFU throughput on B200 per SM sub-partition: tanh.approx.f32 vs tanh.approx.f16x2 vs ex2.approx.ftz.f32, one warp per
+// sub-partition (the shape of the input-transform warps of conv_kf.cu) and 8 warps per sub-partition.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdint.h>
+template <int MODE>
+__global__ void k(long long* out, float seed, int iters) {
+    float f[8];
+    uint32_t h[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { f[j] = seed + 0.01f * j + 0.001f * threadIdx.x; h[j] = 0x38003400u + j * 17 + threadIdx.x; }
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (MODE == 0) asm volatile("tanh.approx.f32 %0, %0;" : "+f"(f[j]));
+            if (MODE == 1) asm volatile("tanh.approx.f16x2 %0, %0;" : "+r"(h[j]));
+            if (MODE == 2) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(f[j]));
+            if (MODE == 3) asm volatile("fma.rn.f32 %0, %0, %0, %0;" : "+f"(f[j]));
+        }
+    }
+    const long long t1 = clock64();
+    float s = 0; uint32_t x = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s += f[j]; x ^= h[j]; }
+    if (threadIdx.x % 32 == 0) out[blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32] = t1 - t0;
+    if (s == 12345.f && x == 77) out[0] = 0;
+}
+template <int MODE>
+void run(const char* name, int threads) {
+    long long* d; cudaMalloc(&d, 148 * 32 * 8);
+    const int iters = 2000;
+    k<MODE><<<148, threads>>>(d, 0.3f, iters);
+    cudaDeviceSynchronize();
+    long long h[148 * 32]; cudaMemcpy(h, d, sizeof(long long) * 148 * (threads / 32), cudaMemcpyDeviceToHost);
+    double tot = 0; for (int i = 0; i < 148 * (threads / 32); ++i) tot += h[i];
+    const double cyc = tot / (148 * (threads / 32));
+    const double warps_per_smsp = threads / 128.0;
+    printf("%-22s %4d threads/SM: %6.2f cycles per warp instruction per sub-partition -> %5.2f lanes/clk/SMSP\n", name, threads,
+           cyc / (iters * 8.0) / warps_per_smsp, 32.0 * warps_per_smsp * iters * 8.0 / cyc);
+    cudaFree(d);
+}
+int main() {
+    for (int t : {128, 1024}) {
+        if (t == 128) { run<0>("tanh.approx.f32", 128); run<1>("tanh.approx.f16x2", 128); run<2>("ex2.approx.ftz.f32", 128); run<3>("fma.rn.f32", 128); }
+        else { run<0>("tanh.approx.f32", 1024); run<1>("tanh.approx.f16x2", 1024); run<2>("ex2.approx.ftz.f32", 1024); run<3>("fma.rn.f32", 1024); }
+    }
+    return 0;
+}
