@@ -1630,7 +1630,7 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
         cudaMalloc(&dbg_dev, 2048 * sizeof(long long));
         std::vector<long long> init(2048, 0);
         if (atoi(getenv("CDC_STRIP_DEBUG")) == 2) init[511] = 1;
-        if (atoi(getenv("CDC_STRIP_DEBUG")) == 3) init[511] = 3;  // APPLY: move the rows through registers without the arithmetic
+        if (atoi(getenv("CDC_STRIP_DEBUG")) >= 3) init[511] = atoi(getenv("CDC_STRIP_DEBUG"));  // APPLY transform variants (conv_kf.cu xf_mode)
         cudaMemcpy(dbg_dev, init.data(), 2048 * sizeof(long long), cudaMemcpyHostToDevice);
         cb.dbg = dbg_dev;
     }
