@@ -17,6 +17,18 @@ __global__ void k(long long* out, float seed, int iters) {
             if (MODE == 1) asm volatile("tanh.approx.f16x2 %0, %0;" : "+r"(h[j]));
             if (MODE == 2) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(f[j]));
             if (MODE == 3) asm volatile("fma.rn.f32 %0, %0, %0, %0;" : "+f"(f[j]));
+            if (MODE == 4) asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h[j]) : "f"(f[j]), "f"(__uint_as_float(h[j])));
+            if (MODE == 5) asm volatile("{.reg .b16 lo, hi; mov.b32 {lo, hi}, %1; cvt.f32.f16 %0, lo;}" : "=f"(f[j]) : "r"(__float_as_uint(f[j])));
+            if (MODE == 6) {  // the apply arithmetic of one element pair: unpack x2, fma x2, tanh x2, fma x2, pack
+                float a, b;
+                asm volatile("{.reg .b16 lo, hi; mov.b32 {lo, hi}, %2; cvt.f32.f16 %0, lo; cvt.f32.f16 %1, hi;}" : "=f"(a), "=f"(b) : "r"(h[j]));
+                a = fmaf(a, 0.51f, 0.01f); b = fmaf(b, 0.49f, -0.01f);
+                float ta, tb;
+                asm volatile("tanh.approx.f32 %0, %1;" : "=f"(ta) : "f"(a));
+                asm volatile("tanh.approx.f32 %0, %1;" : "=f"(tb) : "f"(b));
+                a = fmaf(a, ta, a); b = fmaf(b, tb, b);
+                asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h[j]) : "f"(b), "f"(a));
+            }
         }
     }
     const long long t1 = clock64();
@@ -41,6 +53,9 @@ void run(const char* name, int threads) {
     cudaFree(d);
 }
 int main() {
+    run<4>("cvt.rn.f16x2.f32", 128); run<5>("cvt.f32.f16", 128); run<6>("apply pair (2 elem)", 128);
+    run<4>("cvt.rn.f16x2.f32", 256); run<5>("cvt.f32.f16", 256); run<6>("apply pair (2 elem)", 256);
+    run<4>("cvt.rn.f16x2.f32", 1024); run<5>("cvt.f32.f16", 1024); run<6>("apply pair (2 elem)", 1024);
     for (int t : {128, 1024}) {
         if (t == 128) { run<0>("tanh.approx.f32", 128); run<1>("tanh.approx.f16x2", 128); run<2>("ex2.approx.ftz.f32", 128); run<3>("fma.rn.f32", 128); }
         else { run<0>("tanh.approx.f32", 1024); run<1>("tanh.approx.f16x2", 1024); run<2>("ex2.approx.ftz.f32", 1024); run<3>("fma.rn.f32", 1024); }
