@@ -199,10 +199,9 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                         const uint32_t gi = g + i;
                         mbar_wait(bar_tempty + 8 * (gi % NACC), (gi / NACC) & 1);
                     }
-                    if (RES1 && i >= 1 && i <= L) {  // input row i is the centre row of output row i-1 of the fused 1x1 conv
-                        const uint32_t gr = g + i - 1;
-                        mbar_wait(bar_xempty + 8 * (gr % NRESD), (gr / NRESD) & 1);
-                    }
+                    // (the fused 1x1 conv's short accumulator ring is NOT waited for here: with only 2 slots that would tie
+                    // the load of row i to the epilogue's progress three rows back -- measured 5300 instead of 2750 cycles per
+                    // row; the issuer checks that ring itself, right before the residual MMAs)
 #pragma unroll
                     for (int ch = 0; ch < CH; ++ch) {  // one ring slot per (row, 64-channel chunk)
                         mbar_wait(bar_rempty + 8 * slot, par ^ 1);
@@ -300,6 +299,10 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                             if (RES1 && i >= 1 && i <= L) {  // fused 1x1 residual conv: centre tap, its own accumulator ring
                                 const uint32_t gr = g + i - 1;
                                 const uint32_t dR = tmem_base + (NACC + gr % NRESD) * BN;
+                                if (ch == 0) {  // slot drained and re-zeroed?  (two rows of MMAs ago: practically never blocks)
+                                    mbar_wait(bar_xempty + 8 * (gr % NRESD), (gr / NRESD) & 1);
+                                    tc_fence_after();
+                                }
 #pragma unroll
                                 for (int k = 0; k < 4; ++k)
                                     umma_f16_ss(dR, desc_hi | (alo_base + 8 + 2 * k), desc_hi | ((wres1 >> 4) + ch * WB16 + 2 * k), idesc0 + NB, 1u);

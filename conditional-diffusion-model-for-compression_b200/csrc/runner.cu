@@ -1602,6 +1602,30 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
         cb.cpg = cout / 32;
         cb.gn_acc = reinterpret_cast<gn_sum_t*>(gn_sums);
     }
+    ConvW cwr;  // tools (CDC_TEST_CONV_RES=1): time the conv with a 1x1 residual conv of the same input riding along
+    void* res_buf = nullptr;
+    if (getenv("CDC_TEST_CONV_RES") && gn_sums && ksize == 3 && mode == MODE_S1) {
+        // its weights: the centre tap of the 3x3 weights is as good as any for timing -- w_oihw[o][i][1][1]
+        std::vector<float> w33(static_cast<size_t>(cout) * cin * 9), w11(static_cast<size_t>(cout) * cin);
+        CK(cudaMemcpy(w33.data(), w_oihw, w33.size() * 4, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < w11.size(); ++i) w11[i] = w33[i * 9 + 4];
+        float* w11d = nullptr;
+        CK(cudaMalloc(&w11d, w11.size() * 4));
+        CK(cudaMemcpy(w11d, w11.data(), w11.size() * 4, cudaMemcpyHostToDevice));
+        int rr = make_conv_w(ctx, ar, w11d, bias, cout, cin, 1, cin, cin, false, &cwr, S(s), false);
+        cudaStreamSynchronize(S(s));
+        cudaFree(w11d);
+        if (rr == 0 && cudaMalloc(&res_buf, static_cast<size_t>(B) * H * W * cwr.n_pad * 2) == cudaSuccess) {
+            cb.res_w = &cwr;
+            cb.res_out.p = static_cast<act_t*>(res_buf);
+            cb.res_out.C = cwr.n_pad;
+            cb.res_out.H = H;
+            cb.res_out.W = W;
+            KfGeom kgr;
+            if (!(conv_uses_kf(cb, B, prop.multiProcessorCount, &kgr) && kgr.res)) cb.res_w = nullptr;
+        }
+        printf("test_conv: 1x1 residual conv fused: %s\n", cb.res_w ? "yes" : "no");
+    }
     void* in_gn = nullptr;  // tools (CDC_TEST_CONV_APPLY=1): time the conv with the input GroupNorm fused -- unit statistics
     if (getenv("CDC_TEST_CONV_APPLY") && gn_sums && c1 == 0 && cout == cin) {
         const int cpg_in = cin / 32;
@@ -1717,6 +1741,7 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
     }
     ar.release();
     if (in_gn) cudaFree(in_gn);
+    if (res_buf) cudaFree(res_buf);
     if (ce != cudaSuccess) {
         g_create_err = std::string("test_conv: ") + cudaGetErrorString(ce);
         return CDC_ERR_CUDA;
