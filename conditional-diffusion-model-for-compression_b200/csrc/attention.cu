@@ -46,8 +46,8 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const act_t* qkv
     act_t(*Ks)[kAttBK][kAttPitch] = reinterpret_cast<act_t(*)[kAttBK][kAttPitch]>(kv0 + (grp * 4 + 0) * kAttTile);  // [buffer]
     act_t(*Vs)[kAttBK][kAttPitch] = reinterpret_cast<act_t(*)[kAttBK][kAttPitch]>(kv0 + (grp * 4 + 2) * kAttTile);
     const act_t* base = qkv + static_cast<size_t>(b) * N * ld + h * kAttD;
-    pdl_launch_dependents();
     pdl_wait();  // qkv is written by the preceding conv (it is only read through cp.async below)
+    pdl_launch_dependents();  // (after the wait: see launch.cuh)
 
     auto load_tile = [&](act_t (*dst)[kAttPitch], const act_t* src, int row0, int first, int nthr) {
         for (int i = first; i < 64 * 8; i += nthr) {
@@ -290,8 +290,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_holder;
-    pdl_launch_dependents();
     pdl_wait();
+    pdl_launch_dependents();  // (after the wait: see launch.cuh)
 
     if (warp == 0) {
         if (lane == 0) {

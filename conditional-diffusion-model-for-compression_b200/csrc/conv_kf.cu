@@ -173,8 +173,8 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
     const uint32_t tmem_base = *tmem_holder;
     if (kdbg) p.dbg[501] = clock64();
 
-    pdl_launch_dependents();
     pdl_wait();  // everything below touches activations written by the preceding kernels
+    pdl_launch_dependents();  // (after the wait: see launch.cuh)
 
     auto decode = [&](int u, int& b, int& seg, int& si, int& h0, int& L) {
         si = u % p.S;

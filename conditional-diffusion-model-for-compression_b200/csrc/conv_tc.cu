@@ -87,8 +87,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
-    pdl_launch_dependents();
     pdl_wait();  // the prologue above overlapped the preceding kernel's tail
+    pdl_launch_dependents();  // (after the wait: see launch.cuh)
 
     auto decode = [&](int tile, int& nt, int& ph, int& b, int& th, int& tw) {
         nt = tile % p.n_tiles;

@@ -18,8 +18,8 @@ constexpr int kStatsPix = 64;
 // kernel is resident before that data is final, so the non-coherent read-only path must not be used for them)
 __global__ void __launch_bounds__(256) gn_stats_kernel(const act_t* x, gn_sum_t* acc, int HW, int C) {
     __shared__ float s_sum[8][512], s_sq[8][512];  // [row-in-pass][channel] (C <= 512)
-    pdl_launch_dependents();
     pdl_wait();
+    pdl_launch_dependents();  // (after the wait: see launch.cuh)
     const int b = blockIdx.y, pt = blockIdx.x;
     const int vecs = C / 8;                 // uint4 per pixel
     const int rows = (256 / vecs) < 8 ? (256 / vecs) : 8;  // pixels per pass (smem rows)
@@ -144,7 +144,8 @@ template <bool SILU, bool RES>
 __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const uint4* x, const uint4* r, uint4* y, long long nvec, int vecs_per_pix,
                                                           long long vecs_per_img, const GnCoef g, int B) {
     extern __shared__ float2 s_mr[];  // [B][32] (mean, rstd)
-    pdl_wait();  // (no early trigger here: see pdl_launch_dependents)
+    pdl_wait();
+    pdl_launch_dependents();  // (after the wait: see launch.cuh)
     const long long stride = gridDim.x * 256LL;
     long long i = blockIdx.x * 256LL + threadIdx.x;
     const int cv = static_cast<int>(i % vecs_per_pix), cpg = g.C / 32;

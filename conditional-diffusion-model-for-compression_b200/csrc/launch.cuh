@@ -2,8 +2,10 @@
 // its prologue (barrier init, TMEM allocation, weight TMA loads) overlaps the tail of its predecessor; each kernel
 // executes griddepcontrol.wait (pdl_wait) before it touches memory written by earlier kernels, which keeps completion
 // transitive along the chain.  Measured on B200 inside the captured 17-step graph (bench.py, 768x512): plain stream
-// order 29.37 ms / image, PDL with early triggers in the convs 30.15 ms, early triggers everywhere 30.67 ms -- the
-// programmatic edges cost more than the overlap returns, so PDL is OFF unless CDC_PDL=1 is set in the environment.
+// order 29.37 ms / image, PDL with early triggers in the convs 30.15 ms, early triggers everywhere 30.67 ms (a dependent
+// grid that is triggered before its predecessor's CTAs are all resident takes their SMs).  The kernels now trigger right
+// AFTER their own griddepcontrol.wait (every CTA of the kernel is resident by then): 25.52 ms with PDL against 25.47 ms
+// without -- no loss, but no gain either, so PDL stays OFF unless CDC_PDL=1 is set in the environment.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdlib.h>
