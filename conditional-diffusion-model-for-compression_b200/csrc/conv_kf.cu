@@ -43,7 +43,8 @@ namespace cdc {
 constexpr int kKfRowBytes = 17 * 1024;  // 130 pixels x 128 B = 16640, padded to a 1024 B multiple
 constexpr int kKfRowTx = 130 * 128;
 constexpr int kKfAccMax = 16;           // accumulator-ring barriers (the ring holds min(16, 512 / BN) output rows)
-constexpr int kKfAux = 1024 + 2 * 8 * 16 * 2 * 4 + 2048 + 256;  // barriers + TMEM holder + bias, stats scratch, APPLY coefficients
+constexpr int kKfAux = 1024 + 2 * 8 * 16 * 2 * 4 + 2048 + 256 + 128;  // barriers + TMEM holder + bias, stats scratch, APPLY coefficients, ring barriers
+constexpr int kKfMaxSlots = 8;          // input ring: at most 8 slots (4 unless the stride-2 mode has room for more)
 #ifndef CDC_KF_XF_WARPS
 #define CDC_KF_XF_WARPS 6
 #endif
@@ -72,8 +73,14 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
     // MODE 0: 3x3 conv.  MODE 1: nearest-x2 upsample + 3x3 conv as four 2x2 convs on the low-resolution input, one
     // per output parity (py, px) with pre-summed weights (repack_weight_up2_kernel): N tile nt = (channel tile, parity),
     // taps kh in {py, py+1}, kw in {px, px+1} of the 3x3 window, output pixel (2h + py, 2w + px).
+    // MODE 2: 3x3 conv with stride 2 (p.H, p.W = OUTPUT grid).  Every (input row, 64-channel chunk) lands as TWO tiles --
+    // E = its even pixels 2x and O = its odd pixels 2x+1, through two pixel-stride-2 tensor maps -- so that the three
+    // horizontal taps are again plain row offsets: kw=0 -> O[x-1], kw=1 -> E[x], kw=2 -> O[x].  Vertically, input row
+    // 2h-1 feeds output rows h (kh=0) and h-1 (kh=2) with ONE N = 2*BN MMA, input row 2h feeds row h (kh=1) alone.
     constexpr int NKH = MODE == 1 ? 2 : 3, NKW = MODE == 1 ? 2 : 3;
-    static_assert(MODE == 0 || (!STAGE && EPI == EPI_STORE && !XK16), "UP2 mode: plain scattered store only");
+    constexpr int NSUB = MODE == 2 ? 2 : 1;  // ring slots per (row, chunk)
+    static_assert(MODE != 1 || (!STAGE && EPI == EPI_STORE && !XK16), "UP2 mode: plain scattered store only");
+    static_assert(MODE != 2 || (EPI == EPI_STORE && !XK16 && !RES1 && !APPLY), "stride-2 mode: plain conv + store");
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
@@ -86,8 +93,8 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
     const uint32_t stage = wres1 + (RES1 ? CH * WB : 0);
     const uint32_t aux = stage + STAGE_BYTES;
     uint8_t* aux_gen = gen + (aux - base);
-    // barriers: row_full[4] row_empty[4] tfull[16] tempty[16] wres xfull[8] xempty[8] (x = fused residual conv)
-    const uint32_t bar_rfull = aux, bar_rempty = aux + 32, bar_tfull = aux + 64, bar_tempty = aux + 192, bar_wres = aux + 320;
+    // barriers: tfull[16] tempty[16] wres xfull[8] xempty[8] (x = fused residual conv) ... row_full[8] row_empty[8]
+    const uint32_t bar_rfull = aux + 5376, bar_rempty = aux + 5376 + 64, bar_tfull = aux + 64, bar_tempty = aux + 192, bar_wres = aux + 320;
     const uint32_t bar_xfull = aux + 328, bar_xempty = aux + 392;
     const uint32_t bar_rready = aux + 464;  // APPLY: [4] row chunk transformed (one arrive per transform warp)
     const uint32_t bar_afull = APPLY ? bar_rready : bar_rfull;  // what the MMA issuer waits for
@@ -124,10 +131,10 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
         if (STAGE) prefetch_tensormap(&p.omap);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < 4; ++s) {
+        for (int s = 0; s < kKfMaxSlots; ++s) {
             mbar_init(bar_rfull + 8 * s, 1);
             mbar_init(bar_rempty + 8 * s, 1);
-            if (APPLY) mbar_init(bar_rready + 8 * s, kKfXfThreads / 32);
+            if (APPLY && s < 4) mbar_init(bar_rready + 8 * s, kKfXfThreads / 32);
         }
         for (int s = 0; s < static_cast<int>(NACC); ++s) {
             mbar_init(bar_tfull + 8 * s, 1);
@@ -145,7 +152,13 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
         mbar_expect_tx(bar_wres, (NKH * NKW + (RES1 ? 1 : 0)) * CH * WB);
         if constexpr (RES1)
             for (int ch = 0; ch < CH; ++ch) tma_load_2d(wres1 + ch * WB, &p.rmap, bar_wres, ch * 64, cot * BN);
-        if constexpr (MODE == 0) {
+        if constexpr (MODE == 2) {  // block order per (kw, chunk): kh = 2, 0 (the pair an odd input row feeds), then kh = 1
+            for (int kh = 0; kh < 3; ++kh)
+                for (int kw = 0; kw < 3; ++kw)
+                    for (int ch = 0; ch < CH; ++ch)
+                        tma_load_2d(wbase + ((kw * CH + ch) * 3 + (kh == 2 ? 0 : kh == 0 ? 1 : 2)) * WB, &p.wmap, bar_wres,
+                                    ((kh * 3 + kw) * CH + ch) * 64, cot * BN);
+        } else if constexpr (MODE == 0) {
             for (int kh = 0; kh < 3; ++kh)
                 for (int kw = 0; kw < 3; ++kw)
                     for (int ch = 0; ch < CH; ++ch)
@@ -194,25 +207,34 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                 int b, seg, si, h0, L;
                 decode(u, b, seg, si, h0, L);
                 const int w0 = seg * 128 - 1;
-                for (int i = 0; i < L + 2; ++i) {
-                    if (i < L) {  // input row i opens the accumulator of output row i: drained and re-zeroed?
-                        const uint32_t gi = g + i;
+                const int nrows = MODE == 2 ? 2 * L + 1 : L + 2;  // input rows of the strip
+                for (int i = 0; i < nrows; ++i) {
+                    // input row i opens the accumulator of output row i (stride 2: of row i / 2, i even): drained and re-zeroed?
+                    if (MODE == 2 ? ((i & 1) == 0 && (i >> 1) < L) : i < L) {
+                        const uint32_t gi = g + (MODE == 2 ? (i >> 1) : i);
                         mbar_wait(bar_tempty + 8 * (gi % NACC), (gi / NACC) & 1);
                     }
                     // (the fused 1x1 conv's short accumulator ring is NOT waited for here: with only 2 slots that would tie
                     // the load of row i to the epilogue's progress three rows back -- measured 5300 instead of 2750 cycles per
                     // row; the issuer checks that ring itself, right before the residual MMAs)
 #pragma unroll
-                    for (int ch = 0; ch < CH; ++ch) {  // one ring slot per (row, 64-channel chunk)
-                        mbar_wait(bar_rempty + 8 * slot, par ^ 1);
-                        const uint32_t full = bar_rfull + 8 * slot;
-                        mbar_expect_tx(full, kKfRowTx);
-                        const bool s1 = ch >= p.chunks0;
-                        tma_load_4d(ring + slot * kKfRowBytes, s1 ? &p.amap[1] : &p.amap[0], full, (s1 ? ch - p.chunks0 : ch) * 64, w0,
-                                    h0 - 1 + i, b);
-                        if (++slot == static_cast<uint32_t>(NS)) {
-                            slot = 0;
-                            par ^= 1;
+                    for (int ch = 0; ch < CH; ++ch) {  // one ring slot per (row, 64-channel chunk) (stride 2: two, E then O)
+#pragma unroll
+                        for (int sub = 0; sub < NSUB; ++sub) {
+                            mbar_wait(bar_rempty + 8 * slot, par ^ 1);
+                            const uint32_t full = bar_rfull + 8 * slot;
+                            mbar_expect_tx(full, kKfRowTx);
+                            const bool s1 = ch >= p.chunks0;
+                            const int cc = (s1 ? ch - p.chunks0 : ch) * 64;
+                            if constexpr (MODE == 2)  // E tile: even pixels from output column w0+1; O tile: odd pixels from one earlier
+                                tma_load_4d(ring + slot * kKfRowBytes, &p.amap[(s1 ? 2 : 0) + sub], full, cc, sub ? w0 : w0 + 1,
+                                            2 * h0 - 1 + i, b);
+                            else
+                                tma_load_4d(ring + slot * kKfRowBytes, s1 ? &p.amap[1] : &p.amap[0], full, cc, w0, h0 - 1 + i, b);
+                            if (++slot == static_cast<uint32_t>(NS)) {
+                                slot = 0;
+                                par ^= 1;
+                            }
                         }
                     }
                 }
@@ -229,7 +251,8 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
         {
             constexpr uint32_t idesc0 = make_idesc_f16(128, 0);
             constexpr uint32_t NB = static_cast<uint32_t>(BN >> 3) << 17;  // idesc increment per window slot
-            constexpr int T = 4 * NKW, TH = T / 2;  // K steps per (input row, chunk); position of the wait for the next chunk
+            constexpr int T = 4 * NKW;  // K steps per (input row, chunk); the wait for the next chunk sits after half of them
+            // (stride 2: the E slot carries kw = 1 (4 K steps), the O slot kw = 0 and kw = 2 (8 K steps))
             const uint64_t desc_hi = make_sw128_desc(0) & 0xFFFFFFFF00000000ull;
             const uint32_t wlo = wbase >> 4;
             uint32_t rslot = 0, rpar = 0;
@@ -243,22 +266,29 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                 mbar_wait(bar_afull + 8 * rslot, rpar);  // first chunk of the strip
                 tc_fence_after();
                 if (kdbg && u == cta) p.dbg[504] = clock64();
-                for (int i = 0; i < L + 2; ++i) {
+                const int nrows = MODE == 2 ? 2 * L + 1 : L + 2;
+                for (int i = 0; i < nrows; ++i) {
                     // input row i feeds output rows j = i - py - e, e = 0 .. NKH-1 (kh = py + e); clipped to the strip
-                    const int jtop = i - py;
-                    const int jlo = jtop - (NKH - 1) > 0 ? jtop - (NKH - 1) : 0;
+                    // (stride 2: even i -> rows i/2 - 1 (kh = 2) and i/2 (kh = 0); odd i -> row i/2 (kh = 1))
+                    const int jtop = MODE == 2 ? (i >> 1) : i - py;
+                    const int jspan = MODE == 2 ? ((i & 1) ? 0 : 1) : NKH - 1;
+                    const int jlo = jtop - jspan > 0 ? jtop - jspan : 0;
                     const int jhi = jtop < L ? jtop : L - 1;
                     const uint32_t cnt = jhi >= jlo ? static_cast<uint32_t>(jhi - jlo + 1) : 0u;  // 0: nothing to issue (UP2 edge rows)
                     const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && u == cta && i < 40 && lane == 0;
                     if (dbg) p.dbg[i * 4 + 0] = clock64();
                     const uint32_t slo = (g + jlo) % NACC;
-                    const uint32_t khp = static_cast<uint32_t>((NKH - 1) - (jtop - jlo));  // reversed kh of the first window slot
+                    // weight block of the first window slot (reversed kh; stride 2: blocks are ordered kh = 2, 0, 1)
+                    const uint32_t khp = MODE == 2 ? ((i & 1) ? 2u : static_cast<uint32_t>(1 - (jtop - jlo)))
+                                                   : static_cast<uint32_t>((NKH - 1) - (jtop - jlo));
                     const uint32_t nA = cnt < NACC - slo ? cnt : NACC - slo, nB = cnt - nA;
                     const uint32_t dA = tmem_base + slo * BN, dB = tmem_base;
                     const uint32_t bA = khp * WB16, bB = (khp + nA) * WB16;
                     const uint32_t iA = idesc0 + nA * NB, iB = idesc0 + nB * NB;
 #pragma unroll
-                    for (int ch = 0; ch < CH; ++ch) {
+                    for (int pc = 0; pc < CH * NSUB; ++pc) {
+                        const int ch = pc / NSUB, sub = pc % NSUB;  // sub (stride 2 only): 0 = E tile, 1 = O tile
+                        constexpr int TT = MODE == 2 ? 8 : T;       // K steps of the longest slot (the E slot issues the first 4 only)
                         const uint32_t alo_base = (ring + rslot * kKfRowBytes) >> 4;
                         // K steps t = kw * 4 + k in [t0, t1); a wrapped window issues its two pieces back to back
                         // per half (alternating MMA shapes costs ~30 cycles per switch)
@@ -266,18 +296,25 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                             constexpr int t0 = decltype(t0c)::value, t1 = decltype(t1c)::value;
 #pragma unroll
                             for (int t = t0; t < t1; ++t) {
-                                const int k = t & 3, kw = t >> 2;  // kw: index into the NKW horizontal taps
+                                const int k = t & 3;
+                                // kw: horizontal tap; ashift: its pixel offset inside the slot's tile
+                                const int kw = MODE == 2 ? (sub == 0 ? 1 : (t >> 2) * 2) : t >> 2;
+                                const int ashift = MODE == 2 ? (sub == 1 && (t >> 2) == 1 ? 1 : 0) : kw + px;
+                                if (MODE == 2 && sub == 0 && t >= 4) continue;  // E slot: kw = 1 only
                                 if (XK16 && ch == 0 && k != 0) continue;  // stem: chunk 0 = x_t, channels 16..63 are zero
-                                const uint32_t alo = alo_base + (kw + px) * 8 + 2 * k;
+                                const uint32_t alo = alo_base + ashift * 8 + 2 * k;
                                 const uint32_t blo = wlo + ((kw * CH + ch) * NKH) * WB16 + 2 * k;
                                 umma_f16_ss(dA, desc_hi | alo, desc_hi | (blo + bA), iA, 1u);
                             }
                             if (nB != 0) {
 #pragma unroll
                                 for (int t = t0; t < t1; ++t) {
-                                    const int k = t & 3, kw = t >> 2;
+                                    const int k = t & 3;
+                                    const int kw = MODE == 2 ? (sub == 0 ? 1 : (t >> 2) * 2) : t >> 2;
+                                    const int ashift = MODE == 2 ? (sub == 1 && (t >> 2) == 1 ? 1 : 0) : kw + px;
+                                    if (MODE == 2 && sub == 0 && t >= 4) continue;
                                     if (XK16 && ch == 0 && k != 0) continue;
-                                    const uint32_t alo = alo_base + (kw + px) * 8 + 2 * k;
+                                    const uint32_t alo = alo_base + ashift * 8 + 2 * k;
                                     const uint32_t blo = wlo + ((kw * CH + ch) * NKH) * WB16 + 2 * k;
                                     umma_f16_ss(dB, desc_hi | alo, desc_hi | (blo + bB), iB, 1u);
                                 }
@@ -285,17 +322,18 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                         };
                         // probe the next chunk's barrier now, use the answer after the first half of the MMAs
                         const uint32_t nslot = rslot + 1 == static_cast<uint32_t>(NS) ? 0u : rslot + 1;
-                        const bool more = ch + 1 < CH || i + 1 < L + 2;  // (a new row's first chunk also certifies its accumulator)
+                        const bool more = pc + 1 < CH * NSUB || i + 1 < nrows;  // (a new row's first chunk also certifies its accumulator)
                         const uint32_t npar = nslot == 0 ? rpar ^ 1 : rpar;
                         const uint32_t ready = more ? mbar_test_wait(bar_afull + 8 * nslot, npar) : 1u;
-                        if (cnt != 0 && elect_one_sync()) steps(std::integral_constant<int, 0>{}, std::integral_constant<int, TH>{});
+                        constexpr int TTH = TT / 2;
+                        if (cnt != 0 && elect_one_sync()) steps(std::integral_constant<int, 0>{}, std::integral_constant<int, TTH>{});
                         __syncwarp();
-                        if (dbg && ch == 0) p.dbg[i * 4 + 1] = clock64();
+                        if (dbg && pc == 0) p.dbg[i * 4 + 1] = clock64();
                         if (!ready) mbar_wait(bar_afull + 8 * nslot, npar);
                         if (more) tc_fence_after();
-                        if (dbg && ch == 0) p.dbg[i * 4 + 2] = clock64();
+                        if (dbg && pc == 0) p.dbg[i * 4 + 2] = clock64();
                         if (elect_one_sync()) {
-                            if (cnt != 0) steps(std::integral_constant<int, TH>{}, std::integral_constant<int, T>{});
+                            if (cnt != 0) steps(std::integral_constant<int, TTH>{}, std::integral_constant<int, TT>{});
                             if (RES1 && i >= 1 && i <= L) {  // fused 1x1 residual conv: centre tap, its own accumulator ring
                                 const uint32_t gr = g + i - 1;
                                 const uint32_t dR = tmem_base + (NACC + gr % NRESD) * BN;
@@ -309,7 +347,11 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                                 if (ch == CH - 1) umma_commit(bar_xfull + 8 * (gr % NRESD));
                             }
                             umma_commit(bar_rempty + 8 * rslot);  // chunk consumed
-                            if (ch == CH - 1 && i >= 2) umma_commit(bar_tfull + 8 * ((g + i - 2) % NACC));  // output row i-2 complete
+                            if constexpr (MODE == 2) {  // output row i/2 - 1 is complete after the odd-numbered input row 2h+1 (even i)
+                                if (pc == CH * NSUB - 1 && (i & 1) == 0 && i >= 2) umma_commit(bar_tfull + 8 * ((g + (i >> 1) - 1) % NACC));
+                            } else if (ch == CH - 1 && i >= 2) {
+                                umma_commit(bar_tfull + 8 * ((g + i - 2) % NACC));  // output row i-2 complete
+                            }
                         }
                         __syncwarp();
                         rslot = nslot;
@@ -688,7 +730,9 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
     KF_CASE(64, 2, EPI_STATS, 1, true, false, 0, false, true)     \
     KF_CASE(64, 4, EPI_STATS, 2, false, false, 0, false, true)    \
     KF_CASE(48, 6, EPI_STATS, 3, false, false, 0, false, true)    \
-    KF_CASE(32, 8, EPI_STATS, 4, false, false, 0, false, true)
+    KF_CASE(32, 8, EPI_STATS, 4, false, false, 0, false, true)      \
+    KF_CASE(64, 1, EPI_STORE, 1, true, false, 2, false, false)      \
+    KF_CASE(64, 1, EPI_STORE, 2, false, false, 2, false, false)
 
 int kf_smem_bytes(int bn, int CH, int NS, bool staged, int mode, bool res) {
     return 1024 + NS * kKfRowBytes + ((mode == 1 ? 4 : 9) + (res ? 1 : 0)) * CH * bn * 128 + (staged ? 2 * 128 * bn * 2 : 0) + kKfAux;
@@ -698,7 +742,7 @@ bool kf_plan(int bn, int CH, int mode, bool res, int* NS, bool* staged) {
     const int limit = 227 * 1024;
     for (int st = (mode == 1 || res) ? 0 : 1; st >= 0; --st) {  // NS = ring slots of one (row, chunk) each
         if (st && bn != 64) continue;
-        for (int ns = 4; ns >= 3; --ns)
+        for (int ns = mode == 2 ? kKfMaxSlots : 4; ns >= (mode == 2 ? 4 : 3); --ns)  // (stride 2: two slots per (row, chunk))
             if (kf_smem_bytes(bn, CH, ns, st != 0, mode, res) <= limit) {
                 *NS = ns;
                 *staged = st != 0;

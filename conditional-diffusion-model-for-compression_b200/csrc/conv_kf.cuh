@@ -5,7 +5,7 @@
 namespace cdc {
 
 struct alignas(64) KfParams {
-    CUtensorMap amap[2];  // activation sources, box {64 ch, 130 px, 1 row, 1 image}
+    CUtensorMap amap[4];  // activation sources, box {64 ch, 130 px, 1 row, 1 image}; mode 2: (even, odd)-pixel views per source
     CUtensorMap wmap;     // weights [n_pad][9 * CH * 64] K-major, box {64, BN}
     CUtensorMap omap;     // output, box {BN ch, 128 px, 1 row, 1 image} (staged TMA store only)
     CUtensorMap rmap;     // fused 1x1 residual conv: its weights [n_pad][CH * 64] K-major, box {64, BN}
@@ -39,7 +39,8 @@ struct alignas(64) KfParams {
     long long* dbg;       // optional: issuer / epilogue timeline of CTA 0 (clock64 stamps), tools only
 };
 
-// mode 0: 3x3 conv; mode 1: nearest-x2 upsample + 3x3 conv (four parity 2x2 convs on the low-resolution input)
+// mode 0: 3x3 conv; mode 1: nearest-x2 upsample + 3x3 conv (four parity 2x2 convs on the low-resolution input);
+// mode 2: 3x3 conv with stride 2 (H, W of KfParams are the OUTPUT grid)
 // res: the ResBlock's 1x1 residual conv rides along (its weights are resident too, its accumulators share TMEM)
 // apply: GroupNorm + SiLU of the input applied in shared memory (see in_acc)
 bool kf_inst_ok(int bn, int cpg, int epi, int CH, int mode, bool res, bool apply = false);

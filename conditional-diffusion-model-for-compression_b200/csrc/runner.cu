@@ -221,10 +221,13 @@ static bool kf_disabled() {
     return v == 1;
 }
 static bool conv_uses_kf(const ConvBuild& cb, int B, int num_sms, KfGeom* g) {
-    if (kf_disabled() || cb.mode == MODE_S2 || cb.ksize != 3 || cb.force_bn != 0 || cb.residual) return false;
-    g->mode = cb.mode == MODE_UP2 ? 1 : 0;
+    if (kf_disabled() || cb.ksize != 3 || cb.force_bn != 0 || cb.residual) return false;
+    g->mode = cb.mode == MODE_UP2 ? 1 : cb.mode == MODE_S2 ? 2 : 0;
     if (g->mode == 1 && (!cb.w->up2 || cb.epi != EPI_STORE)) return false;
-    int gw = cb.srcs[0].W, gh = cb.srcs[0].H;
+    if (g->mode == 2 && (cb.epi != EPI_STORE || cb.res_w || cb.in_acc || ((cb.srcs[0].W | cb.srcs[0].H) & 1))) return false;
+    // strip geometry lives on the grid the kernel walks: the input grid (mode 1 writes 2x2 outputs per pixel), for the
+    // stride-2 mode the OUTPUT grid
+    int gw = cb.srcs[0].W >> (g->mode == 2 ? 1 : 0), gh = cb.srcs[0].H >> (g->mode == 2 ? 1 : 0);
     g->tr = false;
     g->nseg = (gw + 127) / 128;
     // segments are 128 pixels wide: too much of the tile would be padding (measured break-even against conv_tc.cu:
@@ -321,6 +324,14 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
             memset(kp.get(), 0, sizeof(KfParams));
             for (size_t s = 0; s < cb.srcs.size(); ++s) {
                 const Act& a = cb.srcs[s];
+                if (kg.mode == 2) {  // even-pixel and odd-pixel views of the source: pixel stride 2, W/2 pixels each
+                    for (int eo = 0; eo < 2; ++eo)
+                        if (encode_act_map(&kp->amap[2 * s + eo], a.p + static_cast<size_t>(eo) * a.C, a.C, a.W / 2, a.H, B,
+                                           2 * static_cast<size_t>(a.C), static_cast<size_t>(a.W) * a.C,
+                                           static_cast<size_t>(a.H) * a.W * a.C, 130, 1))
+                            return fail("cuTensorMapEncodeTiled (kf stride-2 activation) failed");
+                    continue;
+                }
                 const int rc_map = kg.tr ? encode_act_map(&kp->amap[s], a.p, a.C, a.H, a.W, B, static_cast<size_t>(a.W) * a.C,
                                                           static_cast<size_t>(a.C), static_cast<size_t>(a.H) * a.W * a.C, 130, 1)
                                          : encode_act_map(&kp->amap[s], a.p, a.C, a.W, a.H, B, static_cast<size_t>(a.C),
@@ -368,7 +379,7 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
             op->name = cb.name;
             const double Mout = Ms * (kg.mode == 1 ? 4.0 : 1.0);  // algorithmic: the 3x3 conv on the upsampled grid
             op->flops = 2.0 * Mout * w.n_true * (9.0 * w.c_true);
-            op->bytes = 2.0 * (Ms * w.c_true + Mout * w.n_true + 9.0 * w.c_true * w.n_true);
+            op->bytes = 2.0 * (Ms * (kg.mode == 2 ? 4.0 : 1.0) * w.c_true + Mout * w.n_true + 9.0 * w.c_true * w.n_true);
             if (kg.apply) {  // the GroupNorm apply pass no longer touches HBM; its arithmetic rides along
                 op->name += "+gn_in";
             }

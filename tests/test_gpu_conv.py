@@ -115,6 +115,16 @@ CONV_CASES = [
     ("kf_up2_c256_n192", 1, 16, 96, [256], 192, 3, 2, 0),
     ("kf_up2_c256_n256_w48", 1, 10, 48, [256], 256, 3, 2, 0),
     ("kf_up2_one_row", 1, 1, 128, [128], 64, 3, 2, 0),
+    # stride-2 conv3x3 through the kh-fused kernel (even / odd pixel tiles, two-row windows): output widths 128..384,
+    # ragged last segment, one output row, accumulator-ring wrap, several units per CTA, two N tiles, dual source
+    ("kf_s2_c64_n64_512x768", 1, 512, 768, [64], 64, 3, 1, 0),
+    ("kf_s2_c64_n64_ragged_w400", 2, 36, 400, [64], 64, 3, 1, 0),
+    ("kf_s2_one_output_row", 1, 2, 256, [64], 64, 3, 1, 0),
+    ("kf_s2_long_strips", 6, 80, 512, [64], 64, 3, 1, 0),
+    ("kf_s2_units_gt_ctas", 48, 8, 512, [64], 64, 3, 1, 0),
+    ("kf_s2_c128_n128_two_tiles", 1, 256, 384, [128], 128, 3, 1, 0),
+    ("kf_s2_dual_64+64_n64", 1, 64, 512, [64, 64], 64, 3, 1, 0),
+    ("kf_s2_c128_n64", 2, 20, 256, [128], 64, 3, 1, 0),
 ]
 
 

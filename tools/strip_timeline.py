@@ -1,5 +1,5 @@
 """Print the kh-fused conv kernel's issuer / epilogue timeline for one conv (CDC_STRIP_DEBUG=1) and time the launch with CUDA
-events (second, warm call).  Usage: strip_timeline.py [cin] [cout] [H] [W] [mode]   (mode 2 = nearest-x2 input)"""
+events (second, warm call).  Usage: strip_timeline.py [cin] [cout] [H] [W] [mode]   (mode 1 = stride 2, 2 = nearest-x2 input)"""
 import ctypes as C, os, sys
 os.environ.setdefault("CDC_STRIP_DEBUG", "1")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -10,7 +10,7 @@ a = [int(v) for v in sys.argv[1:]]
 cin, cout = (a + [64, 64])[:2] if len(a) < 2 else a[:2]
 H, W = (a[2], a[3]) if len(a) >= 4 else (512, 768)
 mode = a[4] if len(a) >= 5 else 0
-OH, OW = (2 * H, 2 * W) if mode == 2 else (H, W)
+OH, OW = (2 * H, 2 * W) if mode == 2 else (H // 2, W // 2) if mode == 1 else (H, W)
 B = 1
 dt = torch.float16 if L.cdc_act_dtype() == 1 else torch.bfloat16
 x = torch.randn(B, H, W, cin, device="cuda").to(dt)
@@ -20,5 +20,5 @@ out = torch.empty(B, OH, OW, (cout + 63) // 64 * 64, device="cuda", dtype=dt)
 st = torch.zeros(B, 32, 2, device="cuda", dtype=torch.int64)
 for it in range(2):
     rc = L.cdc_test_conv(0, C.c_void_p(x.data_ptr()), cin, None, 0, B, H, W, C.c_void_p(w.data_ptr()), C.c_void_p(b.data_ptr()),
-                         cout, 3, mode, 0, None, C.c_void_p(out.data_ptr()), None if mode == 2 else C.c_void_p(st.data_ptr()), None)
+                         cout, 3, mode, 0, None, C.c_void_p(out.data_ptr()), None if mode != 0 else C.c_void_p(st.data_ptr()), None)
     assert rc == 0, L.cdc_last_error(None)
