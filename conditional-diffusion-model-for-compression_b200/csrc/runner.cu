@@ -225,6 +225,10 @@ static bool conv_uses_kf(const ConvBuild& cb, int B, int num_sms, KfGeom* g) {
     g->mode = cb.mode == MODE_UP2 ? 1 : cb.mode == MODE_S2 ? 2 : 0;
     if (g->mode == 1 && (!cb.w->up2 || cb.epi != EPI_STORE)) return false;
     if (g->mode == 2 && (cb.epi != EPI_STORE || cb.res_w || cb.in_acc || ((cb.srcs[0].W | cb.srcs[0].H) & 1))) return false;
+    // CDC_KF_S2=0: stride-2 convs through the general kernel (A/B).  Only the 64- and 128-channel downsampling convs have
+    // kf instantiations: with 32-channel N tiles (192 / 256 channels, 64x96 outputs and below) the strip form measured
+    // 3 us per step SLOWER than the general kernel.
+    if (g->mode == 2 && getenv("CDC_KF_S2") && atoi(getenv("CDC_KF_S2")) == 0) return false;
     // strip geometry lives on the grid the kernel walks: the input grid (mode 1 writes 2x2 outputs per pixel), for the
     // stride-2 mode the OUTPUT grid
     int gw = cb.srcs[0].W >> (g->mode == 2 ? 1 : 0), gh = cb.srcs[0].H >> (g->mode == 2 ? 1 : 0);

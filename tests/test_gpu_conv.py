@@ -125,6 +125,8 @@ CONV_CASES = [
     ("kf_s2_c128_n128_two_tiles", 1, 256, 384, [128], 128, 3, 1, 0),
     ("kf_s2_dual_64+64_n64", 1, 64, 512, [64, 64], 64, 3, 1, 0),
     ("kf_s2_c128_n64", 2, 20, 256, [128], 64, 3, 1, 0),
+    ("s2_c192_n192_128x192", 1, 128, 192, [192], 192, 3, 1, 0),  # (general kernel: no kf instantiation for these)
+    ("s2_c256_n256_64x96", 2, 64, 96, [256], 256, 3, 1, 0),
 ]
 
 
