@@ -232,6 +232,8 @@ static bool conv_uses_kf(const ConvBuild& cb, int B, int num_sms, KfGeom* g) {
     // strip geometry lives on the grid the kernel walks: the input grid (mode 1 writes 2x2 outputs per pixel), for the
     // stride-2 mode the OUTPUT grid
     int gw = cb.srcs[0].W >> (g->mode == 2 ? 1 : 0), gh = cb.srcs[0].H >> (g->mode == 2 ? 1 : 0);
+    // CDC_KF_MIN_PIXELS=n: levels with fewer pixels per image go through the general kernel (A/B of the small levels)
+    if (getenv("CDC_KF_MIN_PIXELS") && static_cast<long>(gw) * gh < atol(getenv("CDC_KF_MIN_PIXELS"))) return false;
     g->tr = false;
     g->nseg = (gw + 127) / 128;
     // segments are 128 pixels wide: too much of the tile would be padding (measured break-even against conv_tc.cu:
