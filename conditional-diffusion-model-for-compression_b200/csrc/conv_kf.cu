@@ -370,8 +370,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
         const int row = q * 32 + lane;
         uint32_t g = 0, tile_ctr = 0, unit_ctr = 0;
         if constexpr (EPI == EPI_DDIM) {
-            // 3 real output channels: thread = pixel.  The two warp groups (half 0 / 1) take alternate output rows, and
-            // x_t of the row is fetched BEFORE the wait for its accumulator so the global-load latency is hidden.
+            // 3 real output channels: thread = pixel.  The two warp groups (half 0 / 1) take alternate output rows.
             const float b0 = bias_s[0], b1 = bias_s[1], b2 = bias_s[2];
             const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
             if (half == 0) {
@@ -387,13 +386,22 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                 decode(u, b, seg, si, h0, L);
                 const int gx = seg * 128 + row;
                 const bool valid = gx < p.W;
+                // x_t of this group's NEXT row is requested before the current row is processed: the accumulators are usually
+                // ready when the group gets to them, so a load issued right before the wait would have its latency exposed
+                float xt[3] = {0.f, 0.f, 0.f};
+                if (valid && half < L) {
+                    const size_t pix0 = (static_cast<size_t>(b) * p.H + (h0 + half)) * p.W + gx;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) xt[c] = p.x[pix0 * 3 + c];
+                }
                 for (int j = half; j < L; j += 2) {
                     const uint32_t gj = g + j, slot = gj % NACC;
                     const size_t pix = (static_cast<size_t>(b) * p.H + (h0 + j)) * p.W + gx;
-                    float xt[3] = {0.f, 0.f, 0.f};
-                    if (valid) {
+                    float xnext[3] = {0.f, 0.f, 0.f};
+                    if (valid && j + 2 < L) {
+                        const size_t pix2 = pix + 2 * static_cast<size_t>(p.W);
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) xt[c] = p.x[pix * 3 + c];
+                        for (int c = 0; c < 3; ++c) xnext[c] = p.x[pix2 * 3 + c];
                     }
                     mbar_wait(bar_tfull + 8 * slot, (gj / NACC) & 1);
                     tc_fence_after();
@@ -420,6 +428,8 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                         pk.y = pack_act2(xn[2], 0.0f);
                         *reinterpret_cast<uint2*>(p.xpad + pix * 64) = pk;
                     }
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) xt[c] = xnext[c];
                 }
                 g += L;
             }
@@ -738,10 +748,12 @@ int kf_smem_bytes(int bn, int CH, int NS, bool staged, int mode, bool res) {
     return 1024 + NS * kKfRowBytes + ((mode == 1 ? 4 : 9) + (res ? 1 : 0)) * CH * bn * 128 + (staged ? 2 * 128 * bn * 2 : 0) + kKfAux;
 }
 
-bool kf_plan(int bn, int CH, int mode, bool res, int* NS, bool* staged) {
+bool kf_plan(int bn, int CH, int mode, bool res, int epi, int* NS, bool* staged) {
     const int limit = 227 * 1024;
     for (int st = (mode == 1 || res) ? 0 : 1; st >= 0; --st) {  // NS = ring slots of one (row, chunk) each
         if (st && bn != 64) continue;
+        // (a single staging buffer + a 3-slot ring for the two-chunk store-only stem was tried: 35 -> 43 us)
+        (void)epi;
         for (int ns = mode == 2 ? kKfMaxSlots : 4; ns >= (mode == 2 ? 4 : 3); --ns)  // (stride 2: two slots per (row, chunk))
             if (kf_smem_bytes(bn, CH, ns, st != 0, mode, res) <= limit) {
                 *NS = ns;
@@ -755,7 +767,7 @@ bool kf_plan(int bn, int CH, int mode, bool res, int* NS, bool* staged) {
 bool kf_inst_ok(int bn, int cpg, int epi, int CH, int mode, bool res, bool apply) {
     int ns;
     bool st;
-    if (!kf_plan(bn, CH, mode, res, &ns, &st)) return false;
+    if (!kf_plan(bn, CH, mode, res, epi, &ns, &st)) return false;
 #define KF_CASE(BN_, CPG_, EPI_, CH_, ST_, X_, M_, R_, A_) \
     if (bn == BN_ && (EPI_ != EPI_STATS || cpg == CPG_) && epi == EPI_ && CH == CH_ && st == ST_ && mode == M_ && res == R_ && apply == A_) return true;
     KF_ALL_CASES()
@@ -778,7 +790,7 @@ cudaError_t launch_conv_kf(const KfParams& p, int bn, int cpg, int epi, int CH, 
                            cudaStream_t stream) {
     int ns;
     bool st;
-    if (!kf_plan(bn, CH, mode, res, &ns, &st) || ns != p.NS) return cudaErrorInvalidValue;
+    if (!kf_plan(bn, CH, mode, res, epi, &ns, &st) || ns != p.NS) return cudaErrorInvalidValue;
     const dim3 grid(p.n_tiles * p.G1), block(128 + kEpiThreads + (apply ? kKfXfExtra : 0));
     const size_t smem = kf_smem_bytes(bn, CH, ns, st, mode, res);
 #define KF_CASE(BN_, CPG_, EPI_, CH_, ST_, X_, M_, R_, A_)                                                                                \

@@ -44,7 +44,7 @@ struct alignas(64) KfParams {
 // res: the ResBlock's 1x1 residual conv rides along (its weights are resident too, its accumulators share TMEM)
 // apply: GroupNorm + SiLU of the input applied in shared memory (see in_acc)
 bool kf_inst_ok(int bn, int cpg, int epi, int CH, int mode, bool res, bool apply = false);
-bool kf_plan(int bn, int CH, int mode, bool res, int* NS, bool* staged);  // shared-memory plan; false if the weights do not fit
+bool kf_plan(int bn, int CH, int mode, bool res, int epi, int* NS, bool* staged);  // shared-memory plan; false if the weights do not fit
 int kf_smem_bytes(int bn, int CH, int NS, bool staged, int mode, bool res);
 cudaError_t configure_kf_kernels();
 cudaError_t launch_conv_kf(const KfParams& p, int bn, int cpg, int epi, int CH, bool xk16, int mode, bool res, bool apply,

@@ -253,8 +253,8 @@ static bool conv_uses_kf(const ConvBuild& cb, int B, int num_sms, KfGeom* g) {
         // with the ResBlock's 1x1 residual conv riding along when that fits, else without
         g->res = cb.res_w != nullptr && g->mode == 0 && cb.res_w->n_pad == cb.w->n_pad && cb.res_w->taps == 1 &&
                  cb.res_w->c_pad == ctot && kf_inst_ok(bn, cb.cpg, cb.epi, g->CH, g->mode, true) &&
-                 kf_plan(bn, g->CH, g->mode, true, &g->NS, &g->staged);
-        if (!g->res && (!kf_inst_ok(bn, cb.cpg, cb.epi, g->CH, g->mode, false) || !kf_plan(bn, g->CH, g->mode, false, &g->NS, &g->staged)))
+                 kf_plan(bn, g->CH, g->mode, true, cb.epi, &g->NS, &g->staged);
+        if (!g->res && (!kf_inst_ok(bn, cb.cpg, cb.epi, g->CH, g->mode, false) || !kf_plan(bn, g->CH, g->mode, false, cb.epi, &g->NS, &g->staged)))
             continue;
         g->bn = bn;
         break;
