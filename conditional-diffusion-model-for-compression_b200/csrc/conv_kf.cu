@@ -45,18 +45,20 @@ constexpr int kKfRowTx = 130 * 128;
 constexpr int kKfAccMax = 16;           // accumulator-ring barriers (the ring holds min(16, 512 / BN) output rows)
 constexpr int kKfAux = 1024 + 2 * 8 * 16 * 2 * 4 + 2048 + 256 + 128;  // barriers + TMEM holder + bias, stats scratch, APPLY coefficients, ring barriers
 constexpr int kKfMaxSlots = 8;          // input ring: at most 8 slots (4 unless the stride-2 mode has room for more)
-#ifndef CDC_KF_XF_WARPS
-#define CDC_KF_XF_WARPS 6
-#endif
-constexpr int kKfXfWarps = CDC_KF_XF_WARPS;  // APPLY: input-transform warps 2, 3, 12 .. 15 (512 threads: still 128 registers per thread)
-constexpr int kKfXfExtra = (kKfXfWarps - 2) * 32;  // threads beyond the 12 warps of the plain kernel
-constexpr int kKfXfThreads = kKfXfWarps * 32;
-constexpr int kKfXfPix = kKfXfThreads / 8;  // pixels per pass (8 threads = one pixel's 128 bytes)
+// APPLY: eight input-transform warps in TWO groups of four (one warp of each group per SM sub-partition); the groups take
+// alternate row chunks, so the load / arithmetic / store phases of consecutive chunks overlap and each group has two row
+// periods for its chunk.  640 threads launch with 96 registers each; setmaxnreg then moves registers from warpgroup 0
+// (producer / issuer: 48) and the transform warpgroups (64) to the two epilogue warpgroups (152): per sub-partition
+// 48 + 2 * 152 + 2 * 64 = 480 registers per lane = the CTA's launch allocation (the pool setmaxnreg draws from).
+constexpr int kKfXfGroups = 2;
+constexpr int kKfXfExtra = kKfXfGroups * 128;  // threads beyond the 12 warps of the plain kernel
+constexpr int kKfXfThreads = 128;              // per group
+constexpr int kKfXfPix = kKfXfThreads / 8;     // pixels per pass (8 threads = one pixel's 128 bytes)
 
 template <int BN, int CPG, int EPI, int CH, bool STAGE, bool XK16, int MODE, bool RES1, bool APPLY>
 __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 1) conv_kf_kernel(const __grid_constant__ KfParams p) {
     constexpr int kThreads = 128 + kEpiThreads + (APPLY ? kKfXfExtra : 0);
-    static_assert(!APPLY || (MODE == 0 && !XK16 && !RES1 && EPI == EPI_STATS), "input GroupNorm: the ResBlock's second conv");
+    static_assert(!APPLY || (MODE == 0 && !XK16 && !RES1 && EPI == EPI_STATS && CH == 1), "input GroupNorm: a 64-channel ResBlock's second conv");
     constexpr int WB = BN * 128;  // one (tap, chunk) weight block
     constexpr uint32_t WB16 = WB >> 4;
     // accumulator ring: as many output rows as TMEM holds (a window that wraps costs split MMAs: the longer the ring,
@@ -198,6 +200,9 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
         L = (si + 1) * p.H / p.S - h0;
     };
 
+    // (role dispatch by warpgroup first: with APPLY each warpgroup re-sizes its register allocation at the top of its branch)
+    if (warp < 4) {
+    if constexpr (APPLY) setmaxnreg_dec<48>();
     if (warp == 0) {
         // ------------------------------------------------------------ input-row producer
         if (lane == 0) {
@@ -363,8 +368,10 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
             }
             if (kdbg) p.dbg[505] = clock64();
         }
-    } else if (warp >= 4 && warp < 12) {
+    }
+    } else if (warp < 12) {
         // ------------------------------------------------------------ epilogue (8 warps)
+        if constexpr (APPLY) setmaxnreg_inc<152>();
         const int q = warp & 3;            // TMEM sub-partition: lanes 32q .. 32q+31
         const int half = (warp - 4) >> 2;  // column half of the accumulator
         const int row = q * 32 + lane;
@@ -595,109 +602,86 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
 
         }
     } else if constexpr (APPLY) {
-        // ------------------------------------------------------------ input transform (warps 2, 3, 12 .. 15)
+        // ------------------------------------------------------------ input transform (warps 12 .. 19, two groups)
         // y = SiLU(a*x + b) on every landed row chunk, in place, before the MMAs read it: the arithmetic of
         // gn_apply_kernel (gn_apply.cuh), bit for bit.  Thread = (16-byte channel vector c, pixel lane pl): its 8 channels'
-        // (a, b) pairs stay in registers across the pixels of a chunk.  Pixels and rows outside the image are left as
-        // TMA zero-filled them: the conv pads with zeros AFTER the activation.
-        const int xt = (warp < 4 ? warp - 2 : warp - 10) * 32 + lane;
+        // (a, b) pairs stay in registers.  Pixels and rows outside the image are left as TMA zero-filled them: the conv
+        // pads with zeros AFTER the activation.  Group g takes the chunks n = g, g + 2, ... of this CTA's sequence (ring
+        // slot n % NS: with an even ring a slot always belongs to the same group).
+        setmaxnreg_dec<64>();
+        const int grp = (warp - 12) >> 2;
+        const int xt = ((warp - 12) & 3) * 32 + lane;
         const int c = xt & 7, pl = xt >> 3;
         const uint32_t toff = static_cast<uint32_t>(pl) * 128u + (static_cast<uint32_t>(c ^ (pl & 7)) << 4);  // 128-byte swizzle
-        constexpr int NIT = (130 + kKfXfPix - 1) / kKfXfPix;
-        static_assert(kKfXfPix % 8 == 0, "a pixel's swizzle phase must not depend on the pass");
-        const int cpg_in = CH * 2;  // channels per group of the input (C_in / 32)
-        const double inv_n = kGnFixInv / (static_cast<double>(cpg_in) * p.H * p.W);
-        uint32_t slot = 0, par = 0;
+        constexpr int NIT = (130 + kKfXfPix - 1) / kKfXfPix;  // 9 passes of 16 pixels, done as 3 x 3 (64-register budget)
+        static_assert(kKfXfPix % 8 == 0 && NIT == 9, "a pixel's swizzle phase must not depend on the pass");
+        const double inv_n = kGnFixInv / (2.0 * p.H * p.W);  // C_in = 64: two channels per group
+        float2* coef_g = coef_s + grp * 64;                   // each group keeps its own table: no cross-group barrier
+        float2* mr_g = coef_s + 128 + grp * 32;              // (both inside the 2 KB coefficient area)
+        uint32_t n = 0;  // chunk counter of the CTA (all chunks; this group handles n % 2 == grp)
         int cur_b = -1;
         float4 cf[4];
-        const int xf_mode = p.dbg != nullptr ? static_cast<int>(p.dbg[511]) : 0;  // tools only (results are wrong for 4, 5)
-        const bool xf_copy_only = xf_mode == 3;                     // 3: rows through registers, no arithmetic
-        const bool xf_no_ld = xf_mode == 4, xf_no_st = xf_mode == 4 || xf_mode == 5;  // 4: arithmetic only; 5: loads + arithmetic
-        uint32_t xf_sink = 0;
         for (int u = cta; u < units; u += p.G1) {
             int b, seg, si, h0, L;
             decode(u, b, seg, si, h0, L);
             if (b != cur_b) {  // coefficient table of image b (once per CTA when the batch is 1)
-                named_bar_sync(3, kKfXfThreads);
-                if (xt < 32) mr_s[xt] = gn_mean_rstd(p.in_acc + (static_cast<size_t>(b) * 32 + xt) * 2, inv_n, p.in_eps);
-                named_bar_sync(3, kKfXfThreads);
-                for (int ci = xt; ci < CH * 64; ci += kKfXfThreads) {
-                    const float sc = p.in_film ? 1.0f + p.in_film[ci] : 1.0f, sh = p.in_film ? p.in_film[CH * 64 + ci] : 0.0f;
-                    const float2 ab = gn_fold(p.in_gamma[ci], p.in_beta[ci], sc, sh, mr_s[ci / cpg_in]);
-                    coef_s[ci] = make_float2(0.5f * ab.x, 0.5f * ab.y);  // (a/2, b/2): see silu_h
+                named_bar_sync(3 + grp, kKfXfThreads);
+                if (xt < 32) mr_g[xt] = gn_mean_rstd(p.in_acc + (static_cast<size_t>(b) * 32 + xt) * 2, inv_n, p.in_eps);
+                named_bar_sync(3 + grp, kKfXfThreads);
+                if (xt < 64) {
+                    const float sc = p.in_film ? 1.0f + p.in_film[xt] : 1.0f, sh = p.in_film ? p.in_film[64 + xt] : 0.0f;
+                    const float2 ab = gn_fold(p.in_gamma[xt], p.in_beta[xt], sc, sh, mr_g[xt / 2]);
+                    coef_g[xt] = make_float2(0.5f * ab.x, 0.5f * ab.y);  // (a/2, b/2): see silu_h
                 }
-                named_bar_sync(3, kKfXfThreads);
+                named_bar_sync(3 + grp, kKfXfThreads);
                 cur_b = b;
-                if constexpr (CH == 1) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) cf[j] = reinterpret_cast<const float4*>(coef_s + c * 8)[j];
-                }
+                for (int j = 0; j < 4; ++j) cf[j] = reinterpret_cast<const float4*>(coef_g + c * 8)[j];
             }
             const int w0 = seg * 128 - 1;
-            for (int i = 0; i < L + 2; ++i) {
+            for (int i = 0; i < L + 2; ++i, ++n) {
+                if ((n & 1u) != static_cast<uint32_t>(grp)) continue;
+                const uint32_t slot = n % static_cast<uint32_t>(NS), par = (n / static_cast<uint32_t>(NS)) & 1u;
                 const int h = h0 - 1 + i;
                 const bool row_in = h >= 0 && h < p.H;
+                mbar_wait(bar_rfull + 8 * slot, par);
+                if (row_in) {
+                    const uint32_t sb = ring + slot * kKfRowBytes + toff;
+                    // per half: all loads, all arithmetic, all stores, with distinct registers per vector -- a store that
+                    // has to leave the (busy) shared-memory queue before its registers are reused costs ~150 cycles
+                    auto part = [&](auto k0c, auto k1c) {
+                        constexpr int K0 = decltype(k0c)::value, K1 = decltype(k1c)::value;
+                        uint4 v[K1 - K0];
+                        bool ok[K1 - K0];
 #pragma unroll
-                for (int ch = 0; ch < CH; ++ch) {
-                    if constexpr (CH > 1) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) cf[j] = reinterpret_cast<const float4*>(coef_s + ch * 64 + c * 8)[j];
-                    }
-                    long long* xdbg = (p.dbg != nullptr && blockIdx.x == 0 && xt == 0 && u == cta && i * CH + ch < 48) ? p.dbg + 1024 + (i * CH + ch) * 8 : nullptr;
-                    if (xdbg) xdbg[0] = clock64();
-                    mbar_wait(bar_rfull + 8 * slot, par);
-                    if (xdbg) xdbg[1] = clock64();
-                    if (row_in) {
-                        const uint32_t sb = ring + slot * kKfRowBytes + toff;
-                        // three phases with distinct registers per vector: all loads, all arithmetic, all stores -- a store
-                        // that has to leave the (busy) shared-memory queue before its registers are reused costs ~150 cycles
-                        uint4 v[NIT];
-                        bool ok[NIT];
-#pragma unroll
-                        for (int k = 0; k < NIT; ++k) {
+                        for (int k = K0; k < K1; ++k) {
                             const int pxl = pl + kKfXfPix * k, gx = w0 + pxl;
-                            ok[k] = pxl < 130 && gx >= 0 && gx < p.W;
-                            v[k] = make_uint4(0u, 0u, 0u, 0u);
-                            if (xf_no_ld) v[k] = make_uint4(0x3c003800u + k, 0x34003a00u + lane, 0xb800bc00u, 0x3555b555u + slot);
-                            if (ok[k] && !xf_no_ld)
+                            ok[k - K0] = pxl < 130 && gx >= 0 && gx < p.W;
+                            v[k - K0] = make_uint4(0u, 0u, 0u, 0u);
+                            if (ok[k - K0])
                                 asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                                             : "=r"(v[k].x), "=r"(v[k].y), "=r"(v[k].z), "=r"(v[k].w)
+                                             : "=r"(v[k - K0].x), "=r"(v[k - K0].y), "=r"(v[k - K0].z), "=r"(v[k - K0].w)
                                              : "r"(sb + k * (kKfXfPix * 128)));
                         }
-                        if (xdbg) {  // (tools) loads returned: the clock read depends on every loaded vector
-                            uint32_t accx = 0;
 #pragma unroll
-                            for (int k = 0; k < NIT; ++k) accx ^= v[k].x ^ v[k].w;
-                            long long tl;
-                            asm volatile("mov.u64 %0, %%clock64;" : "=l"(tl) : "r"(accx));
-                            xdbg[3] = tl;
-                        }
-                        if (!xf_copy_only) {
+                        for (int k = 0; k < K1 - K0; ++k) v[k] = gn_apply_vec<true, false, true>(v[k], v[k], cf);
 #pragma unroll
-                            for (int k = 0; k < NIT; ++k) v[k] = gn_apply_vec<true, false, true>(v[k], v[k], cf);
-                        }
-#pragma unroll
-                        for (int k = 0; k < NIT; ++k) {
-                            if (xf_no_st) xf_sink ^= v[k].x ^ v[k].y ^ v[k].z ^ v[k].w;
-                            if (ok[k] && !xf_no_st)
-                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + k * (kKfXfPix * 128)), "r"(v[k].x), "r"(v[k].y), "r"(v[k].z),
-                                             "r"(v[k].w)
+                        for (int k = K0; k < K1; ++k) {
+                            if (ok[k - K0])
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + k * (kKfXfPix * 128)), "r"(v[k - K0].x),
+                                             "r"(v[k - K0].y), "r"(v[k - K0].z), "r"(v[k - K0].w)
                                              : "memory");
                         }
-                    }
-                    if (xdbg) xdbg[4] = clock64();
-                    fence_proxy_async_smem();  // generic-proxy writes -> visible to the MMA's async-proxy reads
-                    if (xdbg) xdbg[2] = clock64();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_rready + 8 * slot);
-                    if (++slot == static_cast<uint32_t>(NS)) {
-                        slot = 0;
-                        par ^= 1;
-                    }
+                    };
+                    part(std::integral_constant<int, 0>{}, std::integral_constant<int, 3>{});
+                    part(std::integral_constant<int, 3>{}, std::integral_constant<int, 6>{});
+                    part(std::integral_constant<int, 6>{}, std::integral_constant<int, 9>{});
                 }
+                fence_proxy_async_smem();  // generic-proxy writes -> visible to the MMA's async-proxy reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_rready + 8 * slot);
             }
         }
-        if (xf_sink == 0x12345679u && p.dbg != nullptr) p.dbg[2047] = 1;  // keeps the tools-only arithmetic alive
     }
 
     tc_fence_before();
@@ -738,9 +722,6 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
     KF_CASE(32, 4, EPI_STATS, 3, false, false, 0, true, false)    \
     KF_CASE(32, 4, EPI_STATS, 4, false, false, 0, true, false)    \
     KF_CASE(64, 2, EPI_STATS, 1, true, false, 0, false, true)     \
-    KF_CASE(64, 4, EPI_STATS, 2, false, false, 0, false, true)    \
-    KF_CASE(48, 6, EPI_STATS, 3, false, false, 0, false, true)    \
-    KF_CASE(32, 8, EPI_STATS, 4, false, false, 0, false, true)      \
     KF_CASE(64, 1, EPI_STORE, 1, true, false, 2, false, false)      \
     KF_CASE(64, 1, EPI_STORE, 2, false, false, 2, false, false)
 

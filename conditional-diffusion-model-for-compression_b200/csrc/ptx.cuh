@@ -287,6 +287,17 @@ __device__ __forceinline__ uint32_t elect_one_sync() {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Warpgroup register reallocation (all 4 warps of a warpgroup, converged): dec releases registers to the CTA's pool,
+// inc blocks until the pool holds enough.  Counts are multiples of 8 in [24, 256].  The pool is what the CTA was
+// launched with (threads x launch registers), not the SM's unallocated remainder.
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
