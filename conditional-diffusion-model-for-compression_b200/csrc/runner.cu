@@ -1671,7 +1671,6 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
         cudaMalloc(&dbg_dev, 2048 * sizeof(long long));
         std::vector<long long> init(2048, 0);
         if (atoi(getenv("CDC_STRIP_DEBUG")) == 2) init[511] = 1;
-        if (atoi(getenv("CDC_STRIP_DEBUG")) >= 3) init[511] = atoi(getenv("CDC_STRIP_DEBUG"));  // APPLY transform variants (conv_kf.cu xf_mode)
         cudaMemcpy(dbg_dev, init.data(), 2048 * sizeof(long long), cudaMemcpyHostToDevice);
         cb.dbg = dbg_dev;
     }
@@ -1733,14 +1732,6 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
             const long long* e = dbg + 256 + i * 8;
             printf("  %2d: %6lld %6lld %6lld %6lld %6lld %6lld | %6lld %6lld\n", i, e[1] - e[0], e[2] - e[1], e[3] - e[2], e[4] - e[3],
                    e[5] - e[4], e[6] - e[5], e[6] - e[0], i ? e[0] - (e - 8)[0] : 0LL);
-        }
-        if (dbg[1024 + 2]) {
-            printf("kf input-transform warp 2 timeline (CTA 0): chunk: wait_row loads math+stores fence | since previous\n");
-            for (int i = 0; i < 48 && dbg[1024 + i * 8 + 2]; ++i) {
-                const long long* e = dbg + 1024 + i * 8;
-                printf("  %2d: %6lld %6lld %6lld %6lld | %6lld\n", i, e[1] - e[0], e[3] ? e[3] - e[1] : 0LL, e[3] ? e[4] - e[3] : e[4] - e[1],
-                       e[2] - e[4], i ? e[0] - (e - 8)[0] : 0LL);
-            }
         }
         {  // lifetimes of all CTAs relative to the earliest start
             long long t0 = 0, t1 = 0;
