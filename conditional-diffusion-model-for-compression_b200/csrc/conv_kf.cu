@@ -58,7 +58,7 @@ constexpr int kKfXfPix = kKfXfThreads / 8;     // pixels per pass (8 threads = o
 template <int BN, int CPG, int EPI, int CH, bool STAGE, bool XK16, int MODE, bool RES1, bool APPLY>
 __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 1) conv_kf_kernel(const __grid_constant__ KfParams p) {
     constexpr int kThreads = 128 + kEpiThreads + (APPLY ? kKfXfExtra : 0);
-    static_assert(!APPLY || (MODE == 0 && !XK16 && !RES1 && EPI == EPI_STATS && CH == 1), "input GroupNorm: a 64-channel ResBlock's second conv");
+    static_assert(!APPLY || (MODE == 0 && !XK16 && !RES1 && EPI == EPI_STATS && CH <= 2), "input GroupNorm: a 64/128-channel ResBlock's second conv");
     constexpr int WB = BN * 128;  // one (tap, chunk) weight block
     constexpr uint32_t WB16 = WB >> 4;
     // accumulator ring: as many output rows as TMEM holds (a window that wraps costs split MMAs: the longer the ring,
@@ -104,7 +104,6 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
     float* bias_s = reinterpret_cast<float*>(aux_gen + 512);  // [BN] conv bias, then [BN] residual-conv bias
     float* red_s = reinterpret_cast<float*>(aux_gen + 1024);
     float2* coef_s = reinterpret_cast<float2*>(aux_gen + 3072);      // APPLY: [CH * 64] (a, b) of the current image
-    float2* mr_s = reinterpret_cast<float2*>(aux_gen + 3072 + 2048);  // APPLY: [32] (mean, rstd)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nt = blockIdx.x / p.G1, cta = blockIdx.x % p.G1;
@@ -615,9 +614,9 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
         const uint32_t toff = static_cast<uint32_t>(pl) * 128u + (static_cast<uint32_t>(c ^ (pl & 7)) << 4);  // 128-byte swizzle
         constexpr int NIT = (130 + kKfXfPix - 1) / kKfXfPix;  // 9 passes of 16 pixels, done as 3 x 3 (64-register budget)
         static_assert(kKfXfPix % 8 == 0 && NIT == 9, "a pixel's swizzle phase must not depend on the pass");
-        const double inv_n = kGnFixInv / (2.0 * p.H * p.W);  // C_in = 64: two channels per group
-        float2* coef_g = coef_s + grp * 64;                   // each group keeps its own table: no cross-group barrier
-        float2* mr_g = coef_s + 128 + grp * 32;              // (both inside the 2 KB coefficient area)
+        constexpr int cpg_in = CH * 2;  // channels per group of the input (C_in / 32)
+        const double inv_n = kGnFixInv / (static_cast<double>(cpg_in) * p.H * p.W);
+        float2* coef_g = coef_s + grp * (CH * 64);  // each group keeps its own table: no cross-group barrier
         uint32_t n = 0;  // chunk counter of the CTA (all chunks; this group handles n % 2 == grp)
         int cur_b = -1;
         float4 cf[4];
@@ -626,20 +625,21 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
             decode(u, b, seg, si, h0, L);
             if (b != cur_b) {  // coefficient table of image b (once per CTA when the batch is 1)
                 named_bar_sync(3 + grp, kKfXfThreads);
-                if (xt < 32) mr_g[xt] = gn_mean_rstd(p.in_acc + (static_cast<size_t>(b) * 32 + xt) * 2, inv_n, p.in_eps);
-                named_bar_sync(3 + grp, kKfXfThreads);
-                if (xt < 64) {
-                    const float sc = p.in_film ? 1.0f + p.in_film[xt] : 1.0f, sh = p.in_film ? p.in_film[64 + xt] : 0.0f;
-                    const float2 ab = gn_fold(p.in_gamma[xt], p.in_beta[xt], sc, sh, mr_g[xt / 2]);
+                if (xt < CH * 64) {  // (every thread derives its channel's group statistics itself: a few FP64 operations)
+                    const float2 mr = gn_mean_rstd(p.in_acc + (static_cast<size_t>(b) * 32 + xt / cpg_in) * 2, inv_n, p.in_eps);
+                    const float sc = p.in_film ? 1.0f + p.in_film[xt] : 1.0f, sh = p.in_film ? p.in_film[CH * 64 + xt] : 0.0f;
+                    const float2 ab = gn_fold(p.in_gamma[xt], p.in_beta[xt], sc, sh, mr);
                     coef_g[xt] = make_float2(0.5f * ab.x, 0.5f * ab.y);  // (a/2, b/2): see silu_h
                 }
                 named_bar_sync(3 + grp, kKfXfThreads);
                 cur_b = b;
+                // with two chunks per row the groups' alternation pins group g to chunk g: one coefficient set either way
 #pragma unroll
-                for (int j = 0; j < 4; ++j) cf[j] = reinterpret_cast<const float4*>(coef_g + c * 8)[j];
+                for (int j = 0; j < 4; ++j) cf[j] = reinterpret_cast<const float4*>(coef_g + (CH == 2 ? grp * 64 : 0) + c * 8)[j];
             }
             const int w0 = seg * 128 - 1;
-            for (int i = 0; i < L + 2; ++i, ++n) {
+            for (int ic = 0; ic < (L + 2) * CH; ++ic, ++n) {
+                const int i = ic / CH;
                 if ((n & 1u) != static_cast<uint32_t>(grp)) continue;
                 const uint32_t slot = n % static_cast<uint32_t>(NS), par = (n / static_cast<uint32_t>(NS)) & 1u;
                 const int h = h0 - 1 + i;
@@ -722,6 +722,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
     KF_CASE(32, 4, EPI_STATS, 3, false, false, 0, true, false)    \
     KF_CASE(32, 4, EPI_STATS, 4, false, false, 0, true, false)    \
     KF_CASE(64, 2, EPI_STATS, 1, true, false, 0, false, true)     \
+    KF_CASE(64, 4, EPI_STATS, 2, false, false, 0, false, true)    \
     KF_CASE(64, 1, EPI_STORE, 1, true, false, 2, false, false)      \
     KF_CASE(64, 1, EPI_STORE, 2, false, false, 2, false, false)
 

@@ -211,9 +211,9 @@ static bool fuse_apply_enabled() {  // CDC_FUSE_APPLY=0: GroupNorm 1 of every Re
     const char* e = getenv("CDC_FUSE_APPLY");
     return !(e && atoi(e) == 0);
 }
-static int fuse_apply_max_tiles() {  // CDC_FUSE_APPLY=n > 1: fuse into convs with up to n N tiles (experiments)
+static int fuse_apply_max_tiles() {  // N tiles a conv may have for the fusion (every tile's CTAs repeat the transform); CDC_FUSE_APPLY=n overrides
     const char* e = getenv("CDC_FUSE_APPLY");
-    return e && atoi(e) > 1 ? atoi(e) : 1;
+    return e && atoi(e) >= 1 ? atoi(e) : 2;
 }
 static bool kf_disabled() {
     static int v = -1;
@@ -260,8 +260,8 @@ static bool conv_uses_kf(const ConvBuild& cb, int B, int num_sms, KfGeom* g) {
         break;
     }
     if (!g->bn) return false;
-    // (every N tile's CTAs transform the same rows: with more than fuse_apply_max_tiles() tiles the redundant MUFU work
-    // costs more than the pass it replaces -- measured: fusing levels 1-3 as well made the step 17 % slower)
+    // (every N tile's CTAs transform the same rows: levels 0 and 1 -- one and two N tiles, instantiated for 64 and 128
+    // channels -- gain 2.4 % and 0.8 % images/s; with 3+ tiles the redundant MUFU work costs more than the pass it replaces)
     g->apply = cb.in_acc != nullptr && !g->res && cb.srcs.size() == 1 && cb.cpg == g->CH * 2 &&
                cb.w->n_pad / g->bn <= fuse_apply_max_tiles() && kf_inst_ok(g->bn, cb.cpg, cb.epi, g->CH, g->mode, false, true);
     g->n_tiles = cb.w->n_pad / g->bn * (g->mode == 1 ? 4 : 1);
