@@ -43,7 +43,7 @@ namespace cdc {
 constexpr int kKfRowBytes = 17 * 1024;  // 130 pixels x 128 B = 16640, padded to a 1024 B multiple
 constexpr int kKfRowTx = 130 * 128;
 constexpr int kKfAccMax = 16;           // accumulator-ring barriers (the ring holds min(16, 512 / BN) output rows)
-constexpr int kKfAux = 1024 + 2 * 8 * 16 * 2 * 4 + 2048 + 256 + 128;  // barriers + TMEM holder + bias, stats scratch, APPLY coefficients, ring barriers
+constexpr int kKfAux = 1024 + 2 * 8 * 16 * 2 * 4 + 2048 + 256 + 192;  // barriers + TMEM holder + bias, stats scratch, APPLY coefficients, ring barriers
 constexpr int kKfMaxSlots = 8;          // input ring: at most 8 slots (4 unless the stride-2 mode has room for more)
 // APPLY: eight input-transform warps in TWO groups of four (one warp of each group per SM sub-partition); the groups take
 // alternate row chunks, so the load / arithmetic / store phases of consecutive chunks overlap and each group has two row
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
     // barriers: tfull[16] tempty[16] wres xfull[8] xempty[8] (x = fused residual conv) ... row_full[8] row_empty[8]
     const uint32_t bar_rfull = aux + 5376, bar_rempty = aux + 5376 + 64, bar_tfull = aux + 64, bar_tempty = aux + 192, bar_wres = aux + 320;
     const uint32_t bar_xfull = aux + 328, bar_xempty = aux + 392;
-    const uint32_t bar_rready = aux + 464;  // APPLY: [4] row chunk transformed (one arrive per transform warp)
+    const uint32_t bar_rready = aux + 5376 + 128;  // APPLY: [8] row chunk transformed (one arrive per warp of the owning group)
     const uint32_t bar_afull = APPLY ? bar_rready : bar_rfull;  // what the MMA issuer waits for
     volatile uint32_t* tmem_holder = reinterpret_cast<volatile uint32_t*>(aux_gen + 456);
     float* bias_s = reinterpret_cast<float*>(aux_gen + 512);  // [BN] conv bias, then [BN] residual-conv bias
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
         for (int s = 0; s < kKfMaxSlots; ++s) {
             mbar_init(bar_rfull + 8 * s, 1);
             mbar_init(bar_rempty + 8 * s, 1);
-            if (APPLY && s < 4) mbar_init(bar_rready + 8 * s, kKfXfThreads / 32);
+            if (APPLY) mbar_init(bar_rready + 8 * s, kKfXfThreads / 32);
         }
         for (int s = 0; s < static_cast<int>(NACC); ++s) {
             mbar_init(bar_tfull + 8 * s, 1);
@@ -726,6 +726,12 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
     KF_CASE(64, 1, EPI_STORE, 1, true, false, 2, false, false)      \
     KF_CASE(64, 1, EPI_STORE, 2, false, false, 2, false, false)
 
+static int kf_ring_max_ch1() {  // CDC_KF_RING=n: ring slots of the one-chunk convs (A/B)
+    const char* e = getenv("CDC_KF_RING");
+    const int n = e ? atoi(e) : 6;
+    return n < 3 ? 3 : n > kKfMaxSlots ? kKfMaxSlots : n;
+}
+
 int kf_smem_bytes(int bn, int CH, int NS, bool staged, int mode, bool res) {
     return 1024 + NS * kKfRowBytes + ((mode == 1 ? 4 : 9) + (res ? 1 : 0)) * CH * bn * 128 + (staged ? 2 * 128 * bn * 2 : 0) + kKfAux;
 }
@@ -736,7 +742,9 @@ bool kf_plan(int bn, int CH, int mode, bool res, int epi, int* NS, bool* staged)
         if (st && bn != 64) continue;
         // (a single staging buffer + a 3-slot ring for the two-chunk store-only stem was tried: 35 -> 43 us)
         (void)epi;
-        for (int ns = mode == 2 ? kKfMaxSlots : 4; ns >= (mode == 2 ? 4 : 3); --ns)  // (stride 2: two slots per (row, chunk))
+        // (stride 2: two slots per (row, chunk); one-chunk convs: a deeper ring where shared memory allows -- the input
+        // transform adds a pipeline stage)
+        for (int ns = mode == 2 ? kKfMaxSlots : CH == 1 ? kf_ring_max_ch1() : 4; ns >= (mode == 2 ? 4 : 3); --ns)
             if (kf_smem_bytes(bn, CH, ns, st != 0, mode, res) <= limit) {
                 *NS = ns;
                 *staged = st != 0;
