@@ -20,6 +20,10 @@
 //
 //   warp 0 : input-row producer (TMA)   warp 1 : barrier init + weight load (TMA, once), then tcgen05.mma issuer
 //   warp 2 : TMEM allocator             warps 4-11 : epilogue
+//   warps 12-19 (APPLY only) : GroupNorm + FiLM + SiLU of the INPUT rows, in shared memory, two groups on alternate chunks
+//
+// Modes: 0 = 3x3 / stride 1 (optionally with the ResBlock's 1x1 residual conv riding along, RES1);
+//        1 = nearest-x2 upsample + 3x3 as four parity 2x2 convs;  2 = 3x3 / stride 2 (even / odd pixel tiles).
 //
 // Epilogue: +bias, GroupNorm sums kept in registers over the whole strip and added once per strip to the
 // fixed-point accumulators of gn_sums.cuh (integer atomics: bitwise reproducible), fp16 pack, then either a
