@@ -9,8 +9,9 @@ One "step" = one full decode of one image per GPU (context net + 17 DDIM steps).
   value : images/s, inputs (latent, x_T) resident in HBM, timed with CUDA events, max over ranks
   e2e   : same metric through the public API with HOST tensors (pinned staging, H2D + D2H inside
           the timed region)
-  roofline : tcgen05 conv kernel, algorithmic FLOPs of its launches in one step / their summed
-          CUDA-event durations, against MEASURED_PEAKS.json bf16_tflops
+  roofline : tcgen05 conv kernels, algorithmic FLOPs of their launches in one step / their summed in-graph
+          durations (globaltimer stamps written by the kernels themselves), against MEASURED_PEAKS.json bf16_tflops
+  roofline_int : the integer kernels (latent rounding, CDF lookup) at the cfg5 symbol count, GB/s against hbm_gbs
   cpu_baseline : the oracle (oracle/, "port": the reference ships no code) on the host cores, bounded sample
 """
 import argparse
@@ -142,13 +143,58 @@ def run_reference(args):
     }))
 
 
+def int_roofline(dev, peak_gbs, n=4194304, reps=9):
+    """Achieved HBM GB/s of the integer kernels (rows a8 / a9) at the cfg5 symbol count (2048^2 / 256 * 256 = 4 194 304),
+    algorithmic bytes (16 B and 28 B per symbol) / CUDA-event time, L2 flushed before every launch."""
+    import torch
+    from cdc_b200 import cdf_lookup, quantize_symbols
+    from cdc_b200.decoder import DeviceTables
+    from cdc_b200.synthetic import entropy_inputs, gaussian_tables
+    y, mu, sigma = (t.to(dev) for t in entropy_inputs(n))
+    tb = DeviceTables(gaussian_tables(), dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    q, _ = quantize_symbols(y, mu, device=dev)
+
+    def timed(fn):
+        ts = []
+        for i in range(reps + 2):
+            flush.fill_(i)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                ts.append(s.elapsed_time(e))
+        return statistics.median(ts)
+
+    # (the Python wrappers allocate their outputs: time the raw ABI calls on preallocated buffers)
+    import ctypes as C
+    from cdc_b200 import _ffi
+    L = _ffi.lib()
+    qo = torch.empty(n, dtype=torch.int32, device=dev)
+    yh = torch.empty(n, dtype=torch.float32, device=dev)
+    outs = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(5)]
+    P = lambda t: C.c_void_p(t.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ms_q = timed(lambda: L.cdc_quantize(P(y), P(mu), P(qo), P(yh), n, 0, 0, st))
+    ms_c = timed(lambda: L.cdc_cdf_lookup(P(q), P(sigma), P(tb.cdf), P(tb.row_start), P(tb.cdf_length), P(tb.offset),
+                                          P(tb.scale_table), tb.rows, 1, *[P(o) for o in outs], n, st))
+    assert torch.equal(qo, q)
+    gq, gc = 16.0 * n / (ms_q * 1e-3) / 1e9, 28.0 * n / (ms_c * 1e-3) / 1e9
+    return {"symbols": n, "bound": "hbm", "unit": "GB/s", "peak": peak_gbs,
+            "quantize_kernel": {"achieved": gq, "frac": gq / peak_gbs, "us": ms_q * 1e3, "bytes_per_symbol": 16},
+            "cdf_lookup_kernel": {"achieved": gc, "frac": gc / peak_gbs, "us": ms_c * 1e3, "bytes_per_symbol": 28},
+            "how": "cdc_quantize / cdc_cdf_lookup on device buffers, CUDA events, median of %d, 256 MiB L2 flush before every launch" % reps}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cdc_b200")
-    ap.add_argument("--ops-out", default=None, help="write the per-launch table of one denoise step (CSV)")
+    ap.add_argument("--ops-out", default=None, help="write the per-kernel in-graph table of one denoise step (CSV)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -166,16 +212,22 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(dev))
 
     # the product arm never touches oracle/: weights and inputs come from the package's own generators
-    from cdc_b200 import CDCConfig, Decoder
+    from cdc_b200 import CDCConfig, Decoder, dp
     from cdc_b200.synthetic import init_noise as synthetic_init, latent as synthetic_latent, random_weights
     dec = Decoder(CDCConfig(), random_weights(CDCConfig(), seed=0, with_context=True), device=dev)
     dec.set_sample_schedule(K_DDIM)
+    # The job is a list of world * (warmup + steps) images; rank r decodes {i : i mod world == r} (cdc_b200.dp):
+    # per-GPU work is fixed as N grows (weak scaling), no collective on the data path.
     n_img = args.warmup + args.steps
-    lat_h = [synthetic_latent(1, H, W, index=rank * 1000 + i).pin_memory() for i in range(n_img)]
-    x_h = [synthetic_init(1, H, W, index=rank * 1000 + i).pin_memory() for i in range(n_img)]
-    lat_d = [t.to(dev) for t in lat_h]
-    x_d = [t.to(dev) for t in x_h]
+    n_job = world * n_img
+    mine = dp.shard_indices(n_job, rank, world)
+    assert len(mine) == n_img
+    lat_h = {i: synthetic_latent(1, H, W, index=i).pin_memory() for i in mine}
+    x_h = {i: synthetic_init(1, H, W, index=i).pin_memory() for i in mine}
+    lat_d = {i: t.to(dev) for i, t in lat_h.items()}
+    x_d = {i: t.to(dev) for i, t in x_h.items()}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    n_warm_job = world * args.warmup  # the first `warmup` images of every rank are untimed
 
     def barrier():
         torch.cuda.synchronize()
@@ -186,44 +238,45 @@ def main():
     def timed(fn):
         sampler = ClockSampler(local)
         sampler.start()  # before the warm-up: nvidia-smi needs ~0.1-0.5 s to deliver its first sample
-        for i in range(args.warmup):
-            fn(i)
+        dp.decode_sharded(fn, n_warm_job, rank, world)
         barrier()
         t_begin = time.perf_counter()
         evs = []
-        for i in range(args.warmup, n_img):
+
+        def one(i):
             flush.fill_(i & 0xFF)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            fn(i)
+            out = fn(i)
             e.record()
             evs.append((s, e))
+            return out
+
+        n_done, _ = dp.decode_sharded(lambda j: one(n_warm_job + j), n_job - n_warm_job, rank, world)
         barrier()
         clocks = sampler.stop(t_begin, time.perf_counter())
         ms = sum(s.elapsed_time(e) for s, e in evs)
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), clocks
+        # one gather of (images, device seconds) per rank AFTER the timed region; whole-job rate = images / slowest rank
+        table = dp.gather_metrics([n_done, ms / 1e3], device=dev)
+        return dp.aggregate_throughput(table), float(table[:, 1].max()) * 1e3, clocks
 
     # device-resident leg: latent and x_T already in HBM; context net + K-step graph + image conversion
     out_keep = []
 
     def dev_step(i):
         out_keep[:] = [dec.decode(lat_d[i], K_DDIM, init=x_d[i])]
+        return out_keep[0]
 
-    ms_dev, clocks = timed(dev_step)
+    value, ms_dev, clocks = timed(dev_step)
 
     out_h = torch.empty(1, 3, H, W, dtype=torch.float32).pin_memory()  # the caller's page-locked result buffer
 
     def host_step(i):
         out_keep[:] = [dec.decode(lat_h[i], K_DDIM, init=x_h[i], out=out_h)]  # cdc_decode_host: H2D + decode + D2H + sync
+        return out_keep[0]
 
-    ms_e2e, _ = timed(host_step)
+    e2e, ms_e2e, _ = timed(host_step)
     assert torch.isfinite(out_keep[0]).all()
-
-    value = world * args.steps / (ms_dev / 1e3)
-    e2e = world * args.steps / (ms_e2e / 1e3)
     launches = args.steps * (dec.L.cdc_launches_context(dec.ctx) + 2 + K_DDIM * dec.launches_per_step())
 
     out = {
@@ -231,76 +284,88 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp16" if dec.L.cdc_act_dtype() == 1 else "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "image": [H, W], "ddim_steps": K_DDIM, "batch_per_gpu": 1,
-                   "parallelism": f"image-sharded dp{world}, no data-path collective",
+                   "parallelism": f"image-sharded dp{world} (cdc_b200.dp: rank r decodes images i = r mod {world}), no data-path collective",
                    "l2": "flushed between timed iterations (256 MiB write, outside the event brackets)",
                    "precision": "fp16 storage + tcgen05 kind::f16 operands, fp32 accumulate/statistics/sampler state "
-                                "(bf16 operands miss the 1e-2 per-step tolerance: DESIGN.md section 5)"},
+                                "(ratified in BASELINE.md: bf16 operands measure 0.02-0.04 against the 1e-2 per-step tolerance; "
+                                "tests/test_gpu_parity_r2.py runs the bf16 build)"},
         "clocks": clocks,
-        "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(lat_h[0].numel() * 4 + x_h[0].numel() * 4),
-                "d2h_bytes_per_step": int(x_h[0].numel() * 4)},
+        "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(lat_h[mine[0]].numel() * 4 + x_h[mine[0]].numel() * 4),
+                "d2h_bytes_per_step": int(x_h[mine[0]].numel() * 4), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
+        "saturation_events": dec.saturation_count(),
     }
 
     if rank == 0:
-        # ---- roofline of the dominant kernel class (the tcgen05 convs), measured live with CUDA events ----
-        # In-graph time of a class of kernels = replay time of the full 17-step graph minus the replay time of the same
-        # graph captured without that class (cdc_debug_graph_skip): no per-launch event overhead, warm L2 exactly as in
-        # the timed decode.  The per-op table (--ops-out) still comes from in-stream events around single launches.
+        # ---- roofline of the dominant kernel class (the tcgen05 convs), measured live INSIDE the captured graph ----
+        # cdc_profile_graph replays the same 17-step graph with every kernel stamping (earliest CTA start, latest CTA end)
+        # in globaltimer ns: per-kernel durations and start-to-start slots without event overhead and with the caches
+        # exactly as in the timed decode (replaces round 1's replay-time differencing).
         ops = dec.step_ops()
-
-        def graph_ms(op_class, reps=7):
-            _ffi_check(dec.L.cdc_debug_graph_skip(dec.ctx, op_class))
-            ts = []
-            for i in range(reps + 2):
-                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s.record()
-                _ffi_check(dec.L.cdc_decode(dec.ctx, None))
-                e.record()
-                torch.cuda.synchronize()
-                if i >= 2:
-                    ts.append(s.elapsed_time(e))
-            return statistics.median(ts) if ts else 0.0
-
-        def _ffi_check(rc):
-            if rc != 0:
-                raise RuntimeError(dec.L.cdc_last_error(dec.ctx).decode())
-
-        dec.decode(lat_d[0], K_DDIM, init=x_d[0])
+        i0 = mine[0]
+        dec.decode(lat_d[i0], K_DDIM, init=x_d[i0])
         torch.cuda.synchronize()
-        g_full, g_noconv, g_noew = graph_ms(0), graph_ms(1), graph_ms(2)
-        graph_ms(0, reps=0)  # back to the full graph
-        conv_ms = (g_full - g_noconv) / K_DDIM
-        ew_ms = (g_full - g_noew) / K_DDIM
-        conv = [(n, f, b) for (n, f, b) in ops if f > 0 and "sdpa" not in n]
-        conv_fl = sum(f for _, f, _ in conv)
-        n_gn_in = sum(1 for n, _, _ in conv if "+gn_in" in n)
+        start, dur = dec.profile_graph(reps=7)
+        nops = len(ops)
+        kidx = [i for i in range(nops) if ops[i][0] != "gn.clear"]
+        # slot of a kernel = time until the next kernel of the graph starts (its duration + the gap behind it)
+        flat = [(k, i) for k in range(K_DDIM) for i in kidx]
+        slot = {}
+        for a, b in zip(flat[:-1], flat[1:]):
+            slot[a] = start[b[0]][b[1]] - start[a[0]][a[1]]
+        slot[flat[-1]] = dur[flat[-1][0]][flat[-1][1]]
+        med = lambda v: statistics.median(v)
+        d_us = [med([dur[k][i] for k in range(K_DDIM)]) for i in range(nops)]
+        s_us = [med([slot[(k, i)] for k in range(K_DDIM)]) if i in kidx else 0.0 for i in range(nops)]
+        graph_us = start[K_DDIM - 1][kidx[-1]] + dur[K_DDIM - 1][kidx[-1]]
+        is_conv = [f > 0 and "sdpa" not in n for (n, f, b) in ops]
+        conv_fl = sum(f for (n, f, b), c in zip(ops, is_conv) if c)
+        conv_us = sum(sum(dur[k][i] for i in range(nops) if is_conv[i]) for k in range(K_DDIM)) / K_DDIM
+        conv_slot_us = sum(sum(slot[(k, i)] for i in kidx if is_conv[i]) for k in range(K_DDIM)) / K_DDIM
+        ew = [i for i in kidx if ops[i][1] == 0]
+        ew_us = sum(sum(dur[k][i] for i in ew) for k in range(K_DDIM)) / K_DDIM
+        ew_bytes = sum(ops[i][2] for i in ew)
+        n_conv = sum(is_conv)
+        n_gn_in = sum(1 for (n, f, b), c in zip(ops, is_conv) if c and "+gn_in" in n)
         peak_tf, peak_gbs, which = peaks()
-        ach = conv_fl / (conv_ms / 1e3) / 1e12
+        ach = conv_fl / (conv_us * 1e-6) / 1e12
+        ach_slot = conv_fl / (conv_slot_us * 1e-6) / 1e12
         traffic, traffic_of = None, None
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram bytes / launch of the top kernel (ncu --set full)
         if os.path.exists(tp):
             tj = json.load(open(tp))
             traffic, traffic_of = tj.get("dram_bytes_per_launch"), tj.get("kernel")
-        out["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                           "traffic": traffic, "traffic_of": traffic_of,
-                           "kernel": f"conv_kf_kernel + conv_tc_kernel: the {len(conv)} tcgen05 conv launches of one denoise step "
-                                     f"({conv_fl / 1e9:.1f} GFLOP algorithmic, {conv_ms * 1e3:.0f} us in-graph"
-                                     + (f"; {n_gn_in} of them also apply GroupNorm+FiLM+SiLU to their input rows in shared memory, "
-                                        "replacing elementwise passes)" if n_gn_in else ")"),
-                           "peak_source": which, "how": "graph replay time minus replay time of the graph captured without the convs, / 17 steps",
-                           "graph_ms": g_full, "conv_ms_per_step": conv_ms,
-                           "step_tflops": dec.flops_per_step() / (g_full / K_DDIM / 1e3) / 1e12}
-        ew_bytes = sum(b for n, f, b in ops if f == 0)
-        out["roofline"]["elementwise_ms_per_step"] = ew_ms
-        out["roofline"]["elementwise_gbs"] = ew_bytes / (ew_ms / 1e3) / 1e9 if ew_ms > 0 else None
-        out["roofline"]["elementwise_frac_of_hbm_peak"] = out["roofline"]["elementwise_gbs"] / peak_gbs if ew_ms > 0 else None
-        runs = [dec.profile_step(8, warm=1) for _ in range(5)]
-        med = [statistics.median(r[j] for r in runs) / 1e3 for j in range(len(ops))]
+        out["roofline"] = {
+            "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+            "traffic": traffic, "traffic_of": traffic_of,
+            "kernel": f"conv_kf_kernel + conv_tc_kernel: the {n_conv} tcgen05 conv launches of one denoise step "
+                      f"({conv_fl / 1e9:.1f} GFLOP algorithmic)"
+                      + (f"; {n_gn_in} of them also apply GroupNorm+FiLM+SiLU to their input rows in shared memory, "
+                         "replacing elementwise passes" if n_gn_in else ""),
+            "peak_source": which,
+            "how": "sum over the conv launches of (latest CTA end - earliest CTA start), globaltimer stamps written by the kernels inside the "
+                   "captured 17-step graph (cdc_profile_graph, median of 7 replays), averaged over the 17 steps",
+            "conv_us_per_step": conv_us,
+            "achieved_incl_gaps": ach_slot, "frac_incl_gaps": ach_slot / peak_tf, "conv_slot_us_per_step": conv_slot_us,
+            "incl_gaps_how": "same FLOPs / start-to-next-kernel-start slots (kernel + the launch gap behind it): comparable with round 1's "
+                             "replay-time differencing (0.499)",
+            "graph_ms": graph_us / 1e3, "step_us": graph_us / K_DDIM,
+            "step_tflops": dec.flops_per_step() / (graph_us / K_DDIM * 1e-6) / 1e12,
+            "elementwise_us_per_step": ew_us, "elementwise_launches": len(ew),
+            "elementwise_gbs": ew_bytes / (ew_us * 1e-6) / 1e9 if ew_us > 0 else None,
+            "elementwise_frac_of_hbm_peak": ew_bytes / (ew_us * 1e-6) / 1e9 / peak_gbs if ew_us > 0 else None,
+        }
+        try:
+            out["roofline_int"] = int_roofline(dev, peak_gbs)
+        except Exception as ex:  # never lose the headline line to the secondary measurement
+            out["roofline_int"] = {"error": repr(ex)}
         if args.ops_out:
             with open(args.ops_out, "w") as f:
-                f.write("op,gflop,mbytes,us,tflops,gbs\n")
-                for (n, fl, b), t in zip(ops, med):
-                    f.write(f"{n},{fl / 1e9:.3f},{b / 1e6:.3f},{t * 1e3:.2f},{fl / (t / 1e3) / 1e12:.1f},{b / (t / 1e3) / 1e9:.0f}\n")
+                f.write("op,gflop,mbytes,us_in_graph,slot_us,tflops,gbs\n")
+                for i in kidx:
+                    n, fl, b = ops[i]
+                    t = max(d_us[i], 1e-3)
+                    f.write(f"{n},{fl / 1e9:.3f},{b / 1e6:.3f},{d_us[i]:.2f},{s_us[i]:.2f},{fl / (t * 1e-6) / 1e12:.1f},{b / (t * 1e-6) / 1e9:.0f}\n")
         if not args.no_cpu and world == 1:  # the CPU baseline is an N=1 figure (contract); torchrun also pins OMP threads
             v, cores, t_ctx, t_step = cpu_oracle_sample(n_steps=K_DDIM)
             out["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",

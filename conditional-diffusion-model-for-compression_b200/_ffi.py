@@ -6,15 +6,20 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CDC_LIB_PATH") or os.path.join(_HERE, "libcdc_b200.so")  # override: A/B builds in tools/
 
-# every symbol include/cdc_b200.h declares
+# every symbol include/cdc_b200.h declares (the drop-in boundary) ...
 SYMBOLS = [
     "cdc_create", "cdc_destroy", "cdc_last_error", "cdc_abi_version", "cdc_act_dtype", "cdc_load_weights", "cdc_finalize_weights",
-    "cdc_has_context_net", "cdc_set_schedule", "cdc_schedule_index", "cdc_schedule_coeffs", "cdc_bind_io",
-    "cdc_set_cond", "cdc_set_latent", "cdc_set_x", "cdc_get_x", "cdc_get_x0", "cdc_denoise_step", "cdc_decode",
-    "cdc_decode_host", "cdc_launches_per_step", "cdc_launches_context", "cdc_flops_per_step", "cdc_num_step_ops",
-    "cdc_step_op_name", "cdc_step_op_flops", "cdc_step_op_bytes", "cdc_run_step_op", "cdc_profile_step", "cdc_debug_graph_skip", "cdc_quantize",
-    "cdc_cdf_lookup", "cdc_test_conv", "cdc_test_attention", "cdc_test_gn",
+    "cdc_has_context_net", "cdc_set_schedule", "cdc_schedule_index", "cdc_schedule_coeffs", "cdc_set_sampler",
+    "cdc_schedule_coeffs5", "cdc_film_size", "cdc_get_film", "cdc_bind_io", "cdc_set_cond", "cdc_get_cond", "cdc_set_latent",
+    "cdc_set_x", "cdc_get_x", "cdc_get_x0", "cdc_denoise_step", "cdc_decode", "cdc_decode_host", "cdc_launches_per_step",
+    "cdc_launches_context", "cdc_flops_per_step", "cdc_saturation_count", "cdc_quantize", "cdc_cdf_lookup",
 ]
+# ... and include/cdc_b200_tools.h (tests / profiling / A-B; same library)
+TOOLS_SYMBOLS = [
+    "cdc_set_plan_option", "cdc_num_step_ops", "cdc_step_op_name", "cdc_step_op_flops", "cdc_step_op_bytes", "cdc_run_step_op",
+    "cdc_profile_step", "cdc_profile_graph", "cdc_test_conv", "cdc_test_attention", "cdc_test_gn",
+]
+OPT_FUSE_APPLY, OPT_KF, OPT_KF_S2, OPT_KF_MIN_PIXELS, OPT_KF_RING, OPT_WEIGHT_GROUPS = range(6)
 
 
 class CdcConfig(C.Structure):
@@ -23,31 +28,26 @@ class CdcConfig(C.Structure):
                 ("gn_eps", C.c_float)]
 
 
-_lib = None
+_libs = {}
+VARIANTS = {"product": "libcdc_b200.so", "bf16": "libcdc_b200_bf16.so", "tools": "libcdc_b200_tools.so"}
 
 
-def build(verbose=False):
-    """Compile the extension in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+def build(verbose=False, what="all"):
+    """Compile the extension in-tree for sm_100a (nvcc cross-compiles without a GPU): the product library, the bf16
+    variant the precision tests measure and the tools variant (csrc/build.sh)."""
     import subprocess
     script = os.path.join(_HERE, "csrc", "build.sh")
-    r = subprocess.run(["bash", script], capture_output=True, text=True)
+    r = subprocess.run(["bash", script, what], capture_output=True, text=True)
     if verbose or r.returncode:
         print(r.stdout + r.stderr)
     if r.returncode:
-        raise RuntimeError("building libcdc_b200.so failed:\n" + r.stdout + r.stderr)
+        raise RuntimeError("building libcdc_b200*.so failed:\n" + r.stdout + r.stderr)
     return LIB_PATH
 
 
-def lib():
-    """Load the shared library; fail loudly if it is missing (no fallback path exists)."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
-                           "(cdc_b200 has no CPU or PyTorch fallback)")
-    L = C.CDLL(LIB_PATH)
+def _bind(L):
     p, i32, i64, f32p, i32p = C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p
+    fp = C.POINTER(C.c_float)
     L.cdc_create.argtypes = [C.POINTER(CdcConfig), i32, C.POINTER(p)]
     L.cdc_destroy.argtypes = [p]
     L.cdc_destroy.restype = None
@@ -58,9 +58,14 @@ def lib():
     L.cdc_has_context_net.argtypes = [p]
     L.cdc_set_schedule.argtypes = [p, i32]
     L.cdc_schedule_index.argtypes = [p, i32]
-    L.cdc_schedule_coeffs.argtypes = [p, i32, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.cdc_schedule_coeffs.argtypes = [p, i32, fp, fp]
+    L.cdc_set_sampler.argtypes = [p, i32, C.c_float, C.c_uint64]
+    L.cdc_schedule_coeffs5.argtypes = [p, i32, fp, fp, fp, fp, fp]
+    L.cdc_film_size.argtypes = [p]
+    L.cdc_get_film.argtypes = [p, f32p, p]
     L.cdc_bind_io.argtypes = [p, i32, i32, i32]
     L.cdc_set_cond.argtypes = [p, f32p, f32p, f32p, f32p, p]
+    L.cdc_get_cond.argtypes = [p, f32p, f32p, f32p, f32p, p]
     L.cdc_set_latent.argtypes = [p, f32p, p]
     L.cdc_set_x.argtypes = [p, f32p, p]
     L.cdc_get_x.argtypes = [p, f32p, i32, p]
@@ -72,6 +77,12 @@ def lib():
     L.cdc_launches_context.argtypes = [p]
     L.cdc_flops_per_step.argtypes = [p]
     L.cdc_flops_per_step.restype = C.c_double
+    L.cdc_saturation_count.argtypes = [p, C.POINTER(C.c_uint64), i32, p]
+    L.cdc_quantize.argtypes = [f32p, f32p, i32p, f32p, i64, i64, i64, p]
+    L.cdc_cdf_lookup.argtypes = [i32p, f32p, i32p, i32p, i32p, i32p, f32p, i32, i64, i32p, i32p, i32p, i32p, i32p,
+                                 i64, p]
+    # tools header
+    L.cdc_set_plan_option.argtypes = [p, i32, i32]
     L.cdc_num_step_ops.argtypes = [p]
     L.cdc_step_op_name.argtypes = [p, i32]
     L.cdc_step_op_name.restype = C.c_char_p
@@ -80,21 +91,32 @@ def lib():
     L.cdc_step_op_bytes.argtypes = [p, i32]
     L.cdc_step_op_bytes.restype = C.c_double
     L.cdc_run_step_op.argtypes = [p, i32, i32, p]
-    L.cdc_profile_step.argtypes = [p, i32, i32, C.POINTER(C.c_float), p]
-    L.cdc_debug_graph_skip.argtypes = [p, i32]
-    L.cdc_quantize.argtypes = [f32p, f32p, i32p, f32p, i64, i64, i64, p]
-    L.cdc_cdf_lookup.argtypes = [i32p, f32p, i32p, i32p, i32p, i32p, f32p, i32, i64, i32p, i32p, i32p, i32p, i32p,
-                                 i64, p]
+    L.cdc_profile_step.argtypes = [p, i32, i32, fp, p]
+    L.cdc_profile_graph.argtypes = [p, i32, fp, fp, p]
     L.cdc_test_conv.argtypes = [i32, p, i32, p, i32, i32, i32, i32, f32p, f32p, i32, i32, i32, i32, p, p, p, p]
     L.cdc_test_attention.argtypes = [p, p, i32, i32, i32, p]
     L.cdc_test_gn.argtypes = [p, p, p, f32p, f32p, f32p, i32, i32, i32, i32, C.c_float, p]
-    for s in SYMBOLS:
-        getattr(L, s)  # raises AttributeError if the header and the library disagree
-    _lib = L
+    for s in SYMBOLS + TOOLS_SYMBOLS:
+        getattr(L, s)  # raises AttributeError if the headers and the library disagree
+    if hasattr(L, "cdc_debug_graph_skip"):  # tools build only
+        L.cdc_debug_graph_skip.argtypes = [p, i32]
     return L
 
 
-def check(ctx, rc, what):
+def lib(variant="product"):
+    """Load a build of the shared library; fail loudly if it is missing (no fallback path exists).
+    variant: "product" (default; CDC_LIB_PATH overrides the file), "bf16" or "tools"."""
+    if variant in _libs:
+        return _libs[variant]
+    path = LIB_PATH if variant == "product" else os.path.join(_HERE, VARIANTS[variant])
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(cdc_b200 has no CPU or PyTorch fallback)")
+    _libs[variant] = _bind(C.CDLL(path))
+    return _libs[variant]
+
+
+def check(ctx, rc, what, L=None):
     if rc != 0:
-        msg = lib().cdc_last_error(ctx)
+        msg = (L or lib()).cdc_last_error(ctx)
         raise RuntimeError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")

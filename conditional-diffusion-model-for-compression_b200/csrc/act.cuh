@@ -22,6 +22,7 @@ typedef __half act_t;
 constexpr uint32_t kUmmaFormat = 0;  // tcgen05 kind::f16 a_format / b_format: 0 = F16
 #define CDC_TMA_DTYPE CU_TENSOR_MAP_DATA_TYPE_FLOAT16
 #define CDC_MMA_SYNC_T "f16"
+constexpr float kActMax = 65504.0f;  // values beyond it are stored saturated (and counted: ConvParams::sat)
 __host__ __device__ __forceinline__ float sat_act(float v) { return fminf(fmaxf(v, -65504.0f), 65504.0f); }
 __device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {  // saturating: never stores inf
     uint32_t r;
@@ -34,11 +35,14 @@ __device__ __forceinline__ uint32_t pack_act2_nosat(float lo, float hi) {
 }
 __device__ __forceinline__ float act_lo(uint32_t u) { return __half2float(__ushort_as_half(static_cast<unsigned short>(u & 0xFFFFu))); }
 __device__ __forceinline__ float act_hi(uint32_t u) { return __half2float(__ushort_as_half(static_cast<unsigned short>(u >> 16))); }
+// non-zero if either half of a packed pair holds the largest finite magnitude (i.e. was stored saturated)
+__device__ __forceinline__ uint32_t act2_is_sat(uint32_t u) { return __vcmpeq2(u & 0x7FFF7FFFu, 0x7BFF7BFFu); }
 __device__ __forceinline__ act_t to_act(float v) { return __float2half_rn(sat_act(v)); }
 __device__ __forceinline__ float from_act(act_t v) { return __half2float(v); }
 #else
 typedef __nv_bfloat16 act_t;
 constexpr uint32_t kUmmaFormat = 1;  // 1 = BF16
+constexpr float kActMax = 3.3895313892515355e38f;  // bf16 maximum
 #define CDC_TMA_DTYPE CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
 #define CDC_MMA_SYNC_T "bf16"
 __device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
@@ -48,6 +52,7 @@ __device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
 __device__ __forceinline__ uint32_t pack_act2_nosat(float lo, float hi) { return pack_act2(lo, hi); }
 __device__ __forceinline__ float act_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float act_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t act2_is_sat(uint32_t) { return 0u; }  // bf16 has fp32's range
 __device__ __forceinline__ act_t to_act(float v) { return __float2bfloat16_rn(v); }
 __device__ __forceinline__ float from_act(act_t v) { return __bfloat162float(v); }
 #endif

@@ -1,6 +1,6 @@
 // K-attn: fused flash-style softmax(Q K^T / 8) V for the 1/16-resolution mid block
-// (4 heads x d = 64, N = HW/256 tokens).  Scores never touch HBM.  Two kernels: the product path is the tcgen05
-// kernel at the end of this file; the mma.sync kernel below is kept as the A/B reference (CDC_ATTN_LEGACY=1).
+// (4 heads x d = 64, N = HW/256 tokens).  Scores never touch HBM.  The product path is the tcgen05 kernel at the end
+// of this file; the mma.sync kernel below is compiled only into the tools build (-DCDC_TOOLS) as its A/B reference.
 // Oracle counterpart: oracle/unet.py Attn.forward.
 #include "kernels.cuh"
 #include "launch.cuh"
@@ -8,8 +8,10 @@
 
 namespace cdc {
 
-constexpr int kAttD = 64, kAttBQ = 64, kAttBK = 64, kAttPitch = 72;  // bf16 elements per smem row
+constexpr int kAttD = 64;
 
+#ifdef CDC_TOOLS  // the mma.sync kernel is the A/B reference of tools/ builds only (libcdc_b200_tools.so)
+constexpr int kAttBQ = 64, kAttBK = 64, kAttPitch = 72;  // 16-bit elements per smem row
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool pred) {
     const int sz = pred ? 16 : 0;  // src-size 0 => zero fill
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
@@ -220,6 +222,8 @@ cudaError_t launch_attention(const act_t* qkv, act_t* o, int B, int N, int heads
     return launch_pdl(attention_kernel, grid, dim3(kAttThreads), kAttSmemBytes, s, qkv, o, N, heads);
 }
 
+#endif  // CDC_TOOLS
+
 // =====================================================================================================================
 // tcgen05 version: S = Q K^T and O_tile = P V run on the 5th-generation tensor cores with TMEM accumulators.
 //
@@ -267,6 +271,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
     const int T = (N + 127) / 128;
 
     if (threadIdx.x == 0) {
+        stamp_begin(p.stamp);
         prefetch_tensormap(&p.qkv_map);
         mbar_init(b_qf, 1);
         for (int i = 0; i < 2; ++i) {
@@ -462,6 +467,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
     }
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) stamp_end(p.stamp);
     if (warp == 1) tmem_dealloc(tmem, 512);
 }
 

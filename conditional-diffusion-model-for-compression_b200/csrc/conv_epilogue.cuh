@@ -5,6 +5,7 @@
 #include "conv_tc.cuh"
 #include "gn_sums.cuh"
 #include "ptx.cuh"
+#include "sampler.cuh"
 
 namespace cdc {
 
@@ -16,7 +17,8 @@ struct EpiArgs {
     float* x;
     act_t* xpad;
     float* x0_out;
-    float c0, c1;
+    SamplerCoef sc;
+    unsigned int* sat;  // saturation diagnostics counter (may be null)
 };
 
 template <int G>
@@ -68,14 +70,15 @@ __device__ __forceinline__ void conv_epilogue_tile(const EpiArgs& e, uint32_t ta
         tc_fence_before();
         mbar_arrive(bar_tempty);
         if (valid) {
+            const float ov[3] = {__uint_as_float(v[0]) + bs[0], __uint_as_float(v[1]) + bs[1], __uint_as_float(v[2]) + bs[2]};
+            const float xt[3] = {e.x[pix * 3 + 0], e.x[pix * 3 + 1], e.x[pix * 3 + 2]};
+            float x0[3], xn[3];
+            sampler_update3(e.sc, ov, xt, pix, x0, xn);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float x0 = __uint_as_float(v[c]) + bs[c];
-                const float xt = e.x[pix * 3 + c];
-                const float xn = e.c0 * fminf(fmaxf(x0, -1.0f), 1.0f) + e.c1 * xt;
-                e.x[pix * 3 + c] = xn;
-                e.xpad[pix * 64 + c] = to_act(xn);
-                if (e.x0_out) e.x0_out[pix * 3 + c] = x0;
+                e.x[pix * 3 + c] = xn[c];
+                e.xpad[pix * 64 + c] = to_act(xn[c]);
+                if (e.x0_out) e.x0_out[pix * 3 + c] = x0[c];
             }
         }
     } else {
@@ -90,6 +93,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const EpiArgs& e, uint32_t ta
         act_t* orow = e.out + pix * e.ldc + n0 + c0;
         const act_t* rrow = e.residual ? e.residual + pix * e.ldc + n0 + c0 : nullptr;
         const float msk = valid ? 1.0f : 0.0f;
+        float amax = 0.0f;
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
             uint32_t v[32];
@@ -133,6 +137,8 @@ __device__ __forceinline__ void conv_epilogue_tile(const EpiArgs& e, uint32_t ta
                         f[s4 * 8 + 6] += act_lo(r.w);
                         f[s4 * 8 + 7] += act_hi(r.w);
                     }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) amax = fmaxf(amax, fabsf(f[s4 * 8 + j]));
                     uint4 o;
                     o.x = pack_act2(f[s4 * 8 + 0], f[s4 * 8 + 1]);
                     o.y = pack_act2(f[s4 * 8 + 2], f[s4 * 8 + 3]);
@@ -143,6 +149,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const EpiArgs& e, uint32_t ta
             }
         }
         if (dbg) dbg[2] = clock64();
+        if (amax > kActMax && e.sat) atomicAdd(e.sat, 1u);
         if constexpr (EPI == EPI_STATS) {
             // warp butterfly -> 8 warps through smem -> one (sum, sum of squares) per (tile, group) -> integer atomics
             const float ws = warp_group_reduce<GH>(gs, lane);

@@ -41,6 +41,7 @@
 #include "gn_apply.cuh"
 #include "launch.cuh"
 #include "ptx.cuh"
+#include "sampler.cuh"
 
 namespace cdc {
 
@@ -102,6 +103,10 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
     // barriers: tfull[16] tempty[16] wres xfull[8] xempty[8] (x = fused residual conv) ... row_full[8] row_empty[8]
     const uint32_t bar_rfull = aux + 5376, bar_rempty = aux + 5376 + 64, bar_tfull = aux + 64, bar_tempty = aux + 192, bar_wres = aux + 320;
     const uint32_t bar_xfull = aux + 328, bar_xempty = aux + 392;
+    // weights land in consumption order, one barrier per (chunk, horizontal tap) group: the issuer starts the first input
+    // row as soon as the first group is in (p.wkw), instead of after the whole 72..166 KB block
+    constexpr int NWG = CH * (MODE == 1 ? 2 : 3);
+    const uint32_t bar_wg = aux + 5120;  // [NWG <= 12]
     const uint32_t bar_rready = aux + 5376 + 128;  // APPLY: [8] row chunk transformed (one arrive per warp of the owning group)
     const uint32_t bar_afull = APPLY ? bar_rready : bar_rfull;  // what the MMA issuer waits for
     volatile uint32_t* tmem_holder = reinterpret_cast<volatile uint32_t*>(aux_gen + 456);
@@ -129,6 +134,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
         p.dbg[514 + 3 * blockIdx.x] = smid;
     }
     const int units = p.batch * p.nseg * p.S;
+    if (threadIdx.x == 0) stamp_begin(p.stamp);
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&p.amap[0]);
@@ -146,35 +152,37 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
             mbar_init(bar_tempty + 8 * s, EPI == EPI_DDIM ? 128 : kEpiThreads);
         }
         mbar_init(bar_wres, 1);
+        for (int g = 0; g < NWG; ++g) mbar_init(bar_wg + 8 * g, 1);
         for (int s = 0; s < static_cast<int>(NRES); ++s) {
             mbar_init(bar_xfull + 8 * s, 1);
             mbar_init(bar_xempty + 8 * s, kEpiThreads);
         }
         fence_mbar_init();
-        // The weight block starts loading right away -- before the TMEM allocation and the CTA-wide sync (its barrier
-        // was initialised by this thread), and before griddepcontrol.wait: weights are constants.
+        // The weight block starts loading right away -- before the TMEM allocation and the CTA-wide sync (its barriers
+        // were initialised by this thread), and before griddepcontrol.wait: weights are constants.
         // smem block order [kw][chunk][2 - kh]: the kh taps of one (kw, chunk) form one contiguous B operand.
-        mbar_expect_tx(bar_wres, (NKH * NKW + (RES1 ? 1 : 0)) * CH * WB);
-        if constexpr (RES1)
-            for (int ch = 0; ch < CH; ++ch) tma_load_2d(wres1 + ch * WB, &p.rmap, bar_wres, ch * 64, cot * BN);
-        if constexpr (MODE == 2) {  // block order per (kw, chunk): kh = 2, 0 (the pair an odd input row feeds), then kh = 1
-            for (int kh = 0; kh < 3; ++kh)
-                for (int kw = 0; kw < 3; ++kw)
-                    for (int ch = 0; ch < CH; ++ch)
-                        tma_load_2d(wbase + ((kw * CH + ch) * 3 + (kh == 2 ? 0 : kh == 0 ? 1 : 2)) * WB, &p.wmap, bar_wres,
+        // Issue order = the order the MMAs consume them: chunk, then horizontal tap; group (chunk, kw) has its own barrier.
+        for (int ch = 0; ch < CH; ++ch)
+            for (int kw = 0; kw < NKW; ++kw) {
+                const uint32_t bar = bar_wg + 8 * (ch * NKW + kw);
+                mbar_expect_tx(bar, NKH * WB);
+                if constexpr (MODE == 2) {  // block order per (kw, chunk): kh = 2, 0 (the pair an odd input row feeds), then kh = 1
+                    for (int kh = 0; kh < 3; ++kh)
+                        tma_load_2d(wbase + ((kw * CH + ch) * 3 + (kh == 2 ? 0 : kh == 0 ? 1 : 2)) * WB, &p.wmap, bar,
                                     ((kh * 3 + kw) * CH + ch) * 64, cot * BN);
-        } else if constexpr (MODE == 0) {
-            for (int kh = 0; kh < 3; ++kh)
-                for (int kw = 0; kw < 3; ++kw)
-                    for (int ch = 0; ch < CH; ++ch)
-                        tma_load_2d(wbase + ((kw * CH + ch) * 3 + (2 - kh)) * WB, &p.wmap, bar_wres,
+                } else if constexpr (MODE == 0) {
+                    for (int kh = 0; kh < 3; ++kh)
+                        tma_load_2d(wbase + ((kw * CH + ch) * 3 + (2 - kh)) * WB, &p.wmap, bar,
                                     ((p.tr ? kw * 3 + kh : kh * 3 + kw) * CH + ch) * 64, cot * BN);  // transposed walk: taps swap roles
-        } else {  // pre-summed parity weights: K index ((parity * 4 + a * 2 + b) * CH + chunk) * 64
-            for (int a2 = 0; a2 < 2; ++a2)
-                for (int b2 = 0; b2 < 2; ++b2)
-                    for (int ch = 0; ch < CH; ++ch)
-                        tma_load_2d(wbase + ((b2 * CH + ch) * 2 + (1 - a2)) * WB, &p.wmap, bar_wres,
-                                    (((nt & 3) * 4 + a2 * 2 + b2) * CH + ch) * 64, cot * BN);
+                } else {  // pre-summed parity weights: K index ((parity * 4 + a * 2 + b) * CH + chunk) * 64; kw = b2
+                    for (int a2 = 0; a2 < 2; ++a2)
+                        tma_load_2d(wbase + ((kw * CH + ch) * 2 + (1 - a2)) * WB, &p.wmap, bar,
+                                    (((nt & 3) * 4 + a2 * 2 + kw) * CH + ch) * 64, cot * BN);
+                }
+            }
+        if constexpr (RES1) {  // the fused 1x1 conv's weights: used after the 3x3 taps of a chunk, loaded last
+            mbar_expect_tx(bar_wres, CH * WB);
+            for (int ch = 0; ch < CH; ++ch) tma_load_2d(wres1 + ch * WB, &p.rmap, bar_wres, ch * 64, cot * BN);
         }
     }
     if (warp == 2) {  // (warp-collective)
@@ -205,7 +213,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
 
     // (role dispatch by warpgroup first: with APPLY each warpgroup re-sizes its register allocation at the top of its branch)
     if (warp < 4) {
-    if constexpr (APPLY) setmaxnreg_dec<48>();
+    if constexpr (APPLY) setmaxnreg_dec<64>();
     if (warp == 0) {
         // ------------------------------------------------------------ input-row producer
         if (lane == 0) {
@@ -266,7 +274,13 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
             uint32_t rslot = 0, rpar = 0;
             uint32_t g = 0;  // running output-row counter: row j of the current strip uses accumulator (g + j) % NACC
             if (kdbg) p.dbg[502] = clock64();
-            mbar_wait(bar_wres, 0);
+            // weights: all groups up front, or (p.wkw) group by group while the first input row is issued
+            bool wpend = p.wkw != 0;
+            if (!wpend)
+                for (int g = 0; g < NWG; ++g) mbar_wait(bar_wg + 8 * g, 0);
+            if constexpr (RES1) {
+                if (!wpend) mbar_wait(bar_wres, 0);
+            }
             if (kdbg) p.dbg[503] = clock64();
             for (int u = cta; u < units; u += p.G1) {
                 int b, seg, si, h0, L;
@@ -334,12 +348,28 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                         const uint32_t npar = nslot == 0 ? rpar ^ 1 : rpar;
                         const uint32_t ready = more ? mbar_test_wait(bar_afull + 8 * nslot, npar) : 1u;
                         constexpr int TTH = TT / 2;
-                        if (cnt != 0 && elect_one_sync()) steps(std::integral_constant<int, 0>{}, std::integral_constant<int, TTH>{});
+                        if (wpend) {  // first input row of this CTA: the weight groups are still landing, issue tap by tap
+                            if constexpr (MODE == 2) {
+                                for (int kw = 0; kw < 3; ++kw) mbar_wait(bar_wg + 8 * (ch * 3 + kw), 0);
+                                if (cnt != 0 && elect_one_sync()) steps(std::integral_constant<int, 0>{}, std::integral_constant<int, TTH>{});
+                            } else {
+                                mbar_wait(bar_wg + 8 * (ch * NKW + 0), 0);
+                                if (cnt != 0 && elect_one_sync()) steps(std::integral_constant<int, 0>{}, std::integral_constant<int, 4>{});
+                                __syncwarp();
+                                if constexpr (TTH > 4) {
+                                    mbar_wait(bar_wg + 8 * (ch * NKW + 1), 0);
+                                    if (cnt != 0 && elect_one_sync()) steps(std::integral_constant<int, 4>{}, std::integral_constant<int, TTH>{});
+                                }
+                            }
+                        } else if (cnt != 0 && elect_one_sync()) {
+                            steps(std::integral_constant<int, 0>{}, std::integral_constant<int, TTH>{});
+                        }
                         __syncwarp();
                         if (dbg && pc == 0) p.dbg[i * 4 + 1] = clock64();
                         if (!ready) mbar_wait(bar_afull + 8 * nslot, npar);
                         if (more) tc_fence_after();
                         if (dbg && pc == 0) p.dbg[i * 4 + 2] = clock64();
+                        if (wpend && MODE != 2) mbar_wait(bar_wg + 8 * (ch * NKW + NKW - 1), 0);
                         if (elect_one_sync()) {
                             if (cnt != 0) steps(std::integral_constant<int, TTH>{}, std::integral_constant<int, TT>{});
                             if (RES1 && i >= 1 && i <= L) {  // fused 1x1 residual conv: centre tap, its own accumulator ring
@@ -366,15 +396,23 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                         if (nslot == 0) rpar ^= 1;
                     }
                     if (dbg) p.dbg[i * 4 + 3] = clock64();
+                    if (wpend) {  // every weight group has been waited for while row 0 was issued
+                        if constexpr (RES1) mbar_wait(bar_wres, 0);
+                        wpend = false;
+                    }
                 }
                 g += L;
+            }
+            if (wpend) {  // (a CTA without work must not exit under its own weight loads)
+                for (int g2 = 0; g2 < NWG; ++g2) mbar_wait(bar_wg + 8 * g2, 0);
+                if constexpr (RES1) mbar_wait(bar_wres, 0);
             }
             if (kdbg) p.dbg[505] = clock64();
         }
     }
     } else if (warp < 12) {
         // ------------------------------------------------------------ epilogue (8 warps)
-        if constexpr (APPLY) setmaxnreg_inc<152>();
+        if constexpr (APPLY) setmaxnreg_inc<144>();
         const int q = warp & 3;            // TMEM sub-partition: lanes 32q .. 32q+31
         const int half = (warp - 4) >> 2;  // column half of the accumulator
         const int row = q * 32 + lane;
@@ -382,6 +420,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
         if constexpr (EPI == EPI_DDIM) {
             // 3 real output channels: thread = pixel.  The two warp groups (half 0 / 1) take alternate output rows.
             const float b0 = bias_s[0], b1 = bias_s[1], b2 = bias_s[2];
+            const SamplerCoef sc{p.c0, p.c1, p.e0, p.e1, p.sg, p.seed, p.step};
             const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
             if (half == 0) {
                 for (int s_ = 0; s_ < static_cast<int>(NACC); ++s_) {  // arm every accumulator: zero, then the first "drained" arrive
@@ -423,14 +462,13 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                     tc_fence_before();
                     mbar_arrive(bar_tempty + 8 * slot);
                     if (valid) {
-                        const float bb[3] = {b0, b1, b2};
-                        float xn[3];
+                        const float ov[3] = {__uint_as_float(v[0]) + b0, __uint_as_float(v[1]) + b1, __uint_as_float(v[2]) + b2};
+                        float x0[3], xn[3];
+                        sampler_update3(sc, ov, xt, pix, x0, xn);
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
-                            const float x0 = __uint_as_float(v[c]) + bb[c];
-                            xn[c] = p.c0 * fminf(fmaxf(x0, -1.0f), 1.0f) + p.c1 * xt[c];
                             p.x[pix * 3 + c] = xn[c];
-                            if (p.x0_out) p.x0_out[pix * 3 + c] = x0;
+                            if (p.x0_out) p.x0_out[pix * 3 + c] = x0[c];
                         }
                         // channels 0..2 of the stem's 64-channel x_t copy and the (always zero) channel 3: one 8-byte store
                         uint2 pk;
@@ -471,6 +509,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                 float gs[GH], gq[GH];
 #pragma unroll
                 for (int i = 0; i < GH; ++i) gs[i] = gq[i] = 0.0f;
+                float amax = 0.0f;  // largest |output| of this thread over the strip (saturation diagnostics)
                 for (int j = 0; j < L; ++j, ++tile_ctr) {
                     const uint32_t gj = g + j, slot = gj % NACC;
                     if constexpr (RES1) {  // the fused 1x1 conv's row j (complete one input row before the 3x3's)
@@ -524,7 +563,10 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                     if (edbg) edbg[2] = clock64();
                     float f[HC];
 #pragma unroll
-                    for (int c = 0; c < HC; ++c) f[c] = __uint_as_float(v[c]) + bias_r[c];
+                    for (int c = 0; c < HC; ++c) {
+                        f[c] = __uint_as_float(v[c]) + bias_r[c];
+                        amax = fmaxf(amax, fabsf(f[c]));
+                    }
                     if constexpr (EPI == EPI_STATS) {
 #pragma unroll
                         for (int c = 0; c < HC; ++c) {
@@ -579,6 +621,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                     if (edbg) edbg[6] = clock64();
                 }
                 g += L;
+                if (valid && amax > kActMax && p.sat) atomicAdd(p.sat, 1u);  // stored saturated (act.cuh pack_act2)
                 if constexpr (EPI == EPI_STATS) {
                     // one (sum, sum of squares) per (strip, group): warp butterfly -> 4 lane quarters through smem -> integer atomics
                     const float ws = warp_group_reduce<GH>(gs, lane);
@@ -597,7 +640,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                         const float* r0 = red + ((hh * 4) * 16 + gl) * 2;
                         const float s = ((r0[0] + r0[32]) + r0[64]) + r0[96];
                         const float s2 = ((r0[1] + r0[33]) + r0[65]) + r0[97];
-                        gn_sums_add(p.gn_acc + static_cast<size_t>(b) * 64, cot * (BN / CPG) + t, s, s2);
+                        gn_sums_add(p.gn_acc + static_cast<size_t>(b) * kGnImgStride, cot * (BN / CPG) + t, s, s2);
                     }
                 }
             }
@@ -619,7 +662,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
         constexpr int NIT = (130 + kKfXfPix - 1) / kKfXfPix;  // 9 passes of 16 pixels, done as 3 x 3 (64-register budget)
         static_assert(kKfXfPix % 8 == 0 && NIT == 9, "a pixel's swizzle phase must not depend on the pass");
         constexpr int cpg_in = CH * 2;  // channels per group of the input (C_in / 32)
-        const double inv_n = kGnFixInv / (static_cast<double>(cpg_in) * p.H * p.W);
+        const double inv_n = 1.0 / (static_cast<double>(cpg_in) * p.H * p.W);
         float2* coef_g = coef_s + grp * (CH * 64);  // each group keeps its own table: no cross-group barrier
         uint32_t n = 0;  // chunk counter of the CTA (all chunks; this group handles n % 2 == grp)
         int cur_b = -1;
@@ -630,7 +673,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
             if (b != cur_b) {  // coefficient table of image b (once per CTA when the batch is 1)
                 named_bar_sync(3 + grp, kKfXfThreads);
                 if (xt < CH * 64) {  // (every thread derives its channel's group statistics itself: a few FP64 operations)
-                    const float2 mr = gn_mean_rstd(p.in_acc + (static_cast<size_t>(b) * 32 + xt / cpg_in) * 2, inv_n, p.in_eps);
+                    const float2 mr = gn_mean_rstd(p.in_acc + (static_cast<size_t>(b) * 32 + xt / cpg_in) * kGnVals, inv_n, p.in_eps);
                     const float sc = p.in_film ? 1.0f + p.in_film[xt] : 1.0f, sh = p.in_film ? p.in_film[CH * 64 + xt] : 0.0f;
                     const float2 ab = gn_fold(p.in_gamma[xt], p.in_beta[xt], sc, sh, mr);
                     coef_g[xt] = make_float2(0.5f * ab.x, 0.5f * ab.y);  // (a/2, b/2): see silu_h
@@ -690,6 +733,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
 
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) stamp_end(p.stamp);
     if (kdbg) {
         p.dbg[506] = clock64();
         unsigned long long gt;
@@ -730,25 +774,21 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
     KF_CASE(64, 1, EPI_STORE, 1, true, false, 2, false, false)      \
     KF_CASE(64, 1, EPI_STORE, 2, false, false, 2, false, false)
 
-static int kf_ring_max_ch1() {  // CDC_KF_RING=n: ring slots of the one-chunk convs (A/B)
-    const char* e = getenv("CDC_KF_RING");
-    const int n = e ? atoi(e) : 6;
-    return n < 3 ? 3 : n > kKfMaxSlots ? kKfMaxSlots : n;
-}
 
 int kf_smem_bytes(int bn, int CH, int NS, bool staged, int mode, bool res) {
     return 1024 + NS * kKfRowBytes + ((mode == 1 ? 4 : 9) + (res ? 1 : 0)) * CH * bn * 128 + (staged ? 2 * 128 * bn * 2 : 0) + kKfAux;
 }
 
-bool kf_plan(int bn, int CH, int mode, bool res, int epi, int* NS, bool* staged) {
+bool kf_plan(int bn, int CH, int mode, bool res, int epi, int* NS, bool* staged, int ring_ch1) {
     const int limit = 227 * 1024;
+    ring_ch1 = ring_ch1 < 3 ? 3 : ring_ch1 > kKfMaxSlots ? kKfMaxSlots : ring_ch1;
     for (int st = (mode == 1 || res) ? 0 : 1; st >= 0; --st) {  // NS = ring slots of one (row, chunk) each
         if (st && bn != 64) continue;
         // (a single staging buffer + a 3-slot ring for the two-chunk store-only stem was tried: 35 -> 43 us)
         (void)epi;
         // (stride 2: two slots per (row, chunk); one-chunk convs: a deeper ring where shared memory allows -- the input
         // transform adds a pipeline stage)
-        for (int ns = mode == 2 ? kKfMaxSlots : CH == 1 ? kf_ring_max_ch1() : 4; ns >= (mode == 2 ? 4 : 3); --ns)
+        for (int ns = mode == 2 ? kKfMaxSlots : CH == 1 ? ring_ch1 : 4; ns >= (mode == 2 ? 4 : 3); --ns)
             if (kf_smem_bytes(bn, CH, ns, st != 0, mode, res) <= limit) {
                 *NS = ns;
                 *staged = st != 0;
@@ -758,10 +798,13 @@ bool kf_plan(int bn, int CH, int mode, bool res, int epi, int* NS, bool* staged)
     return false;
 }
 
-bool kf_inst_ok(int bn, int cpg, int epi, int CH, int mode, bool res, bool apply) {
+bool kf_inst_ok(int bn, int cpg, int epi, int CH, int mode, bool res, bool apply, int ring_ch1) {
     int ns;
     bool st;
-    if (!kf_plan(bn, CH, mode, res, epi, &ns, &st)) return false;
+    if (!kf_plan(bn, CH, mode, res, epi, &ns, &st, ring_ch1)) return false;
+    // APPLY: transform group g owns the chunks n = g (mod 2) and waits on ring slot n % NS by parity -- sound only when
+    // a slot always belongs to the same group, i.e. for an EVEN ring
+    if (apply && (ns & 1)) return false;
 #define KF_CASE(BN_, CPG_, EPI_, CH_, ST_, X_, M_, R_, A_) \
     if (bn == BN_ && (EPI_ != EPI_STATS || cpg == CPG_) && epi == EPI_ && CH == CH_ && st == ST_ && mode == M_ && res == R_ && apply == A_) return true;
     KF_ALL_CASES()
@@ -781,12 +824,11 @@ cudaError_t configure_kf_kernels() {
 }
 
 cudaError_t launch_conv_kf(const KfParams& p, int bn, int cpg, int epi, int CH, bool xk16, int mode, bool res, bool apply,
-                           cudaStream_t stream) {
-    int ns;
-    bool st;
-    if (!kf_plan(bn, CH, mode, res, epi, &ns, &st) || ns != p.NS) return cudaErrorInvalidValue;
+                           bool st, cudaStream_t stream) {
+    if (p.NS < 3 || p.NS > kKfMaxSlots || (apply && (p.NS & 1))) return cudaErrorInvalidValue;
     const dim3 grid(p.n_tiles * p.G1), block(128 + kEpiThreads + (apply ? kKfXfExtra : 0));
-    const size_t smem = kf_smem_bytes(bn, CH, ns, st, mode, res);
+    const size_t smem = kf_smem_bytes(bn, CH, p.NS, st, mode, res);
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
 #define KF_CASE(BN_, CPG_, EPI_, CH_, ST_, X_, M_, R_, A_)                                                                                \
     if (bn == BN_ && (EPI_ != EPI_STATS || cpg == CPG_) && epi == EPI_ && CH == CH_ && st == ST_ && xk16 == X_ && mode == M_ && res == R_ && \
         apply == A_)                                                                                                                         \

@@ -24,10 +24,10 @@ struct alignas(64) KfParams {
     act_t* res_out;       // fused 1x1 residual conv (same input, centre tap only): output tensor, channels, bias
     int res_ldc;
     const float* res_bias;
-    gn_sum_t* gn_acc;     // EPI_STATS: [batch][32][2] fixed-point accumulators (gn_sums.cuh), zero on entry
+    gn_sum_t* gn_acc;     // EPI_STATS: [batch][32][kGnVals] fixed-point accumulators (gn_sums.cuh), zero on entry
     // APPLY: the input is the raw output of the preceding conv; GroupNorm (+ FiLM) + SiLU of THAT conv's statistics is
     // applied to every input row in shared memory before the MMAs read it (replaces a gn_apply_kernel pass over HBM)
-    const gn_sum_t* in_acc;   // [batch][32][2] totals of the input tensor (complete: written by the preceding kernel)
+    const gn_sum_t* in_acc;   // [batch][32][kGnVals] totals of the input tensor (complete: written by the preceding kernel)
     const float* in_gamma;    // [C_in]
     const float* in_beta;
     const float* in_film;     // [2 * C_in] (scale | shift) of this step, or null
@@ -36,6 +36,12 @@ struct alignas(64) KfParams {
     act_t* xpad;
     float* x0_out;
     float c0, c1;
+    float e0, e1, sg;     // generalised sampler update (see ConvParams)
+    unsigned long long seed;
+    int step;
+    long long* stamp;     // diagnostics, may be null (see ConvParams)
+    unsigned int* sat;
+    int wkw;              // 1: the issuer starts as soon as the first horizontal tap's weights have landed (one barrier per kw)
     long long* dbg;       // optional: issuer / epilogue timeline of CTA 0 (clock64 stamps), tools only
 };
 
@@ -43,11 +49,12 @@ struct alignas(64) KfParams {
 // mode 2: 3x3 conv with stride 2 (H, W of KfParams are the OUTPUT grid)
 // res: the ResBlock's 1x1 residual conv rides along (its weights are resident too, its accumulators share TMEM)
 // apply: GroupNorm + SiLU of the input applied in shared memory (see in_acc)
-bool kf_inst_ok(int bn, int cpg, int epi, int CH, int mode, bool res, bool apply = false);
-bool kf_plan(int bn, int CH, int mode, bool res, int epi, int* NS, bool* staged);  // shared-memory plan; false if the weights do not fit
+// ring_ch1: input-ring slots wanted for one-chunk convs (default 6)
+bool kf_inst_ok(int bn, int cpg, int epi, int CH, int mode, bool res, bool apply = false, int ring_ch1 = 6);
+bool kf_plan(int bn, int CH, int mode, bool res, int epi, int* NS, bool* staged, int ring_ch1 = 6);  // shared-memory plan; false if the weights do not fit
 int kf_smem_bytes(int bn, int CH, int NS, bool staged, int mode, bool res);
 cudaError_t configure_kf_kernels();
 cudaError_t launch_conv_kf(const KfParams& p, int bn, int cpg, int epi, int CH, bool xk16, int mode, bool res, bool apply,
-                           cudaStream_t stream);  // xk16: chunk 0 has 16 real channels (stem)
+                           bool staged, cudaStream_t stream);  // xk16: chunk 0 has 16 real channels (stem)
 
 }  // namespace cdc

@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int BWl = p.bw_log2, BW = 1 << BWl, BH = 128 >> BWl;
     const int total_tiles = p.n_tiles * p.nphase * p.batch * p.tiles_h * p.tiles_w;
+    if (threadIdx.x == 0) stamp_begin(p.stamp);
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&p.wmap);
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
         const int half = (warp - 4) >> 2;  // column half of the accumulator
         const int row = q * 32 + lane;
         const int ty = row >> BWl, tx = row & (BW - 1);
-        const EpiArgs ea{p.out, p.residual, p.ldc, p.x, p.xpad, p.x0_out, p.c0, p.c1};
+        const EpiArgs ea{p.out, p.residual, p.ldc, p.x, p.xpad, p.x0_out, SamplerCoef{p.c0, p.c1, p.e0, p.e1, p.sg, p.seed, p.step}, p.sat};
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             int nt, ph, b, th, tw;
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
             mbar_wait(bar_tfull + 8 * as, aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE;
-            gn_sum_t* sdst = (EPI == EPI_STATS) ? p.gn_acc + (static_cast<size_t>(b) * 32 + nt * (BN / CPG)) * 2 : nullptr;
+            gn_sum_t* sdst = (EPI == EPI_STATS) ? p.gn_acc + (static_cast<size_t>(b) * 32 + nt * (BN / CPG)) * kGnVals : nullptr;
             conv_epilogue_tile<BN, CPG, EPI>(ea, taddr, bar_tempty + 8 * as, bias_s + nt * BN,
                                              red_s + (it & 1) * (2 * 4 * 16 * 2), q, half, lane, valid, pix, nt * BN, sdst);
         }
@@ -184,6 +185,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
 
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) stamp_end(p.stamp);
     if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 

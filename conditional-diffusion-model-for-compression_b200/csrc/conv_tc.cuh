@@ -48,12 +48,21 @@ struct alignas(64) ConvParams {
     act_t* out;
     const float* bias;                 // [n_total]
     const act_t* residual;     // optional, same layout as out
-    gn_sum_t* gn_acc;                  // EPI_STATS: [batch][32][2] fixed-point accumulators (gn_sums.cuh), zero on entry
+    gn_sum_t* gn_acc;                  // EPI_STATS: [batch][32][kGnVals] fixed-point accumulators (gn_sums.cuh), zero on entry
     // EPI_DDIM
     float* x;                          // [B*H*W][3] fp32, updated in place
     act_t* xpad;               // [B*H*W][64] bf16, channels 0..2 rewritten
     float* x0_out;                     // optional [B*H*W][3] raw x0_hat
     float c0, c1;
+    // generalised sampler update (oracle/sampler.py ddim_update): x0 = e0*x_t + e1*out; x_prev = c0*clamp(x0) + c1*x_t + sg*z
+    // (X-parameterised deterministic DDIM: e0 = 0, e1 = 1, sg = 0); z = Philox noise of (seed, step, pixel) -- sampler.cuh
+    float e0, e1, sg;
+    unsigned long long seed;
+    int step;
+    // diagnostics (either may be null): [0] = earliest CTA start, [1] = latest CTA end (globaltimer ns, atomic min / max);
+    // number of (thread, tile) epilogue passes that met a value beyond the fp16 range (stored saturated)
+    long long* stamp;
+    unsigned int* sat;
 };
 
 // Launches the instantiation for (bn, cpg, epi).  Returns cudaErrorInvalidValue when that

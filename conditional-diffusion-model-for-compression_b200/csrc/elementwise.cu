@@ -16,8 +16,9 @@ constexpr int kStatsPix = 64;
 
 // (tensors written by the preceding kernel are read through plain pointers, not const __restrict__: under PDL the
 // kernel is resident before that data is final, so the non-coherent read-only path must not be used for them)
-__global__ void __launch_bounds__(256) gn_stats_kernel(const act_t* x, gn_sum_t* acc, int HW, int C) {
+__global__ void __launch_bounds__(256) gn_stats_kernel(const act_t* x, gn_sum_t* acc, int HW, int C, long long* stamp) {
     __shared__ float s_sum[8][512], s_sq[8][512];  // [row-in-pass][channel] (C <= 512)
+    if (threadIdx.x == 0) stamp_begin(stamp);
     pdl_wait();
     pdl_launch_dependents();  // (after the wait: see launch.cuh)
     const int b = blockIdx.y, pt = blockIdx.x;
@@ -67,14 +68,15 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const act_t* x, gn_sum_t*
             a += c_sum[t * cpg + j];
             d += c_sq[t * cpg + j];
         }
-        gn_sums_add(acc + static_cast<size_t>(b) * 64, t, a, d);
+        gn_sums_add(acc + static_cast<size_t>(b) * kGnImgStride, t, a, d);
     }
+    if (threadIdx.x == 0) stamp_end(stamp);
 }
 
-cudaError_t launch_gn_stats(const act_t* x, gn_sum_t* acc, int B, int HW, int C, cudaStream_t s) {
+cudaError_t launch_gn_stats(const act_t* x, gn_sum_t* acc, int B, int HW, int C, cudaStream_t s, long long* stamp) {
     if (C % 32 != 0 || C > 512 || C < 32) return cudaErrorInvalidValue;
     const int PT = (HW + kStatsPix - 1) / kStatsPix;
-    return launch_pdl(gn_stats_kernel, dim3(PT, B), dim3(256), 0, s, x, acc, HW, C);
+    return launch_pdl(gn_stats_kernel, dim3(PT, B), dim3(256), 0, s, x, acc, HW, C, stamp);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -89,14 +91,16 @@ struct GnCoef {
     const float* film;     // [2C] (scale | shift) of this step, or null
     int C, HW;
     float eps;
+    long long* stamp;   // diagnostics, may be null
+    unsigned int* sat;  // counts threads that stored a saturated value (residual path), may be null
 };
 // (mean, rstd) of every (image, group), once per CTA: exact integer totals -> double mean / variance (a handful of
 // FP64 multiply-adds), rstd in fp32 (MUFU rsqrt + one Newton step, < 1 ulp) like the oracle's fp32 group_norm.
 __device__ __forceinline__ void gn_group_stats(const GnCoef& g, int B, float2* s_mr) {
     const int cpg = g.C / 32;
-    const double inv_n = kGnFixInv / (static_cast<double>(cpg) * g.HW);
+    const double inv_n = 1.0 / (static_cast<double>(cpg) * g.HW);
     for (int i = threadIdx.x; i < B * 32; i += blockDim.x) {
-        s_mr[i] = gn_mean_rstd(g.acc + static_cast<size_t>(i) * 2, inv_n, g.eps);
+        s_mr[i] = gn_mean_rstd(g.acc + static_cast<size_t>(i) * kGnVals, inv_n, g.eps);
     }
     __syncthreads();
 }
@@ -144,6 +148,7 @@ template <bool SILU, bool RES>
 __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const uint4* x, const uint4* r, uint4* y, long long nvec, int vecs_per_pix,
                                                           long long vecs_per_img, const GnCoef g, int B) {
     extern __shared__ float2 s_mr[];  // [B][32] (mean, rstd)
+    if (threadIdx.x == 0) stamp_begin(g.stamp);
     pdl_wait();
     pdl_launch_dependents();  // (after the wait: see launch.cuh)
     const long long stride = gridDim.x * 256LL;
@@ -159,6 +164,7 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const uint4* x, const 
         cur_b = (single || i >= nvec) ? 0 : static_cast<int>(i / vecs_per_img);
         gn_coef(k, s_mr, cur_b, cv * 8, cpg, c);
     }
+    uint32_t satm = 0u;
     for (; i < nvec; i += 2 * stride) {
         const long long i2 = i + stride;
         const bool has2 = i2 < nvec;
@@ -176,7 +182,9 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const uint4* x, const 
             gn_coef(k, s_mr, b, cv * 8, cpg, c);
             cur_b = b;
         }
-        y[i] = gn_apply_vec<SILU, RES>(u0, r0, c);
+        const uint4 y0 = gn_apply_vec<SILU, RES>(u0, r0, c);
+        y[i] = y0;
+        if (RES) satm |= act2_is_sat(y0.x) | act2_is_sat(y0.y) | act2_is_sat(y0.z) | act2_is_sat(y0.w);
         if (has2) {
             b = single ? 0 : static_cast<int>(i2 / vecs_per_img);
             if (b != cur_b) {
@@ -185,13 +193,18 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const uint4* x, const 
                 gn_coef(k, s_mr, b, cv * 8, cpg, c);
                 cur_b = b;
             }
-            y[i2] = gn_apply_vec<SILU, RES>(u1, r1, c);
+            const uint4 y1 = gn_apply_vec<SILU, RES>(u1, r1, c);
+            y[i2] = y1;
+            if (RES) satm |= act2_is_sat(y1.x) | act2_is_sat(y1.y) | act2_is_sat(y1.z) | act2_is_sat(y1.w);
         }
     }
+    if (RES && satm != 0u && g.sat) atomicAdd(g.sat, 1u);
+    if (threadIdx.x == 0) stamp_end(g.stamp);
 }
 
 cudaError_t launch_gn_apply(const act_t* x, const gn_sum_t* acc, const float* gamma, const float* beta, const float* film,
-                            float eps, const act_t* r, act_t* y, int B, int HW, int C, int silu, int num_sms, cudaStream_t s) {
+                            float eps, const act_t* r, act_t* y, int B, int HW, int C, int silu, int num_sms, cudaStream_t s,
+                            long long* stamp, unsigned int* sat) {
     const long long nvec = static_cast<long long>(B) * HW * C / 8;
     const int vpp = C / 8;
     const long long vpi = static_cast<long long>(HW) * vpp;
@@ -206,7 +219,7 @@ cudaError_t launch_gn_apply(const act_t* x, const gn_sum_t* acc, const float* ga
     const uint4* rv = reinterpret_cast<const uint4*>(r);
     uint4* yv = reinterpret_cast<uint4*>(y);
     const dim3 g(static_cast<unsigned>(grid)), blk(256);
-    const GnCoef gc{acc, gamma, beta, film, C, HW, eps};
+    const GnCoef gc{acc, gamma, beta, film, C, HW, eps, stamp, sat};
     const size_t sm = static_cast<size_t>(B) * 32 * sizeof(float2);
     if (sm > 48 * 1024) return cudaErrorInvalidValue;
     if (silu && r) return launch_pdl(gn_apply_kernel<true, true>, g, blk, sm, s, xv, rv, yv, nvec, vpp, vpi, gc, B);

@@ -44,17 +44,20 @@ __device__ __forceinline__ uint4 gn_apply_vec(const uint4 u, const uint4 rr, con
             v0 += act_lo(rw[j]);
             v1 += act_hi(rw[j]);
         }
-        o[j] = pack_act2_nosat(v0, v1);  // |SiLU(GN(x))| (+ residual) cannot reach the fp16 limit
+        // |SiLU(GN(x))| alone cannot reach the fp16 limit; with the residual added it can (trained weights): saturate
+        o[j] = RES ? pack_act2(v0, v1) : pack_act2_nosat(v0, v1);
     }
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 // (mean, rstd) of one (image, group) from its fixed-point totals: exact integer totals -> double mean / variance
 // (a handful of FP64 multiply-adds), rstd in fp32 (MUFU rsqrt + one Newton step, < 1 ulp) like the oracle's fp32 group_norm.
-// inv_n = kGnFixInv / (channels per group * pixels)
-__device__ __forceinline__ float2 gn_mean_rstd(const gn_sum_t* a, double inv_n, float eps) {
-    const double m = static_cast<double>(a[0]) * inv_n;
-    const double var = static_cast<double>(a[1]) * inv_n - m * m;
+// inv_cnt = 1 / (channels per group * pixels)
+__device__ __forceinline__ float2 gn_mean_rstd(const gn_sum_t* a, double inv_cnt, float eps) {
+    double s, q;
+    gn_sums_read(a, s, q);
+    const double m = s * inv_cnt;
+    const double var = q * inv_cnt - m * m;
     const float v = fmaxf(static_cast<float>(var), 0.0f) + eps;
     float r = rsqrtf(v);
     r = r * (1.5f - 0.5f * v * r * r);

@@ -11,11 +11,12 @@ namespace cdc {
 // ---- GroupNorm (oracle/unet.py RB / Attn) -------------------------------
 // Statistics are fixed-point integer accumulators [B][32 groups][2] (gn_sums.cuh), zero on entry, filled by the conv
 // epilogues or by gn_stats (where the producer is not a conv: attention input).
-cudaError_t launch_gn_stats(const act_t* x, gn_sum_t* acc, int B, int HW, int C, cudaStream_t s);
+cudaError_t launch_gn_stats(const act_t* x, gn_sum_t* acc, int B, int HW, int C, cudaStream_t s, long long* stamp = nullptr);
 // y = act(GN(x) * (1 + film_scale) + film_shift) (+ r); act = SiLU if silu != 0; film may be null.  In place allowed.
 // The normalisation coefficients are derived from `acc` inside the kernel (no finalize pass).
 cudaError_t launch_gn_apply(const act_t* x, const gn_sum_t* acc, const float* gamma, const float* beta, const float* film,
-                            float eps, const act_t* r, act_t* y, int B, int HW, int C, int silu, int num_sms, cudaStream_t s);
+                            float eps, const act_t* r, act_t* y, int B, int HW, int C, int silu, int num_sms, cudaStream_t s,
+                            long long* stamp = nullptr, unsigned int* sat = nullptr);
 
 // ---- time embedding + FiLM (C8; oracle/unet.py TimeEmbed, RB.film) ----------------------------
 struct FilmLayer {
@@ -51,14 +52,17 @@ cudaError_t launch_repack_weight_up2(const float* src, act_t* dst, int O, int I,
 
 // ---- attention (C7; oracle/unet.py Attn) --------------------------------------------------------
 // qkv [B*N][768] act_t (q | k | v, head h = channels 64h..64h+63) -> o [B*N][256] bf16
-cudaError_t launch_attention(const act_t* qkv, act_t* o, int B, int N, int heads, cudaStream_t s);
+#ifdef CDC_TOOLS
+cudaError_t launch_attention(const act_t* qkv, act_t* o, int B, int N, int heads, cudaStream_t s);  // mma.sync A/B reference
 cudaError_t configure_attention();  // dynamic shared-memory limit (call once, outside graph capture)
+#endif
 // tcgen05 version (attention.cu): qkv_map = 3-D tensor map {768 cols, N rows, B} of the qkv tensor, box {64, 128, 1},
 // 128-byte swizzle (built by the host runtime)
 struct alignas(64) AttnTcParams {
     CUtensorMap qkv_map;
     act_t* out;  // [B*N][heads * 64]
     int N, heads;
+    long long* stamp;  // diagnostics, may be null (ptx.cuh stamp_begin / stamp_end)
 };
 cudaError_t configure_attention_tc();
 cudaError_t launch_attention_tc(const AttnTcParams& p, int B, cudaStream_t s);

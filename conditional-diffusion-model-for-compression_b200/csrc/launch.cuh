@@ -5,7 +5,7 @@
 // order 29.37 ms / image, PDL with early triggers in the convs 30.15 ms, early triggers everywhere 30.67 ms (a dependent
 // grid that is triggered before its predecessor's CTAs are all resident takes their SMs).  The kernels now trigger right
 // AFTER their own griddepcontrol.wait (every CTA of the kernel is resident by then): 25.52 ms with PDL against 25.47 ms
-// without -- no loss, but no gain either, so PDL stays OFF unless CDC_PDL=1 is set in the environment.
+// without -- no loss, but no gain either, so PDL stays OFF (the tools build, -DCDC_TOOLS, enables it with CDC_PDL=1).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdlib.h>
@@ -15,8 +15,12 @@
 namespace cdc {
 
 inline bool pdl_enabled() {
+#ifdef CDC_TOOLS
     static const bool on = getenv("CDC_PDL") != nullptr;
     return on;
+#else
+    return false;  // the product build reads no environment variables
+#endif
 }
 
 template <typename... KArgs, typename... Args>

@@ -63,13 +63,17 @@ __device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity
         : "memory");
     return ok;
 }
-// Bounded wait: a protocol bug must trap (sticky launch failure), never hang the GPU box.
+// Bounded wait: a protocol bug must trap (sticky launch failure), never hang the GPU box.  The tools build also says
+// which barrier (printf's argument buffer, inlined at every wait site, costs the 48..64-register producer / issuer warps
+// of the APPLY kernels spills, so the product build only traps).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 8000000000LL) {  // ~4 s at 2 GHz
+#ifdef CDC_TOOLS
             printf("cdc: mbarrier timeout block %d thread %d bar 0x%x parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
+#endif
             __trap();
         }
     }
@@ -298,6 +302,21 @@ template <int N>
 __device__ __forceinline__ void setmaxnreg_dec() {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
+// In-graph timing stamps (diagnostics): slot[0] = earliest CTA start, slot[1] = latest CTA end of a launch, in
+// globaltimer nanoseconds; the host initialises the slot to (~0, 0).  One thread per CTA calls each, so the cost is two
+// atomics per CTA -- and nothing when the pointer is null (the product's decode graph).
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void stamp_begin(long long* slot) {
+    if (slot) atomicMin(reinterpret_cast<unsigned long long*>(slot), globaltimer_ns());
+}
+__device__ __forceinline__ void stamp_end(long long* slot) {
+    if (slot) atomicMax(reinterpret_cast<unsigned long long*>(slot) + 1, globaltimer_ns());
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -12,13 +12,14 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <functional>
 #include <map>
 #include <memory>
 #include <string>
 #include <vector>
 
-#include "../../include/cdc_b200.h"
+#include "../../include/cdc_b200_tools.h"
 #include "conv_kf.cuh"
 #include "conv_tc.cuh"
 #include "kernels.cuh"
@@ -26,6 +27,41 @@
 namespace cdc {
 
 static std::string g_create_err;
+
+// Planner decisions that tests / tools A/B through cdc_set_plan_option (include/cdc_b200_tools.h).  The product build
+// reads NO environment variables; the tools build (-DCDC_TOOLS) lets the environment override the defaults.
+struct PlanOpts {
+    int v[CDC_OPT_COUNT] = {2, 1, 1, 0, 6, 1};
+    int fuse_apply_max_tiles() const { return v[CDC_OPT_FUSE_APPLY]; }
+    bool kf() const { return v[CDC_OPT_KF] != 0; }
+    bool kf_s2() const { return v[CDC_OPT_KF_S2] != 0; }
+    long kf_min_pixels() const { return v[CDC_OPT_KF_MIN_PIXELS]; }
+    int kf_ring() const { return v[CDC_OPT_KF_RING]; }
+    bool weight_groups() const { return v[CDC_OPT_WEIGHT_GROUPS] != 0; }
+};
+static PlanOpts default_plan_opts() {
+    PlanOpts o;
+#ifdef CDC_TOOLS
+    const char* names[CDC_OPT_COUNT] = {"CDC_FUSE_APPLY", "CDC_KF", "CDC_KF_S2", "CDC_KF_MIN_PIXELS", "CDC_KF_RING", "CDC_WEIGHT_GROUPS"};
+    for (int i = 0; i < CDC_OPT_COUNT; ++i)
+        if (const char* e = getenv(names[i])) o.v[i] = atoi(e);
+    if (getenv("CDC_NO_KF")) o.v[CDC_OPT_KF] = 0;
+#endif
+    return o;
+}
+
+// Every entry point that takes a cdc_ctx runs on the context's device and restores the caller's current device on
+// exit (a Decoder on cuda:1 must work -- and must not move the process -- while cuda:0 is current).
+struct DevGuard {
+    int prev = -1, dev;
+    explicit DevGuard(int d) : dev(d) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DevGuard() {
+        if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+    }
+};
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -58,7 +94,14 @@ struct ConvW {  // repacked conv weights: act_t [n_pad][taps][c_pad], fp32 bias 
 struct Op {
     std::string name;
     double flops = 0, bytes = 0;
-    std::function<cudaError_t(cudaStream_t, int)> run;
+    // (stream, sampler step k, timing slot or null): see ptx.cuh stamp_begin / stamp_end
+    std::function<cudaError_t(cudaStream_t, int, long long*)> run;
+};
+
+// per-step sampler coefficients (host copies; oracle/sampler.py make_schedule)
+struct SamplerTab {
+    std::vector<float> c0, c1, e0, e1, sg;
+    unsigned long long seed = 0;
 };
 
 enum ConvMode { MODE_S1 = 0, MODE_S2 = 1, MODE_UP2 = 2 };
@@ -103,8 +146,8 @@ struct ConvBuild {
     float* x = nullptr;
     act_t* xpad = nullptr;
     float* x0_out = nullptr;
-    const std::vector<float>* c0 = nullptr;  // per-step sampler coefficients (host)
-    const std::vector<float>* c1 = nullptr;
+    const SamplerTab* samp = nullptr;  // per-step sampler coefficients (host)
+    unsigned int* sat = nullptr;       // saturation diagnostics counter (device)
     long long* dbg = nullptr;  // kf kernel issuer / epilogue timeline (tools)
     // fused 1x1 residual conv of the same input (kf path only; build_conv reports whether it was taken)
     const ConvW* res_w = nullptr;
@@ -148,10 +191,12 @@ static int encode_qkv_map(CUtensorMap* m, const act_t* qkv, int cols, int N, int
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
 }
-static bool attention_legacy() {  // A/B switch: the mma.sync kernel
+#ifdef CDC_TOOLS
+static bool attention_legacy() {  // A/B switch of the tools build: the mma.sync kernel
     static const bool v = getenv("CDC_ATTN_LEGACY") != nullptr;
     return v;
 }
+#endif
 
 static int encode_w_map(CUtensorMap* m, const act_t* w, int K, int N, int BN) {
     EncodeTiledFn enc = get_encode();
@@ -207,33 +252,20 @@ struct KfGeom {
     bool apply;  // the input GroupNorm + SiLU runs inside the kernel
     bool tr;  // transposed walk: strips run along image columns (less padding / halo for e.g. a 128 x 192 level)
 };
-static bool fuse_apply_enabled() {  // CDC_FUSE_APPLY=0: GroupNorm 1 of every ResBlock as a pass of its own (A/B, tests)
-    const char* e = getenv("CDC_FUSE_APPLY");
-    return !(e && atoi(e) == 0);
-}
-static int fuse_apply_max_tiles() {  // N tiles a conv may have for the fusion (every tile's CTAs repeat the transform); CDC_FUSE_APPLY=n overrides
-    const char* e = getenv("CDC_FUSE_APPLY");
-    return e && atoi(e) >= 1 ? atoi(e) : 2;
-}
-static bool kf_disabled() {
-    static int v = -1;
-    if (v < 0) v = getenv("CDC_NO_KF") ? 1 : 0;
-    return v == 1;
-}
-static bool conv_uses_kf(const ConvBuild& cb, int B, int num_sms, KfGeom* g) {
-    if (kf_disabled() || cb.ksize != 3 || cb.force_bn != 0 || cb.residual) return false;
+static bool conv_uses_kf(const ConvBuild& cb, int B, int num_sms, const PlanOpts& po, KfGeom* g) {
+    if (!po.kf() || cb.ksize != 3 || cb.force_bn != 0 || cb.residual) return false;
     g->mode = cb.mode == MODE_UP2 ? 1 : cb.mode == MODE_S2 ? 2 : 0;
     if (g->mode == 1 && (!cb.w->up2 || cb.epi != EPI_STORE)) return false;
     if (g->mode == 2 && (cb.epi != EPI_STORE || cb.res_w || cb.in_acc || ((cb.srcs[0].W | cb.srcs[0].H) & 1))) return false;
     // CDC_KF_S2=0: stride-2 convs through the general kernel (A/B).  Only the 64- and 128-channel downsampling convs have
     // kf instantiations: with 32-channel N tiles (192 / 256 channels, 64x96 outputs and below) the strip form measured
     // 3 us per step SLOWER than the general kernel.
-    if (g->mode == 2 && getenv("CDC_KF_S2") && atoi(getenv("CDC_KF_S2")) == 0) return false;
+    if (g->mode == 2 && !po.kf_s2()) return false;
     // strip geometry lives on the grid the kernel walks: the input grid (mode 1 writes 2x2 outputs per pixel), for the
     // stride-2 mode the OUTPUT grid
     int gw = cb.srcs[0].W >> (g->mode == 2 ? 1 : 0), gh = cb.srcs[0].H >> (g->mode == 2 ? 1 : 0);
     // CDC_KF_MIN_PIXELS=n: levels with fewer pixels per image go through the general kernel (A/B of the small levels)
-    if (getenv("CDC_KF_MIN_PIXELS") && static_cast<long>(gw) * gh < atol(getenv("CDC_KF_MIN_PIXELS"))) return false;
+    if (static_cast<long>(gw) * gh < po.kf_min_pixels()) return false;
     g->tr = false;
     g->nseg = (gw + 127) / 128;
     // segments are 128 pixels wide: too much of the tile would be padding (measured break-even against conv_tc.cu:
@@ -252,9 +284,10 @@ static bool conv_uses_kf(const ConvBuild& cb, int B, int num_sms, KfGeom* g) {
         if (cb.w->n_pad % bn || (cb.epi == EPI_STATS && bn % cb.cpg)) continue;
         // with the ResBlock's 1x1 residual conv riding along when that fits, else without
         g->res = cb.res_w != nullptr && g->mode == 0 && cb.res_w->n_pad == cb.w->n_pad && cb.res_w->taps == 1 &&
-                 cb.res_w->c_pad == ctot && kf_inst_ok(bn, cb.cpg, cb.epi, g->CH, g->mode, true) &&
-                 kf_plan(bn, g->CH, g->mode, true, cb.epi, &g->NS, &g->staged);
-        if (!g->res && (!kf_inst_ok(bn, cb.cpg, cb.epi, g->CH, g->mode, false) || !kf_plan(bn, g->CH, g->mode, false, cb.epi, &g->NS, &g->staged)))
+                 cb.res_w->c_pad == ctot && kf_inst_ok(bn, cb.cpg, cb.epi, g->CH, g->mode, true, false, po.kf_ring()) &&
+                 kf_plan(bn, g->CH, g->mode, true, cb.epi, &g->NS, &g->staged, po.kf_ring());
+        if (!g->res && (!kf_inst_ok(bn, cb.cpg, cb.epi, g->CH, g->mode, false, false, po.kf_ring()) ||
+                        !kf_plan(bn, g->CH, g->mode, false, cb.epi, &g->NS, &g->staged, po.kf_ring())))
             continue;
         g->bn = bn;
         break;
@@ -263,7 +296,8 @@ static bool conv_uses_kf(const ConvBuild& cb, int B, int num_sms, KfGeom* g) {
     // (every N tile's CTAs transform the same rows: levels 0 and 1 -- one and two N tiles, instantiated for 64 and 128
     // channels -- gain 2.4 % and 0.8 % images/s; with 3+ tiles the redundant MUFU work costs more than the pass it replaces)
     g->apply = cb.in_acc != nullptr && !g->res && cb.srcs.size() == 1 && cb.cpg == g->CH * 2 &&
-               cb.w->n_pad / g->bn <= fuse_apply_max_tiles() && kf_inst_ok(g->bn, cb.cpg, cb.epi, g->CH, g->mode, false, true);
+               cb.w->n_pad / g->bn <= po.fuse_apply_max_tiles() &&
+               kf_inst_ok(g->bn, cb.cpg, cb.epi, g->CH, g->mode, false, true, po.kf_ring());
     g->n_tiles = cb.w->n_pad / g->bn * (g->mode == 1 ? 4 : 1);
     if (cb.epi == EPI_DDIM && g->n_tiles != 1) return false;
     // strip geometry for a walk along image rows (tr = 0) or image columns (tr = 1): relative cost = padding of the
@@ -295,7 +329,7 @@ static bool conv_uses_kf(const ConvBuild& cb, int B, int num_sms, KfGeom* g) {
     return true;
 }
 
-static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::string* err) {
+static int build_conv(const ConvBuild& cb, int B, int num_sms, const PlanOpts& po, Op* op, std::string* err) {
     auto fail = [&](const std::string& m) {
         *err = "conv " + cb.name + ": " + m;
         return CDC_ERR_SHAPE;
@@ -325,7 +359,7 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
     // ---- kh-fused strip variant (conv_kf.cu) ----
     {
         KfGeom kg;
-        if (conv_uses_kf(cb, B, num_sms, &kg)) {
+        if (conv_uses_kf(cb, B, num_sms, po, &kg)) {
             auto kp = std::shared_ptr<KfParams>(new KfParams());
             memset(kp.get(), 0, sizeof(KfParams));
             for (size_t s = 0; s < cb.srcs.size(); ++s) {
@@ -381,6 +415,9 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
             kp->xpad = cb.xpad;
             kp->x0_out = cb.x0_out;
             kp->dbg = cb.dbg;
+            kp->sat = cb.sat;
+            kp->wkw = po.weight_groups() ? 1 : 0;
+            kp->e1 = 1.0f;
             const double Ms = static_cast<double>(B) * gh * gw;
             op->name = cb.name;
             const double Mout = Ms * (kg.mode == 1 ? 4.0 : 1.0);  // algorithmic: the 3x3 conv on the upsampled grid
@@ -397,26 +434,29 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
             const int epi = cb.epi, cpg = cb.cpg, bn_k = kg.bn, CHk = kg.CH;
             const bool xk = cb.x16 && cb.epi == EPI_STORE && kg.bn == 64 && kg.CH == 2 && cb.srcs[0].C == 64 && kg.mode == 0;
             const int kmode = kg.mode;
-            const bool kres = kg.res, kapply = kg.apply;
-            const std::vector<float>*c0 = cb.c0, *c1 = cb.c1;
+            const bool kres = kg.res, kapply = kg.apply, kstaged = kg.staged;
+            const SamplerTab* samp = cb.samp;
             float* const* film_base = cb.film_base;
             const int* film_total = cb.film_total;
             const int film_off = cb.in_film_off;
-            op->run = [kp, bn_k, cpg, epi, CHk, xk, kmode, kres, kapply, c0, c1, film_base, film_total, film_off](cudaStream_t s,
-                                                                                                                 int k) -> cudaError_t {
+            op->run = [kp, bn_k, cpg, epi, CHk, xk, kmode, kres, kapply, kstaged, samp, film_base, film_total, film_off](
+                          cudaStream_t s, int k, long long* stamp) -> cudaError_t {
+                KfParams q = *kp;
+                q.stamp = stamp;
                 if (epi == EPI_DDIM) {
-                    if (!c0 || k < 0 || k >= static_cast<int>(c0->size())) return cudaErrorInvalidValue;
-                    KfParams q = *kp;
-                    q.c0 = (*c0)[k];
-                    q.c1 = (*c1)[k];
-                    return launch_conv_kf(q, bn_k, cpg, epi, CHk, xk, kmode, kres, false, s);
+                    if (!samp || k < 0 || k >= static_cast<int>(samp->c0.size())) return cudaErrorInvalidValue;
+                    q.c0 = samp->c0[k];
+                    q.c1 = samp->c1[k];
+                    q.e0 = samp->e0[k];
+                    q.e1 = samp->e1[k];
+                    q.sg = samp->sg[k];
+                    q.seed = samp->seed;
+                    q.step = k;
+                    return launch_conv_kf(q, bn_k, cpg, epi, CHk, xk, kmode, kres, false, kstaged, s);
                 }
-                if (kapply && film_off >= 0) {  // this step's FiLM (scale | shift) of the input GroupNorm
-                    KfParams q = *kp;
+                if (kapply && film_off >= 0)  // this step's FiLM (scale | shift) of the input GroupNorm
                     q.in_film = *film_base + static_cast<size_t>(k) * *film_total + film_off;
-                    return launch_conv_kf(q, bn_k, cpg, epi, CHk, xk, kmode, kres, true, s);
-                }
-                return launch_conv_kf(*kp, bn_k, cpg, epi, CHk, xk, kmode, kres, kapply, s);
+                return launch_conv_kf(q, bn_k, cpg, epi, CHk, xk, kmode, kres, kapply, kstaged, s);
             };
             return CDC_OK;
         }
@@ -448,6 +488,7 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
         }
     }
     if (!bn || w.n_pad % bn) return fail("no N tile for C_out");
+    if (w.n_pad > 768) return fail("C_out beyond the general kernel's 768-entry bias table");
     if (cb.epi == EPI_STATS && !stats_inst_ok(bn, cb.cpg)) return fail("no stats instantiation for (BN, cpg)");
 
     // tensor maps
@@ -544,6 +585,8 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
     cp->x = cb.x;
     cp->xpad = cb.xpad;
     cp->x0_out = cb.x0_out;
+    cp->sat = cb.sat;
+    cp->e1 = 1.0f;
 
     const double M = static_cast<double>(B) * OH * OW;
     op->name = cb.name;
@@ -551,13 +594,24 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, Op* op, std::stri
     const double m_in = static_cast<double>(B) * cb.srcs[0].H * cb.srcs[0].W;
     op->bytes = 2.0 * (m_in * w.c_true + M * w.n_true + static_cast<double>(taps) * w.c_true * w.n_true);
     const int epi = cb.epi, cpg = cb.cpg;
-    const std::vector<float>*c0 = cb.c0, *c1 = cb.c1;
-    op->run = [cp, bn, cpg, epi, num_sms, c0, c1](cudaStream_t s, int k) -> cudaError_t {
+    const SamplerTab* samp = cb.samp;
+    op->run = [cp, bn, cpg, epi, num_sms, samp](cudaStream_t s, int k, long long* stamp) -> cudaError_t {
         if (epi == EPI_DDIM) {
-            if (!c0 || k < 0 || k >= static_cast<int>(c0->size())) return cudaErrorInvalidValue;
+            if (!samp || k < 0 || k >= static_cast<int>(samp->c0.size())) return cudaErrorInvalidValue;
             ConvParams q = *cp;
-            q.c0 = (*c0)[k];
-            q.c1 = (*c1)[k];
+            q.c0 = samp->c0[k];
+            q.c1 = samp->c1[k];
+            q.e0 = samp->e0[k];
+            q.e1 = samp->e1[k];
+            q.sg = samp->sg[k];
+            q.seed = samp->seed;
+            q.step = k;
+            q.stamp = stamp;
+            return launch_conv(q, bn, cpg, epi, num_sms, s);
+        }
+        if (stamp) {
+            ConvParams q = *cp;
+            q.stamp = stamp;
             return launch_conv(q, bn, cpg, epi, num_sms, s);
         }
         return launch_conv(*cp, bn, cpg, epi, num_sms, s);
@@ -587,10 +641,16 @@ struct cdc_ctx {
     bool finalized = false, has_ctx = false;
     int C[4];
 
+    PlanOpts opts = default_plan_opts();
+    bool opts_dirty = false;  // an option changed since the plan was built: the next cdc_bind_io re-plans
+
     // schedule
     int K = 0;
     std::vector<int> idx;
-    std::vector<float> c0, c1;
+    SamplerTab samp;         // c0, c1, e0, e1, sigma per step
+    int pred_eps = 0;        // cdc_set_sampler: 0 = the network predicts x0, 1 = it predicts the noise
+    float eta = 0.0f;
+    unsigned long long seed = 0;
     float* film = nullptr;   // [K][film_total]
     float* sinus = nullptr;  // [K][64]
     int film_total = 0;
@@ -602,7 +662,8 @@ struct cdc_ctx {
     std::vector<Op> step_ops, ctx_ops;
     Act cond[4], xpad, latent;
     float *xs = nullptr, *x0s = nullptr;
-    gn_sum_t* gn_slots = nullptr;  // [kMaxGnSlots][B][32][2] fixed-point GroupNorm accumulators (gn_sums.cuh)
+    gn_sum_t* gn_slots = nullptr;  // [2][kMaxGnSlots][B][32][kGnVals] fixed-point GroupNorm accumulators (gn_sums.cuh)
+    unsigned int* sat_dev = nullptr;  // saturation diagnostics counter (cdc_saturation_count)
     int gn_used_step = 0, gn_used_ctx = 0;
     float *stage_f32 = nullptr;  // NCHW fp32 staging for host-buffer calls
     size_t stage_elems = 0;
@@ -612,7 +673,7 @@ struct cdc_ctx {
     cudaEvent_t ev_x = nullptr, ev_fork = nullptr;
     cudaGraphExec_t graph = nullptr;
     int graph_K = 0;
-    int graph_skip = 0;  // measurement only (cdc_debug_graph_skip): class of ops left out of the captured graph
+    int graph_skip = 0;  // tools build only (cdc_debug_graph_skip): class of ops left out of the captured graph
     cudaStream_t cap_stream = nullptr;
 
     int fail(int code, const char* fmt, ...) {
@@ -755,7 +816,8 @@ struct PlanB {
         if (rc) return;
         Op op;
         std::string e;
-        int r = build_conv(cb, ctx->B, ctx->num_sms, &op, &e);
+        cb.sat = ctx->sat_dev;
+        int r = build_conv(cb, ctx->B, ctx->num_sms, ctx->opts, &op, &e);
         if (r) {
             rc = ctx->fail(r, "%s", e.c_str());
             return;
@@ -770,7 +832,7 @@ struct PlanB {
             rc = ctx->fail(CDC_ERR_SHAPE, "too many GroupNorms in one sequence");
             return slots;
         }
-        return slots + static_cast<size_t>(next_slot++) * ctx->B * 64;
+        return slots + static_cast<size_t>(next_slot++) * ctx->B * kGnImgStride;
     }
     void clear_slots_op() {  // placeholder op: sized when the sequence is complete (see finish())
         Op z;
@@ -778,8 +840,8 @@ struct PlanB {
         cdc_ctx* c = ctx;
         gn_sum_t* base = slots;
         const int* used = ops == &ctx->step_ops ? &ctx->gn_used_step : &ctx->gn_used_ctx;
-        z.run = [c, base, used](cudaStream_t s, int) {
-            return cudaMemsetAsync(base, 0, static_cast<size_t>(*used) * c->B * 64 * sizeof(gn_sum_t), s);
+        z.run = [c, base, used](cudaStream_t s, int, long long*) {
+            return cudaMemsetAsync(base, 0, static_cast<size_t>(*used) * c->B * kGnImgStride * sizeof(gn_sum_t), s);
         };
         ops->push_back(z);
     }
@@ -798,9 +860,9 @@ struct PlanB {
         const act_t *xp = x.p, *rp = res;
         act_t* yp = y.p;
         const int si = silu ? 1 : 0;
-        a.run = [c, acc, gamma, beta, foff, xp, rp, yp, B, HW, Cc, si](cudaStream_t s, int k) {
+        a.run = [c, acc, gamma, beta, foff, xp, rp, yp, B, HW, Cc, si](cudaStream_t s, int k, long long* stamp) {
             const float* film = foff >= 0 ? c->film + static_cast<size_t>(k) * c->film_total + foff : nullptr;
-            return launch_gn_apply(xp, acc, gamma, beta, film, c->cfg.gn_eps, rp, yp, B, HW, Cc, si, c->num_sms, s);
+            return launch_gn_apply(xp, acc, gamma, beta, film, c->cfg.gn_eps, rp, yp, B, HW, Cc, si, c->num_sms, s, stamp, c->sat_dev);
         };
         ops->push_back(a);
     }
@@ -826,7 +888,7 @@ struct PlanB {
             c1.res_w = &ctx->convs[wp + ".res"];
             c1.res_out = rbuf;
             KfGeom kg;
-            res_fused = conv_uses_kf(c1, ctx->B, ctx->num_sms, &kg) && kg.res;
+            res_fused = conv_uses_kf(c1, ctx->B, ctx->num_sms, ctx->opts, &kg) && kg.res;
             if (!res_fused) c1.res_w = nullptr;
         }
         conv(c1);
@@ -851,7 +913,7 @@ struct PlanB {
             c2.film_total = &ctx->film_total;
         }
         KfGeom kg2;
-        if (!(fuse_apply_enabled() && conv_uses_kf(c2, ctx->B, ctx->num_sms, &kg2) && kg2.apply)) {
+        if (!(ctx->opts.fuse_apply_max_tiles() > 0 && conv_uses_kf(c2, ctx->B, ctx->num_sms, ctx->opts, &kg2) && kg2.apply)) {
             c2.in_acc = nullptr;
             gn(name + ".gn1", wp + ".gn1", film_idx, c1.gn_acc, t1, nullptr, t1, true);
         }
@@ -880,7 +942,9 @@ static int build_plans(cdc_ctx* ctx) {
     const size_t px = static_cast<size_t>(B) * H * W;
     CK(ar.alloc(reinterpret_cast<void**>(&ctx->xs), px * 3 * 4));
     CK(ar.alloc(reinterpret_cast<void**>(&ctx->x0s), px * 3 * 4));
-    CK(ar.alloc(reinterpret_cast<void**>(&ctx->gn_slots), 2 * static_cast<size_t>(kMaxGnSlots) * B * 64 * sizeof(gn_sum_t)));
+    CK(ar.alloc(reinterpret_cast<void**>(&ctx->gn_slots), 2 * static_cast<size_t>(kMaxGnSlots) * B * kGnImgStride * sizeof(gn_sum_t)));
+    CK(ar.alloc(reinterpret_cast<void**>(&ctx->sat_dev), 256));
+    CK(cudaMemset(ctx->sat_dev, 0, 256));
 
     ctx->stage_elems = px * 64;  // largest NCHW fp32 tensor crossing the boundary (c0)
     CK(ar.alloc(reinterpret_cast<void**>(&ctx->stage_f32), ctx->stage_elems * 4));
@@ -940,7 +1004,7 @@ static int build_plans(cdc_ctx* ctx) {
         st.bytes = static_cast<double>(B) * HW * Cm * 2;
         const act_t* m1p = m1.p;
         gn_sum_t* aslot = pb.new_gn_slot();
-        st.run = [aslot, m1p, B, HW, Cm](cudaStream_t s, int) { return launch_gn_stats(m1p, aslot, B, HW, Cm, s); };
+        st.run = [aslot, m1p, B, HW, Cm](cudaStream_t s, int, long long* stamp) { return launch_gn_stats(m1p, aslot, B, HW, Cm, s, stamp); };
         ctx->step_ops.push_back(st);
         pb.gn("mid.attn.gn", "mid.attn.gn", -1, aslot, m1, nullptr, n, false);
         ConvBuild cq;
@@ -963,8 +1027,17 @@ static int build_plans(cdc_ctx* ctx) {
         ap->out = op_;
         ap->N = HW;
         ap->heads = heads;
-        at.run = [ap, qp, op_, B, HW, heads](cudaStream_t s, int) {
-            return attention_legacy() ? launch_attention(qp, op_, B, HW, heads, s) : launch_attention_tc(*ap, B, s);
+        at.run = [ap, qp, op_, B, HW, heads](cudaStream_t s, int, long long* stamp) {
+#ifdef CDC_TOOLS
+            if (attention_legacy()) return launch_attention(qp, op_, B, HW, heads, s);
+#endif
+            (void)qp;
+            (void)op_;
+            (void)heads;
+            (void)HW;
+            AttnTcParams q = *ap;
+            q.stamp = stamp;
+            return launch_attention_tc(q, B, s);
         };
         ctx->step_ops.push_back(at);
         ConvBuild cpj;
@@ -1003,8 +1076,7 @@ static int build_plans(cdc_ctx* ctx) {
         cb.x = ctx->xs;
         cb.xpad = ctx->xpad.p;
         cb.x0_out = ctx->x0s;
-        cb.c0 = &ctx->c0;
-        cb.c1 = &ctx->c1;
+        cb.samp = &ctx->samp;
         pb.conv(cb);
     }
     if (pb.rc) return pb.rc;
@@ -1015,7 +1087,7 @@ static int build_plans(cdc_ctx* ctx) {
         PlanB pc;
         pc.ctx = ctx;
         pc.ops = &ctx->ctx_ops;
-        pc.slots = ctx->gn_slots + static_cast<size_t>(kMaxGnSlots) * B * 64;
+        pc.slots = ctx->gn_slots + static_cast<size_t>(kMaxGnSlots) * B * kGnImgStride;
         pc.clear_slots_op();
         Act hh = ctx->latent;
         for (int i = 3; i >= 0; --i) {
@@ -1044,15 +1116,18 @@ static void drop_graph(cdc_ctx* ctx) {
     ctx->graph_K = 0;
 }
 
-static int capture_graph(cdc_ctx* ctx) {
-    drop_graph(ctx);
+// Captures the K-step loop into one graph.  stamps != null: the timing variant (cdc_profile_graph) -- every kernel gets
+// its own (start, end) slot [k][op][2].
+static int capture_graph(cdc_ctx* ctx, cudaGraphExec_t* out, long long* stamps) {
     if (!ctx->cap_stream) CK(cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking));
     cudaGraph_t g = nullptr;
     CK(cudaStreamBeginCapture(ctx->cap_stream, cudaStreamCaptureModeThreadLocal));
     cudaError_t e = cudaSuccess;
     std::string bad;
-    // tools only: CDC_GRAPH_SKIP=substr[,substr...] leaves ops whose name contains a substring out of the graph, so that
-    // the in-graph cost of a class of ops can be read off as a difference of replay times (results are then garbage)
+#ifdef CDC_TOOLS
+    // tools build only: CDC_GRAPH_SKIP=substr[,substr...] leaves ops whose name contains a substring out of the graph, so
+    // that the in-graph cost of a class of ops can be read off as a difference of replay times (results are then garbage
+    // and cdc_get_x refuses to return them)
     std::vector<std::string> skip;
     if (const char* sk = getenv("CDC_GRAPH_SKIP")) {
         std::string t(sk);
@@ -1065,15 +1140,21 @@ static int capture_graph(cdc_ctx* ctx) {
             pos = c + 1;
         }
     }
+    if (!skip.empty() && ctx->graph_skip == 0) ctx->graph_skip = 4;
+#endif
+    const size_t nops = ctx->step_ops.size();
     for (int k = 0; k < ctx->K && e == cudaSuccess; ++k)
-        for (Op& op : ctx->step_ops) {
+        for (size_t i = 0; i < nops; ++i) {
+            Op& op = ctx->step_ops[i];
+#ifdef CDC_TOOLS
             const bool is_conv = op.flops > 0 && op.name.find("sdpa") == std::string::npos;
             const bool is_attn = op.name.find("sdpa") != std::string::npos;
             bool skipped = (ctx->graph_skip == 1 && is_conv) || (ctx->graph_skip == 2 && op.flops == 0 && op.name != "gn.clear") ||
                            (ctx->graph_skip == 3 && is_attn);
             for (const std::string& w : skip) skipped = skipped || op.name.find(w) != std::string::npos;
             if (skipped) continue;
-            e = op.run(ctx->cap_stream, k);
+#endif
+            e = op.run(ctx->cap_stream, k, stamps ? stamps + (static_cast<size_t>(k) * nops + i) * 2 : nullptr);
             if (e != cudaSuccess) {
                 bad = op.name;
                 break;
@@ -1085,17 +1166,27 @@ static int capture_graph(cdc_ctx* ctx) {
         return ctx->fail(CDC_ERR_CUDA, "graph capture: %s failed: %s", bad.c_str(), cudaGetErrorString(e));
     }
     CK(e2);
-    e = cudaGraphInstantiate(&ctx->graph, g, 0);
+    e = cudaGraphInstantiate(out, g, 0);
     cudaGraphDestroy(g);
     CK(e);
+    return CDC_OK;
+}
+
+static int ensure_graph(cdc_ctx* ctx) {
+    if (ctx->graph && ctx->graph_K == ctx->K) return CDC_OK;
+    drop_graph(ctx);
+    int r = capture_graph(ctx, &ctx->graph, nullptr);
+    if (r) return r;
     ctx->graph_K = ctx->K;
     return CDC_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ C ABI
+#define GUARD() DevGuard dev_guard_(ctx->device)
+
 extern "C" {
 
-int cdc_abi_version(void) { return 1; }
+int cdc_abi_version(void) { return 2; }
 
 int cdc_act_dtype(void) { return CDC_ACT_FP16 ? 1 : 0; }
 
@@ -1117,21 +1208,26 @@ int cdc_create(const cdc_config* cfg, int device, cdc_ctx** out) {
                        "; this library is sm_100a only and has no fallback";
         return CDC_ERR_ARCH;
     }
-    if (cfg->groups != 32 || cfg->head_dim != 64 || cfg->heads * cfg->head_dim != cfg->base * cfg->mults[3] ||
-        cfg->base != 64 || cfg->temb > 256 || cfg->latent_ch % 64) {
-        g_create_err = "unsupported config (need base 64, 32 groups, head_dim 64, temb <= 256)";
+    bool mults_ok = true;
+    for (int i = 0; i < 4; ++i) mults_ok = mults_ok && cfg->mults[i] >= 1 && cfg->mults[i] <= 4;
+    if (!mults_ok || cfg->groups != 32 || cfg->head_dim != 64 || cfg->heads < 1 || cfg->heads * cfg->head_dim != cfg->base * cfg->mults[3] ||
+        cfg->base != 64 || cfg->temb < 1 || cfg->temb > 256 || cfg->latent_ch < 64 || cfg->latent_ch % 64 || cfg->T < 1 ||
+        !(cfg->gn_eps > 0.0f)) {
+        g_create_err = "unsupported config (need base 64, mults in 1..4, 32 groups, head_dim 64, heads * 64 == base * mults[3], "
+                       "1 <= temb <= 256, latent_ch a multiple of 64, T >= 1, gn_eps > 0)";
         return CDC_ERR_SHAPE;
     }
-    if ((e = cudaSetDevice(device)) != cudaSuccess) {
-        g_create_err = cudaGetErrorString(e);
-        return CDC_ERR_CUDA;
-    }
+    DevGuard guard(device);
     if (!get_encode()) {
         g_create_err = "cuTensorMapEncodeTiled entry point not found";
         return CDC_ERR_CUDA;
     }
-    if ((e = configure_attention()) != cudaSuccess || (e = configure_attention_tc()) != cudaSuccess ||
-        (e = configure_conv_kernels()) != cudaSuccess ||         (e = configure_kf_kernels()) != cudaSuccess) {
+    if (
+#ifdef CDC_TOOLS
+        (e = configure_attention()) != cudaSuccess ||
+#endif
+        (e = configure_attention_tc()) != cudaSuccess || (e = configure_conv_kernels()) != cudaSuccess ||
+        (e = configure_kf_kernels()) != cudaSuccess) {
         g_create_err = std::string("cudaFuncSetAttribute(conv kernels): ") + cudaGetErrorString(e);
         return CDC_ERR_CUDA;
     }
@@ -1146,29 +1242,34 @@ int cdc_create(const cdc_config* cfg, int device, cdc_ctx** out) {
 
 void cdc_destroy(cdc_ctx* ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
-    cudaDeviceSynchronize();
-    drop_graph(ctx);
-    if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
-    ctx->arena.release();
-    ctx->warena.release();
-    if (ctx->film) cudaFree(ctx->film);
-    if (ctx->sinus) cudaFree(ctx->sinus);
-    if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
-    if (ctx->pin_x) cudaFreeHost(ctx->pin_x);
-    if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
-    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-    if (ctx->ev_x) cudaEventDestroy(ctx->ev_x);
-    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    {
+        GUARD();
+        cudaDeviceSynchronize();
+        drop_graph(ctx);
+        if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
+        ctx->arena.release();
+        ctx->warena.release();
+        if (ctx->film) cudaFree(ctx->film);
+        if (ctx->sinus) cudaFree(ctx->sinus);
+        if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
+        if (ctx->pin_x) cudaFreeHost(ctx->pin_x);
+        if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
+        if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+        if (ctx->ev_x) cudaEventDestroy(ctx->ev_x);
+        if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    }
     delete ctx;
 }
 
 int cdc_load_weights(cdc_ctx* ctx, const char* name, const void* dev_ptr, const int64_t* shape, int ndim) {
-    if (!ctx || !name || !dev_ptr || ndim < 1 || ndim > 4) return ctx ? ctx->fail(CDC_ERR_SHAPE, "bad argument") : CDC_ERR_SHAPE;
+    if (!ctx) return CDC_ERR_STATE;
+    if (!name || !dev_ptr || !shape || ndim < 1 || ndim > 4) return ctx->fail(CDC_ERR_SHAPE, "cdc_load_weights: null argument or ndim outside 1..4");
     if (ctx->finalized) return ctx->fail(CDC_ERR_STATE, "weights already finalized");
+    GUARD();
     WeightT t;
     t.numel = 1;
     for (int i = 0; i < ndim; ++i) {
+        if (shape[i] < 1) return ctx->fail(CDC_ERR_SHAPE, "%s: non-positive dimension", name);
         t.shape.push_back(shape[i]);
         t.numel *= static_cast<size_t>(shape[i]);
     }
@@ -1181,6 +1282,7 @@ int cdc_load_weights(cdc_ctx* ctx, const char* name, const void* dev_ptr, const 
 int cdc_finalize_weights(cdc_ctx* ctx) {
     if (!ctx) return CDC_ERR_STATE;
     if (ctx->finalized) return CDC_OK;
+    GUARD();
     const int* C = ctx->C;
     int r;
     // stem: cat[x_t (3), c0 (64)] -> image channels padded to 64, context follows at slot 64
@@ -1238,9 +1340,26 @@ int cdc_finalize_weights(cdc_ctx* ctx) {
 
 int cdc_has_context_net(cdc_ctx* ctx) { return ctx && ctx->has_ctx ? 1 : 0; }
 
+int cdc_set_sampler(cdc_ctx* ctx, int pred_eps, float eta, uint64_t seed) {
+    if (!ctx) return CDC_ERR_STATE;
+    if ((pred_eps != 0 && pred_eps != 1) || !(eta >= 0.0f) || eta > 10.0f) return ctx->fail(CDC_ERR_SHAPE, "pred_eps must be 0/1 and 0 <= eta <= 10");
+    if (pred_eps != ctx->pred_eps || eta != ctx->eta || seed != ctx->seed) {
+        ctx->pred_eps = pred_eps;
+        ctx->eta = eta;
+        ctx->seed = seed;
+        if (ctx->K > 0) {  // coefficients are baked into the graph: recompute them now
+            const int K = ctx->K;
+            ctx->K = 0;
+            return cdc_set_schedule(ctx, K);
+        }
+    }
+    return CDC_OK;
+}
+
 int cdc_set_schedule(cdc_ctx* ctx, int K) {
     if (!ctx || !ctx->finalized) return ctx ? ctx->fail(CDC_ERR_STATE, "finalize weights first") : CDC_ERR_STATE;
     if (K < 1 || K > ctx->cfg.T) return ctx->fail(CDC_ERR_SHAPE, "steps must be in [1, T]");
+    GUARD();
     const int T = ctx->cfg.T;
     // cosine schedule, float64 (oracle/sampler.py alphas_cumprod)
     std::vector<double> ab(T);
@@ -1256,21 +1375,31 @@ int cdc_set_schedule(cdc_ctx* ctx, int K) {
         ab[t] = cum;
     }
     std::vector<int> idx(K);
-    std::vector<float> c0(K), c1(K);
+    SamplerTab st;
+    st.c0.resize(K);
+    st.c1.resize(K);
+    st.e0.resize(K);
+    st.e1.resize(K);
+    st.sg.resize(K);
+    st.seed = ctx->seed;
     for (int k = 0; k < K; ++k)
         idx[k] = K == 1 ? T - 1 : static_cast<int>((static_cast<long long>(K - 1 - k) * (T - 1) + (K - 1) / 2) / (K - 1));
-    for (int k = 0; k < K; ++k) {
+    for (int k = 0; k < K; ++k) {  // oracle/sampler.py make_schedule, float64 -> fp32
         const double at = ab[idx[k]], ap = k + 1 < K ? ab[idx[k + 1]] : 1.0;
-        const double v1 = sqrt(1.0 - ap) / sqrt(1.0 - at);
-        c1[k] = static_cast<float>(v1);
-        c0[k] = static_cast<float>(sqrt(ap) - v1 * sqrt(at));
+        const double sg = ctx->eta > 0.0f && ap < 1.0 ? static_cast<double>(ctx->eta) * sqrt((1.0 - ap) / (1.0 - at)) * sqrt(1.0 - at / ap) : 0.0;
+        const double dir2 = 1.0 - ap - sg * sg;
+        const double v1 = sqrt(dir2 > 0.0 ? dir2 : 0.0) / sqrt(1.0 - at);
+        st.c1[k] = static_cast<float>(v1);
+        st.c0[k] = static_cast<float>(sqrt(ap) - v1 * sqrt(at));
+        st.sg[k] = static_cast<float>(sg);
+        st.e0[k] = ctx->pred_eps ? static_cast<float>(1.0 / sqrt(at)) : 0.0f;
+        st.e1[k] = ctx->pred_eps ? static_cast<float>(-sqrt(1.0 - at) / sqrt(at)) : 1.0f;
     }
     // the graph bakes per-step pointers/coefficients: any schedule change invalidates it
     drop_graph(ctx);
     ctx->K = K;
     ctx->idx = idx;
-    ctx->c0 = c0;
-    ctx->c1 = c1;
+    ctx->samp = st;
 
     // sinusoidal embedding per step (host, float64 -> fp32), then MLP + FiLM on the device
     std::vector<float> sin_h(static_cast<size_t>(K) * 64);
@@ -1315,16 +1444,37 @@ int cdc_set_schedule(cdc_ctx* ctx, int K) {
 int cdc_schedule_index(cdc_ctx* ctx, int k) { return (ctx && k >= 0 && k < ctx->K) ? ctx->idx[k] : -1; }
 
 int cdc_schedule_coeffs(cdc_ctx* ctx, int k, float* c0, float* c1) {
-    if (!ctx || k < 0 || k >= ctx->K) return CDC_ERR_SHAPE;
-    *c0 = ctx->c0[k];
-    *c1 = ctx->c1[k];
+    if (!ctx || k < 0 || k >= ctx->K || !c0 || !c1) return CDC_ERR_SHAPE;
+    *c0 = ctx->samp.c0[k];
+    *c1 = ctx->samp.c1[k];
+    return CDC_OK;
+}
+
+int cdc_schedule_coeffs5(cdc_ctx* ctx, int k, float* c0, float* c1, float* e0, float* e1, float* sigma) {
+    if (!ctx || k < 0 || k >= ctx->K || !c0 || !c1 || !e0 || !e1 || !sigma) return CDC_ERR_SHAPE;
+    *c0 = ctx->samp.c0[k];
+    *c1 = ctx->samp.c1[k];
+    *e0 = ctx->samp.e0[k];
+    *e1 = ctx->samp.e1[k];
+    *sigma = ctx->samp.sg[k];
+    return CDC_OK;
+}
+
+int cdc_film_size(cdc_ctx* ctx) { return ctx && ctx->finalized ? ctx->film_total : 0; }
+
+int cdc_get_film(cdc_ctx* ctx, float* film_dev, cdc_stream s) {
+    if (!ctx || !ctx->film || ctx->K < 1) return ctx ? ctx->fail(CDC_ERR_STATE, "call cdc_set_schedule first") : CDC_ERR_STATE;
+    if (!film_dev) return ctx->fail(CDC_ERR_SHAPE, "null output");
+    GUARD();
+    CK(cudaMemcpyAsync(film_dev, ctx->film, static_cast<size_t>(ctx->K) * ctx->film_total * 4, cudaMemcpyDeviceToDevice, S(s)));
     return CDC_OK;
 }
 
 int cdc_bind_io(cdc_ctx* ctx, int B, int H, int W) {
     if (!ctx || !ctx->finalized) return ctx ? ctx->fail(CDC_ERR_STATE, "finalize weights first") : CDC_ERR_STATE;
     if (B < 1 || H < 64 || W < 64 || (H % 64) || (W % 64)) return ctx->fail(CDC_ERR_SHAPE, "H and W must be multiples of 64, batch >= 1");
-    if (B == ctx->B && H == ctx->H && W == ctx->W && !ctx->step_ops.empty()) return CDC_OK;
+    if (B == ctx->B && H == ctx->H && W == ctx->W && !ctx->step_ops.empty() && !ctx->opts_dirty) return CDC_OK;
+    GUARD();
     CK(cudaDeviceSynchronize());
     drop_graph(ctx);
     ctx->step_ops.clear();
@@ -1333,6 +1483,7 @@ int cdc_bind_io(cdc_ctx* ctx, int B, int H, int W) {
     ctx->B = B;
     ctx->H = H;
     ctx->W = W;
+    ctx->opts_dirty = false;
     int r = build_plans(ctx);
     if (r) {
         ctx->step_ops.clear();
@@ -1346,14 +1497,27 @@ int cdc_bind_io(cdc_ctx* ctx, int B, int H, int W) {
 }
 
 #define NEED_PLAN()                                                                     \
-    if (!ctx || ctx->step_ops.empty()) return ctx ? ctx->fail(CDC_ERR_STATE, "call cdc_bind_io first") : CDC_ERR_STATE
+    if (!ctx || ctx->step_ops.empty()) return ctx ? ctx->fail(CDC_ERR_STATE, "call cdc_bind_io first") : CDC_ERR_STATE; \
+    GUARD()
 
 int cdc_set_cond(cdc_ctx* ctx, const float* c0, const float* c1, const float* c2, const float* c3, cdc_stream s) {
     NEED_PLAN();
     const float* src[4] = {c0, c1, c2, c3};
     for (int i = 0; i < 4; ++i) {
+        if (!src[i]) return ctx->fail(CDC_ERR_SHAPE, "cdc_set_cond: null context map %d", i);
         const Act& a = ctx->cond[i];
         CK(launch_nchw_f32_to_nhwc_act(src[i], a.p, ctx->B, a.C, a.H * a.W, a.C, S(s)));
+    }
+    return CDC_OK;
+}
+
+int cdc_get_cond(cdc_ctx* ctx, float* c0, float* c1, float* c2, float* c3, cdc_stream s) {
+    NEED_PLAN();
+    float* dst[4] = {c0, c1, c2, c3};
+    for (int i = 0; i < 4; ++i) {
+        if (!dst[i]) continue;
+        const Act& a = ctx->cond[i];
+        CK(launch_nhwc_act_to_nchw_f32(a.p, dst[i], ctx->B, a.C, a.H * a.W, S(s)));
     }
     return CDC_OK;
 }
@@ -1361,10 +1525,11 @@ int cdc_set_cond(cdc_ctx* ctx, const float* c0, const float* c1, const float* c2
 int cdc_set_latent(cdc_ctx* ctx, const float* y_hat, cdc_stream s) {
     NEED_PLAN();
     if (!ctx->has_ctx) return ctx->fail(CDC_ERR_WEIGHT, "context-net weights (context.*) were not loaded");
+    if (!y_hat) return ctx->fail(CDC_ERR_SHAPE, "null latent");
     const Act& a = ctx->latent;
     CK(launch_nchw_f32_to_nhwc_act(y_hat, a.p, ctx->B, a.C, a.H * a.W, a.C, S(s)));
     for (Op& op : ctx->ctx_ops) {
-        cudaError_t e = op.run(S(s), 0);
+        cudaError_t e = op.run(S(s), 0, nullptr);
         if (e != cudaSuccess) return ctx->fail(CDC_ERR_CUDA, "%s: %s", op.name.c_str(), cudaGetErrorString(e));
     }
     return CDC_OK;
@@ -1372,18 +1537,22 @@ int cdc_set_latent(cdc_ctx* ctx, const float* y_hat, cdc_stream s) {
 
 int cdc_set_x(cdc_ctx* ctx, const float* x, cdc_stream s) {
     NEED_PLAN();
+    if (!x) return ctx->fail(CDC_ERR_SHAPE, "null x");
     CK(launch_x_in(x, ctx->xs, ctx->xpad.p, ctx->B, ctx->H * ctx->W, S(s)));
     return CDC_OK;
 }
 
 int cdc_get_x(cdc_ctx* ctx, float* x, int to_image, cdc_stream s) {
     NEED_PLAN();
+    if (!x) return ctx->fail(CDC_ERR_SHAPE, "null output");
+    if (ctx->graph_skip) return ctx->fail(CDC_ERR_STATE, "ops are being left out of the graph (tools build, graph skip): x is garbage");
     CK(launch_x_out(ctx->xs, x, ctx->B, ctx->H * ctx->W, to_image, S(s)));
     return CDC_OK;
 }
 
 int cdc_get_x0(cdc_ctx* ctx, float* x0, cdc_stream s) {
     NEED_PLAN();
+    if (!x0) return ctx->fail(CDC_ERR_SHAPE, "null output");
     CK(launch_x_out(ctx->x0s, x0, ctx->B, ctx->H * ctx->W, 0, S(s)));
     return CDC_OK;
 }
@@ -1392,7 +1561,7 @@ int cdc_denoise_step(cdc_ctx* ctx, int k, cdc_stream s) {
     NEED_PLAN();
     if (k < 0 || k >= ctx->K) return ctx->fail(CDC_ERR_SHAPE, "step %d outside the %d-step schedule", k, ctx->K);
     for (Op& op : ctx->step_ops) {
-        cudaError_t e = op.run(S(s), k);
+        cudaError_t e = op.run(S(s), k, nullptr);
         if (e != cudaSuccess) return ctx->fail(CDC_ERR_CUDA, "%s: %s", op.name.c_str(), cudaGetErrorString(e));
     }
     return CDC_OK;
@@ -1401,10 +1570,8 @@ int cdc_denoise_step(cdc_ctx* ctx, int k, cdc_stream s) {
 int cdc_decode(cdc_ctx* ctx, cdc_stream s) {
     NEED_PLAN();
     if (ctx->K < 1) return ctx->fail(CDC_ERR_STATE, "call cdc_set_schedule first");
-    if (!ctx->graph || ctx->graph_K != ctx->K) {
-        int r = capture_graph(ctx);
-        if (r) return r;
-    }
+    int r = ensure_graph(ctx);
+    if (r) return r;
     CK(cudaGraphLaunch(ctx->graph, S(s)));
     return CDC_OK;
 }
@@ -1420,6 +1587,7 @@ static bool host_ptr_is_pinned(const void* p) {
 
 int cdc_decode_host(cdc_ctx* ctx, const float* latent_host, const float* xT_host, float* image_host, cdc_stream s) {
     NEED_PLAN();
+    if (!latent_host || !xT_host || !image_host) return ctx->fail(CDC_ERR_SHAPE, "null host buffer");
     const size_t nl = static_cast<size_t>(ctx->B) * ctx->cfg.latent_ch * (ctx->H / 16) * (ctx->W / 16);
     const size_t nx = static_cast<size_t>(ctx->B) * 3 * ctx->H * ctx->W;
     if (nl > ctx->pin_nl || nx > ctx->pin_nx) {  // (re)size the pinned staging buffers for this shape
@@ -1428,6 +1596,7 @@ int cdc_decode_host(cdc_ctx* ctx, const float* latent_host, const float* xT_host
         if (ctx->pin_x) cudaFreeHost(ctx->pin_x);
         if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
         ctx->pin_in = ctx->pin_x = ctx->pin_out = nullptr;
+        ctx->pin_nl = ctx->pin_nx = 0;
         CK(cudaMallocHost(&ctx->pin_in, nl * 4));
         CK(cudaMallocHost(&ctx->pin_x, nx * 4));
         CK(cudaMallocHost(&ctx->pin_out, nx * 4));
@@ -1490,6 +1659,28 @@ double cdc_flops_per_step(cdc_ctx* ctx) {
     return f;
 }
 
+int cdc_saturation_count(cdc_ctx* ctx, uint64_t* count, int reset, cdc_stream s) {
+    NEED_PLAN();
+    if (!count) return ctx->fail(CDC_ERR_SHAPE, "null output");
+    unsigned int v = 0;
+    CK(cudaMemcpyAsync(&v, ctx->sat_dev, 4, cudaMemcpyDeviceToHost, S(s)));
+    if (reset) CK(cudaMemsetAsync(ctx->sat_dev, 0, 4, S(s)));
+    CK(cudaStreamSynchronize(S(s)));
+    *count = v;
+    return CDC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- tools header
+int cdc_set_plan_option(cdc_ctx* ctx, int option, int value) {
+    if (!ctx) return CDC_ERR_STATE;
+    if (option < 0 || option >= CDC_OPT_COUNT || value < 0) return ctx->fail(CDC_ERR_SHAPE, "unknown plan option %d / negative value", option);
+    if (ctx->opts.v[option] != value) {
+        ctx->opts.v[option] = value;
+        ctx->opts_dirty = true;
+    }
+    return CDC_OK;
+}
+
 int cdc_num_step_ops(cdc_ctx* ctx) { return ctx ? static_cast<int>(ctx->step_ops.size()) : 0; }
 const char* cdc_step_op_name(cdc_ctx* ctx, int i) {
     return (ctx && i >= 0 && i < static_cast<int>(ctx->step_ops.size())) ? ctx->step_ops[i].name.c_str() : "";
@@ -1503,23 +1694,25 @@ double cdc_step_op_bytes(cdc_ctx* ctx, int i) {
 int cdc_run_step_op(cdc_ctx* ctx, int i, int k, cdc_stream s) {
     NEED_PLAN();
     if (i < 0 || i >= static_cast<int>(ctx->step_ops.size()) || k < 0 || k >= ctx->K) return ctx->fail(CDC_ERR_SHAPE, "bad op/step index");
-    CK(ctx->step_ops[i].run(S(s), k));
+    CK(ctx->step_ops[i].run(S(s), k, nullptr));
     return CDC_OK;
 }
 
-// Measurement only: leave a class of ops out of the captured graph (0 = none, 1 = the tcgen05 convs, 2 = the
+#ifdef CDC_TOOLS
+// Tools build only: leave a class of ops out of the captured graph (0 = none, 1 = the tcgen05 convs, 2 = the
 // elementwise / GroupNorm kernels, 3 = attention), so that a class's in-graph cost is the difference of two replay
-// times.  The decoded image is garbage while a class is skipped.
+// times.  The decoded image is garbage while a class is skipped: cdc_get_x / cdc_decode_host refuse to return it.
 int cdc_debug_graph_skip(cdc_ctx* ctx, int op_class) {
     if (!ctx || op_class < 0 || op_class > 3) return CDC_ERR_SHAPE;
     if (op_class != ctx->graph_skip) drop_graph(ctx);
     ctx->graph_skip = op_class;
     return CDC_OK;
 }
+#endif
 
 // Per-op device time of one denoise step, measured in stream order: all ops are enqueued back to back with an event
 // between consecutive launches (the host stays ahead of the GPU, so the differences are the ops' in-stream durations
-// including the inter-kernel gap -- what the captured graph replays), after `warm` untimed steps.
+// including the inter-kernel gap), after `warm` untimed steps.
 int cdc_profile_step(cdc_ctx* ctx, int k, int warm, float* us_out, cdc_stream s) {
     NEED_PLAN();
     if (k < 0 || k >= ctx->K || !us_out) return ctx->fail(CDC_ERR_SHAPE, "bad step index / output");
@@ -1527,10 +1720,10 @@ int cdc_profile_step(cdc_ctx* ctx, int k, int warm, float* us_out, cdc_stream s)
     std::vector<cudaEvent_t> ev(n + 1);
     for (auto& e : ev) CK(cudaEventCreate(&e));
     for (int w = 0; w < warm; ++w)
-        for (Op& op : ctx->step_ops) CK(op.run(S(s), k));
+        for (Op& op : ctx->step_ops) CK(op.run(S(s), k, nullptr));
     CK(cudaEventRecord(ev[0], S(s)));
     for (size_t i = 0; i < n; ++i) {
-        CK(ctx->step_ops[i].run(S(s), k));
+        CK(ctx->step_ops[i].run(S(s), k, nullptr));
         CK(cudaEventRecord(ev[i + 1], S(s)));
     }
     CK(cudaStreamSynchronize(S(s)));
@@ -1543,7 +1736,58 @@ int cdc_profile_step(cdc_ctx* ctx, int k, int warm, float* us_out, cdc_stream s)
     return CDC_OK;
 }
 
-// ---- stateless integer path ----
+// In-graph timing (include/cdc_b200_tools.h): the same captured K-step loop, every kernel stamping
+// (earliest CTA start, latest CTA end) in globaltimer ns into its own slot.
+int cdc_profile_graph(cdc_ctx* ctx, int reps, float* start_us, float* dur_us, cdc_stream s) {
+    NEED_PLAN();
+    if (ctx->K < 1) return ctx->fail(CDC_ERR_STATE, "call cdc_set_schedule first");
+    if (reps < 1 || reps > 64 || !start_us || !dur_us) return ctx->fail(CDC_ERR_SHAPE, "reps must be in 1..64, outputs non-null");
+    const size_t nops = ctx->step_ops.size(), n = static_cast<size_t>(ctx->K) * nops;
+    long long* dev = nullptr;
+    CK(cudaMalloc(&dev, n * 2 * sizeof(long long)));
+    std::vector<long long> init(n * 2), got(n * 2);
+    for (size_t i = 0; i < n; ++i) {
+        init[2 * i] = -1;  // = ~0 as unsigned: atomicMin target
+        init[2 * i + 1] = 0;
+    }
+    cudaGraphExec_t gx = nullptr;
+    int r = capture_graph(ctx, &gx, dev);
+    if (r) {
+        cudaFree(dev);
+        return r;
+    }
+    std::vector<std::vector<float>> st(n), du(n);
+    cudaError_t e = cudaSuccess;
+    for (int it = 0; it <= reps && e == cudaSuccess; ++it) {  // replay 0 is the warm-up
+        e = cudaMemcpyAsync(dev, init.data(), n * 16, cudaMemcpyHostToDevice, S(s));
+        if (e == cudaSuccess) e = cudaGraphLaunch(gx, S(s));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(got.data(), dev, n * 16, cudaMemcpyDeviceToHost, S(s));
+        if (e == cudaSuccess) e = cudaStreamSynchronize(S(s));
+        if (e != cudaSuccess || it == 0) continue;
+        unsigned long long t0 = ~0ull;
+        for (size_t i = 0; i < n; ++i)
+            if (got[2 * i + 1] != 0 && static_cast<unsigned long long>(got[2 * i]) < t0) t0 = static_cast<unsigned long long>(got[2 * i]);
+        for (size_t i = 0; i < n; ++i) {
+            const bool ran = got[2 * i + 1] != 0;
+            st[i].push_back(ran ? static_cast<float>(static_cast<double>(static_cast<unsigned long long>(got[2 * i]) - t0) * 1e-3) : 0.0f);
+            du[i].push_back(ran ? static_cast<float>(static_cast<double>(got[2 * i + 1] - got[2 * i]) * 1e-3) : 0.0f);
+        }
+    }
+    cudaGraphExecDestroy(gx);
+    cudaFree(dev);
+    if (e != cudaSuccess) return ctx->fail(CDC_ERR_CUDA, "cdc_profile_graph: %s", cudaGetErrorString(e));
+    auto median = [](std::vector<float>& v) {
+        std::sort(v.begin(), v.end());
+        return v.empty() ? 0.0f : v[v.size() / 2];
+    };
+    for (size_t i = 0; i < n; ++i) {
+        start_us[i] = median(st[i]);
+        dur_us[i] = median(du[i]);
+    }
+    return CDC_OK;
+}
+
+// ---- stateless integer path (runs on the CURRENT device: the pointers' device) ----
 static int dev_sms() {
     int dev = 0, n = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
@@ -1561,6 +1805,7 @@ int cdc_cdf_lookup(const int32_t* q, const float* sigma, const int32_t* cdf, con
                    const int32_t* cdf_length, const int32_t* offset, const float* scale_table, int rows, int64_t inner,
                    int32_t* idx, int32_t* v, int32_t* lo, int32_t* hi, int32_t* raw, int64_t n, cdc_stream s) {
     if (n < 0 || rows < 1 || rows > 256 || (!sigma && inner < 1)) return CDC_ERR_SHAPE;
+    if (n > 0 && (!q || !cdf || !row_start || !cdf_length || !offset || !idx || !v || !lo || !hi || !raw)) return CDC_ERR_SHAPE;
     CdfTables t{cdf, row_start, cdf_length, offset, scale_table, rows};
     return launch_cdf_lookup(q, sigma, t, inner, idx, v, lo, hi, raw, n, dev_sms(), S(s)) == cudaSuccess ? CDC_OK
                                                                                                         : CDC_ERR_CUDA;
@@ -1572,6 +1817,7 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
                   const void* residual, void* out, int64_t* gn_sums, cdc_stream s) {
     cdc_ctx tmp;
     cdc_ctx* ctx = &tmp;
+    DevGuard guard(device);
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) {
@@ -1619,8 +1865,13 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
         cb.cpg = cout / 32;
         cb.gn_acc = reinterpret_cast<gn_sum_t*>(gn_sums);
     }
-    ConvW cwr;  // tools (CDC_TEST_CONV_RES=1): time the conv with a 1x1 residual conv of the same input riding along
     void* res_buf = nullptr;
+    void* in_gn = nullptr;
+#ifdef CDC_TOOLS
+    long long* dbg = nullptr;
+    long long* dbg_dev = nullptr;
+    std::vector<long long> dbg_host(2048, 0);
+    ConvW cwr;  // tools (CDC_TEST_CONV_RES=1): time the conv with a 1x1 residual conv of the same input riding along
     if (getenv("CDC_TEST_CONV_RES") && gn_sums && ksize == 3 && mode == MODE_S1) {
         // its weights: the centre tap of the 3x3 weights is as good as any for timing -- w_oihw[o][i][1][1]
         std::vector<float> w33(static_cast<size_t>(cout) * cin * 9), w11(static_cast<size_t>(cout) * cin);
@@ -1639,18 +1890,16 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
             cb.res_out.H = H;
             cb.res_out.W = W;
             KfGeom kgr;
-            if (!(conv_uses_kf(cb, B, prop.multiProcessorCount, &kgr) && kgr.res)) cb.res_w = nullptr;
+            if (!(conv_uses_kf(cb, B, prop.multiProcessorCount, tmp.opts, &kgr) && kgr.res)) cb.res_w = nullptr;
         }
         printf("test_conv: 1x1 residual conv fused: %s\n", cb.res_w ? "yes" : "no");
     }
-    void* in_gn = nullptr;  // tools (CDC_TEST_CONV_APPLY=1): time the conv with the input GroupNorm fused -- unit statistics
+    // tools (CDC_TEST_CONV_APPLY=1): time the conv with the input GroupNorm fused -- unit statistics
     if (getenv("CDC_TEST_CONV_APPLY") && gn_sums && c1 == 0 && cout == cin) {
         const int cpg_in = cin / 32;
-        std::vector<long long> acc(static_cast<size_t>(B) * 64);
-        for (size_t i = 0; i < acc.size(); i += 2) {
-            acc[i] = 0;
-            acc[i + 1] = static_cast<long long>(cpg_in) * H * W * (1LL << 20);  // mean 0, variance 1
-        }
+        std::vector<long long> acc(static_cast<size_t>(B) * kGnImgStride, 0);
+        for (size_t i = 0; i < acc.size(); i += kGnVals)
+            acc[i + 2] = static_cast<long long>(cpg_in) * H * W / 1024;  // mean 0, variance ~1 (squares_hi counts 1024s)
         std::vector<float> gb(2 * cin, 0.0f);
         for (int i = 0; i < cin; ++i) gb[i] = 1.0f;
         CK(cudaMalloc(&in_gn, acc.size() * 8 + gb.size() * 4));
@@ -1660,12 +1909,9 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
         cb.in_gamma = reinterpret_cast<const float*>(static_cast<char*>(in_gn) + acc.size() * 8);
         cb.in_beta = cb.in_gamma + cin;
         KfGeom kga;
-        if (!(conv_uses_kf(cb, B, prop.multiProcessorCount, &kga) && kga.apply)) cb.in_acc = nullptr;
+        if (!(conv_uses_kf(cb, B, prop.multiProcessorCount, tmp.opts, &kga) && kga.apply)) cb.in_acc = nullptr;
         printf("test_conv: input GroupNorm fused: %s\n", cb.in_acc ? "yes" : "no");
     }
-    long long* dbg = nullptr;
-    long long* dbg_dev = nullptr;
-    std::vector<long long> dbg_host(2048, 0);
     if (getenv("CDC_STRIP_DEBUG")) {
         // plain device memory (managed memory would page-fault inside the timed regions)
         cudaMalloc(&dbg_dev, 2048 * sizeof(long long));
@@ -1674,16 +1920,18 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
         cudaMemcpy(dbg_dev, init.data(), 2048 * sizeof(long long), cudaMemcpyHostToDevice);
         cb.dbg = dbg_dev;
     }
+#endif
     Op op;
     std::string e;
-    r = build_conv(cb, B, prop.multiProcessorCount, &op, &e);
+    r = build_conv(cb, B, prop.multiProcessorCount, tmp.opts, &op, &e);
     if (r) {
         g_create_err = e;
         ar.release();
         return r;
     }
-    cudaError_t ce = op.run(S(s), 0);
+    cudaError_t ce = op.run(S(s), 0, nullptr);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(S(s));
+#ifdef CDC_TOOLS
     if (ce == cudaSuccess && getenv("CDC_TEST_CONV_REPS")) {  // tools/conv_bench.py: device time of the conv launch alone
         const int reps = atoi(getenv("CDC_TEST_CONV_REPS"));
         void* flush = nullptr;
@@ -1696,7 +1944,7 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
             for (int i = 0; i < reps && ce == cudaSuccess; ++i) {
                 cudaMemsetAsync(flush, i, fb, S(s));
                 cudaEventRecord(e0, S(s));
-                ce = op.run(S(s), 0);
+                ce = op.run(S(s), 0, nullptr);
                 cudaEventRecord(e1, S(s));
                 cudaStreamSynchronize(S(s));
                 float ms = 0.f;
@@ -1717,7 +1965,7 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
         dbg = dbg_host.data();
     }
     KfGeom kgd;
-    if (dbg && conv_uses_kf(cb, B, prop.multiProcessorCount, &kgd)) {
+    if (dbg && conv_uses_kf(cb, B, prop.multiProcessorCount, tmp.opts, &kgd)) {
         printf("kf issuer timeline (CTA 0, first strip; S=%d NS=%d staged=%d): row: issue_a wait_next issue_b | since previous row start\n", kgd.S,
                kgd.NS, kgd.staged ? 1 : 0);
         for (int i = 0; i < 40 && dbg[i * 4 + 3]; ++i)
@@ -1747,6 +1995,7 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
         }
         dbg = nullptr;
     }
+#endif
     ar.release();
     if (in_gn) cudaFree(in_gn);
     if (res_buf) cudaFree(res_buf);
@@ -1758,10 +2007,14 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
 }
 
 int cdc_test_attention(const void* qkv, void* out, int B, int N, int heads, cdc_stream s) {
+    if (!qkv || !out || B < 1 || N < 1 || heads < 1) return CDC_ERR_SHAPE;
+    if (configure_attention_tc() != cudaSuccess) return CDC_ERR_CUDA;
+#ifdef CDC_TOOLS
     if (attention_legacy())
         return launch_attention(static_cast<const act_t*>(qkv), static_cast<act_t*>(out), B, N, heads, S(s)) == cudaSuccess
                    ? CDC_OK
                    : CDC_ERR_CUDA;
+#endif
     AttnTcParams ap;
     memset(&ap, 0, sizeof ap);
     if (encode_qkv_map(&ap.qkv_map, static_cast<const act_t*>(qkv), 3 * heads * 64, N, B)) return CDC_ERR_CUDA;
@@ -1774,8 +2027,8 @@ int cdc_test_attention(const void* qkv, void* out, int B, int N, int heads, cdc_
 int cdc_test_gn(const void* x, const void* r, void* y, const float* gamma, const float* beta, const float* film, int B,
                 int HW, int C, int silu, float eps, cdc_stream s) {
     gn_sum_t* acc = nullptr;
-    if (cudaMalloc(&acc, static_cast<size_t>(B) * 64 * sizeof(gn_sum_t)) != cudaSuccess) return CDC_ERR_CUDA;
-    cudaError_t e = cudaMemsetAsync(acc, 0, static_cast<size_t>(B) * 64 * sizeof(gn_sum_t), S(s));
+    if (cudaMalloc(&acc, static_cast<size_t>(B) * kGnImgStride * sizeof(gn_sum_t)) != cudaSuccess) return CDC_ERR_CUDA;
+    cudaError_t e = cudaMemsetAsync(acc, 0, static_cast<size_t>(B) * kGnImgStride * sizeof(gn_sum_t), S(s));
     if (e == cudaSuccess) e = launch_gn_stats(static_cast<const act_t*>(x), acc, B, HW, C, S(s));
     if (e == cudaSuccess)
         e = launch_gn_apply(static_cast<const act_t*>(x), acc, gamma, beta, film, eps, static_cast<const act_t*>(r),

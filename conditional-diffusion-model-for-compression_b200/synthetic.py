@@ -74,3 +74,23 @@ def latent(B, H, W, index=0, ch=256):
 def init_noise(B, H, W, index=0, gamma=0.8):
     g = torch.Generator().manual_seed(2000 + index)
     return gamma * torch.randn(B, 3, H, W, generator=g)
+
+
+def entropy_inputs(n, seed=3000):
+    """(y, mu, sigma) of the integer path: sigma = exp(U[ln .05, ln 300]) -- beyond both ends of the
+    scale table --, y - mu ~ sigma * randn plus 0.1 % outliers at +-(5..50) sigma (escapes)."""
+    g = torch.Generator().manual_seed(seed)
+    u = torch.rand(n, generator=g)
+    sigma = torch.exp(math.log(0.05) + u * (math.log(300.0) - math.log(0.05)))
+    mu = 3.0 * torch.randn(n, generator=g)
+    r = sigma * torch.randn(n, generator=g)
+    outlier = torch.rand(n, generator=g) < 1e-3
+    mag = (5.0 + 45.0 * torch.rand(n, generator=g)) * sigma
+    sgn = torch.where(torch.rand(n, generator=g) < 0.5, -1.0, 1.0)
+    r = torch.where(outlier, sgn * mag, r)
+    return (mu + r).float(), mu.float(), sigma.float()
+
+
+def gaussian_tables():
+    from .entropy_tables import gaussian_tables as build
+    return build()

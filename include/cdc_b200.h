@@ -53,7 +53,7 @@ typedef struct {
 int cdc_create(const cdc_config* cfg, int device, cdc_ctx** out);
 void cdc_destroy(cdc_ctx* ctx);
 const char* cdc_last_error(cdc_ctx* ctx); /* ctx may be NULL: last error of a failed cdc_create */
-int cdc_abi_version(void);
+int cdc_abi_version(void); /* 2 */
 int cdc_act_dtype(void); /* storage / MMA operand type of activations: 1 = fp16 (default build), 0 = bf16 */
 
 /* ---- weights: oracle/unet.py UNet.state_dict() (+ "context." + oracle/codec.py ContextNet) ----
@@ -69,6 +69,16 @@ int cdc_has_context_net(cdc_ctx* ctx);
 int cdc_set_schedule(cdc_ctx* ctx, int steps);
 int cdc_schedule_index(cdc_ctx* ctx, int k);              /* training index idx_k, or <0 */
 int cdc_schedule_coeffs(cdc_ctx* ctx, int k, float* c0, float* c1);
+/* sampler variant (oracle/sampler.py make_schedule(..., eta, pred)): pred_eps = 0 the network
+ * predicts x0 (default), 1 it predicts the noise; eta >= 0 is the DDIM stochasticity (0 = deterministic), seed keys the
+ * counter-based noise z(seed, step, pixel).  Takes effect at the next cdc_set_schedule. */
+int cdc_set_sampler(cdc_ctx* ctx, int pred_eps, float eta, uint64_t seed);
+/* all five coefficients of step k: x0 = e0*x_t + e1*out; x_prev = c0*clamp(x0) + c1*x_t + sigma*z */
+int cdc_schedule_coeffs5(cdc_ctx* ctx, int k, float* c0, float* c1, float* e0, float* e1, float* sigma);
+/* oracle/unet.py TimeEmbed + RB.film for every step of the schedule: floats per step, and the table
+ * [steps][cdc_film_size] (18 ResBlocks x (scale | shift)) copied to a device buffer */
+int cdc_film_size(cdc_ctx* ctx);
+int cdc_get_film(cdc_ctx* ctx, float* film_dev, cdc_stream s);
 
 /* ---- shape binding: allocates the workspace arena, builds tensor maps and the launch plan ------ */
 int cdc_bind_io(cdc_ctx* ctx, int batch, int height, int width);
@@ -77,6 +87,9 @@ int cdc_set_latent(cdc_ctx* ctx, const float* y_hat, cdc_stream s); /* runs the 
 int cdc_set_x(cdc_ctx* ctx, const float* x_nchw, cdc_stream s);
 int cdc_get_x(cdc_ctx* ctx, float* x_nchw, int to_image01, cdc_stream s);
 int cdc_get_x0(cdc_ctx* ctx, float* x0_nchw, cdc_stream s); /* raw x0_hat of the last step (predict_x0) */
+/* the bound context maps (oracle/codec.py ContextNet.forward output, or what cdc_set_cond stored): NCHW fp32
+ * c_i [B, C_i, H >> i, W >> i]; any pointer may be NULL to skip that level */
+int cdc_get_cond(cdc_ctx* ctx, float* c0, float* c1, float* c2, float* c3, cdc_stream s);
 
 /* ---- oracle/sampler.py OracleDecoder.denoise_step / decode ------------------------------------ */
 int cdc_denoise_step(cdc_ctx* ctx, int k, cdc_stream s); /* x <- c0_k*clamp(unet(x, idx_k, cond)) + c1_k*x */
@@ -87,18 +100,10 @@ int cdc_decode_host(cdc_ctx* ctx, const float* latent_host, const float* xT_host
 int cdc_launches_per_step(cdc_ctx* ctx);
 int cdc_launches_context(cdc_ctx* ctx);
 double cdc_flops_per_step(cdc_ctx* ctx); /* algorithmic, SURVEY.md section 8d rule */
-
-/* ---- per-layer access for tests / profiling ---------------------------------------------------- */
-int cdc_num_step_ops(cdc_ctx* ctx);
-const char* cdc_step_op_name(cdc_ctx* ctx, int i);
-double cdc_step_op_flops(cdc_ctx* ctx, int i);
-double cdc_step_op_bytes(cdc_ctx* ctx, int i);
-int cdc_run_step_op(cdc_ctx* ctx, int i, int k, cdc_stream s);
-/* in-stream device time (microseconds) of every op of step k, after `warm` untimed steps; us_out[cdc_num_step_ops] */
-int cdc_profile_step(cdc_ctx* ctx, int k, int warm, float* us_out, cdc_stream s);
-/* measurement only: leave a class of ops out of the captured graph (0 none, 1 tcgen05 convs, 2 elementwise/GroupNorm,
- * 3 attention) so that the class's in-graph cost is a difference of replay times; the image is garbage meanwhile */
-int cdc_debug_graph_skip(cdc_ctx* ctx, int op_class);
+/* fp16 storage diagnostics: number of epilogue passes (thread x tile) that met a value beyond +-65504 and stored it
+ * saturated since the context was created or the counter last reset.  0 with the synthetic weights; a trained
+ * checkpoint that makes this non-zero is losing accuracy silently otherwise.  Synchronises the stream. */
+int cdc_saturation_count(cdc_ctx* ctx, uint64_t* count, int reset, cdc_stream s);
 
 /* ---- oracle/entropy.py quantize_symbols / cdf_lookup (stateless) ------------------------------- */
 /* q = rint(y - mu) int32 (half-to-even), y_hat = q + mu.  mu_mod == 0: mu is elementwise;
@@ -110,17 +115,6 @@ int cdc_cdf_lookup(const int32_t* q, const float* sigma, const int32_t* cdf, con
                    const int32_t* cdf_length, const int32_t* offset, const float* scale_table, int rows,
                    int64_t inner, int32_t* idx, int32_t* v, int32_t* lo, int32_t* hi, int32_t* raw, int64_t n,
                    cdc_stream s);
-
-/* ---- single-op entry points for kernel-level parity tests -------------------------------------- */
-/* conv: x NHWC 16-bit (cdc_act_dtype) sources (1 or 2), w OIHW fp32 (device), bias fp32; mode 0 = stride 1,
- * 1 = stride 2, 2 = nearest-x2 input; out NHWC 16-bit; gn_sums (optional, ZERO on entry): GroupNorm statistics of the
- * output, [B][32 groups][2] = (sum, sum of squares) as 64-bit fixed point with 20 fractional bits. */
-int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1, int B, int H, int W,
-                  const float* w_oihw, const float* bias, int cout, int ksize, int mode, int force_bn,
-                  const void* residual, void* out, int64_t* gn_sums, cdc_stream s);
-int cdc_test_attention(const void* qkv, void* out, int B, int N, int heads, cdc_stream s);
-int cdc_test_gn(const void* x, const void* r, void* y, const float* gamma, const float* beta, const float* film,
-                int B, int HW, int C, int silu, float eps, cdc_stream s);
 
 #ifdef __cplusplus
 }

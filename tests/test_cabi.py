@@ -12,20 +12,58 @@ PKG = os.path.join(ROOT, "conditional-diffusion-model-for-compression_b200")
 @pytest.fixture(scope="module")
 def built():
     import __graft_entry__ as g
-    if not os.path.exists(os.path.join(PKG, "libcdc_b200.so")):
+    if not all(os.path.exists(os.path.join(PKG, n)) for n in ("libcdc_b200.so", "libcdc_b200_bf16.so", "libcdc_b200_tools.so")):
         g.build()
     return True
 
 
+def _declared(header):
+    hdr = open(os.path.join(ROOT, "include", header)).read()
+    hdr = re.sub(r"#ifdef CDC_TOOLS.*?#endif", "", hdr, flags=re.S)  # tools-build-only declarations
+    return set(re.findall(r"\b(cdc_[a-z0-9_]+)\s*\(", hdr)) - {"cdc_b200"}
+
+
 def test_header_symbols_are_exported(built):
+    """The product library exports exactly what the two headers declare: the drop-in boundary (cdc_b200.h) and the
+    test / profiling entry points (cdc_b200_tools.h); the measurement hook that corrupts results is NOT in it."""
     from cdc_b200 import _ffi
-    hdr = open(os.path.join(ROOT, "include", "cdc_b200.h")).read()
-    declared = set(re.findall(r"\b(cdc_[a-z0-9_]+)\s*\(", hdr)) - {"cdc_b200"}
-    assert declared == set(_ffi.SYMBOLS), declared ^ set(_ffi.SYMBOLS)
+    assert _declared("cdc_b200.h") == set(_ffi.SYMBOLS), _declared("cdc_b200.h") ^ set(_ffi.SYMBOLS)
+    assert _declared("cdc_b200_tools.h") == set(_ffi.TOOLS_SYMBOLS), _declared("cdc_b200_tools.h") ^ set(_ffi.TOOLS_SYMBOLS)
     L = _ffi.lib()
-    for s in declared:
+    for s in _ffi.SYMBOLS + _ffi.TOOLS_SYMBOLS:
         assert hasattr(L, s), s
-    assert L.cdc_abi_version() == 1
+    assert L.cdc_abi_version() == 2
+    assert L.cdc_act_dtype() == 1
+    assert not hasattr(L, "cdc_debug_graph_skip")
+
+
+def test_variant_builds_load(built):
+    """build() also produces the bf16 variant (precision tests) and the tools variant (A/B switches, graph-skip hook)."""
+    from cdc_b200 import _ffi
+    assert _ffi.lib("bf16").cdc_act_dtype() == 0
+    T = _ffi.lib("tools")
+    assert T.cdc_act_dtype() == 1 and hasattr(T, "cdc_debug_graph_skip")
+
+
+def test_product_reads_no_environment(built):
+    """Environment switches exist only under -DCDC_TOOLS: the product sources may not call getenv outside such blocks."""
+    csrc = os.path.join(PKG, "csrc")
+    for f in sorted(os.listdir(csrc)):
+        if not f.endswith((".cu", ".cuh")):
+            continue
+        src = open(os.path.join(csrc, f)).read()
+        depth, tools = [], False
+        for ln in src.splitlines():
+            t = ln.strip()
+            if t.startswith("#if"):
+                depth.append(t.startswith("#ifdef CDC_TOOLS"))
+            elif t.startswith("#else") and depth:
+                depth[-1] = False if depth[-1] else depth[-1]
+            elif t.startswith("#endif") and depth:
+                depth.pop()
+            tools = any(depth)
+            if "getenv(" in ln and not ln.lstrip().startswith("//"):
+                assert tools, f"{f}: getenv outside #ifdef CDC_TOOLS: {ln.strip()}"
 
 
 def test_product_never_imports_the_oracle():

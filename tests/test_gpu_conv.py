@@ -1,4 +1,4 @@
-"""K-conv (tcgen05 implicit GEMM) parity on a real B200, every call through the C ABI (include/cdc_b200.h).
+"""K-conv (tcgen05 implicit GEMM) parity on a real B200, every call through the C ABI (kernel-level entry points: include/cdc_b200_tools.h).
 Checker: torch fp32 ops for the floating-point kernels, the CPU oracle for the integer path."""
 import ctypes as C
 import os
@@ -42,7 +42,8 @@ def _run_conv(srcs, w, b, ksize, mode, force_bn=0, residual=None, stats=False):
     s = [_nhwc_act(t) for t in srcs]
     out = torch.full((B, OH, OW, n_pad), float("nan"), device=DEV, dtype=_act_dtype())
     res = _nhwc_act(residual) if residual is not None else None
-    st = torch.zeros(B, 32, 2, device=DEV, dtype=torch.int64) if stats else None  # fixed point, 20 fractional bits
+    # [B][32][4] = (sum * 2^20, (squares mod 1024) * 2^20, floor(squares / 1024), unused): csrc/gn_sums.cuh
+    st = torch.zeros(B, 32, 4, device=DEV, dtype=torch.int64) if stats else None
     rc = L.cdc_test_conv(0, _ptr(s[0]), s[0].shape[-1], _ptr(s[1]) if len(s) > 1 else C.c_void_p(0),
                          s[1].shape[-1] if len(s) > 1 else 0, B, H, W, _ptr(w.contiguous()), _ptr(b.contiguous()),
                          cout, ksize, mode, force_bn, _ptr(res), _ptr(out), _ptr(st), C.c_void_p(0))
@@ -168,7 +169,8 @@ def test_conv_groupnorm_partials(cfg):
     o, part = _run_conv(srcs, w, b, 3, 0, fbn, stats=True)
     ref = _ref_conv(srcs, w, b, 3, 0)
     _check(o, ref, "stats-conv output")
-    got = part.double() / 2.0 ** 20  # [B, 32, 2] (sum, sum of squares) per image and group
+    pd = part.double()
+    got = torch.stack([pd[..., 0] / 2.0 ** 20, pd[..., 1] / 2.0 ** 20 + pd[..., 2] * 1024.0], dim=-1)  # (sum, sum of squares)
     rg = ref.double().reshape(B, 32, -1)
     want = torch.stack([rg.sum(-1), (rg * rg).sum(-1)], dim=-1)
     rel = (got - want).abs() / want.abs().clamp(min=1.0)

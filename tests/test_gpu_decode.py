@@ -135,18 +135,19 @@ def test_flops_and_launch_accounting():
 
 
 @pytest.mark.parametrize("shape", [(1, 256, 384), (2, 128, 192), (3, 64, 128), (1, 512, 768)])
-def test_fused_input_groupnorm_is_bit_identical(shape, monkeypatch):
+def test_fused_input_groupnorm_is_bit_identical(shape):
     """conv2 applying GroupNorm 1 + FiLM + SiLU to its input rows in shared memory (default) must reproduce, bit for bit,
-    the plan that runs the same arithmetic as a pass of its own (CDC_FUSE_APPLY=0): same fp16 activations, same MMA order."""
-    from cdc_b200 import CDCConfig, Decoder
+    the plan that runs the same arithmetic as a pass of its own (plan option FUSE_APPLY = 0): same fp16 activations, same
+    MMA order."""
+    from cdc_b200 import CDCConfig, Decoder, _ffi
     from cdc_b200.synthetic import init_noise, latent, random_weights
     B, H, W = shape
     w = random_weights(CDCConfig(), seed=0, with_context=True)
     lat, x = latent(B, H, W, index=3), init_noise(B, H, W, index=3)
     outs, n_gn1 = [], []
-    for fuse in ("1", "0"):
-        monkeypatch.setenv("CDC_FUSE_APPLY", fuse)
+    for fuse in (2, 0):
         d = Decoder(CDCConfig(), w, device=DEV)
+        d.set_plan_option(_ffi.OPT_FUSE_APPLY, fuse)
         outs.append(d.decode(lat, 3, init=x).clone())
         n_gn1.append(sum(1 for o in d.step_ops() if ".gn1." in o[0]))
         del d

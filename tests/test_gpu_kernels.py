@@ -1,4 +1,4 @@
-"""Kernel-level parity on a real B200, every call through the C ABI (include/cdc_b200.h).
+"""Kernel-level parity on a real B200, every call through the C ABI (include/cdc_b200.h, kernel-level entry points in include/cdc_b200_tools.h).
 Checker: torch fp32 ops for the floating-point kernels, the CPU oracle for the integer path."""
 import ctypes as C
 import os
@@ -30,38 +30,6 @@ def _act_dtype():
 
 def _nhwc_act(t):
     return t.permute(0, 2, 3, 1).contiguous().to(_act_dtype())
-
-
-def _run_conv(srcs, w, b, ksize, mode, force_bn=0, residual=None, stats=False):
-    """srcs: list of NCHW fp32 cuda tensors (bf16-exact).  Returns (out NCHW fp32, GroupNorm sums or None)."""
-    L = _lib()
-    B, _, H, W = srcs[0].shape
-    cout = w.shape[0]
-    n_pad = (cout + 63) // 64 * 64
-    OH, OW = (H // 2, W // 2) if mode == 1 else ((2 * H, 2 * W) if mode == 2 else (H, W))
-    s = [_nhwc_act(t) for t in srcs]
-    out = torch.full((B, OH, OW, n_pad), float("nan"), device=DEV, dtype=_act_dtype())
-    res = _nhwc_act(residual) if residual is not None else None
-    st = torch.zeros(B * (OH * OW // 64 + 64) * 64, device=DEV, dtype=torch.float32) if stats else None
-    pt = C.c_int(0)
-    rc = L.cdc_test_conv(0, _ptr(s[0]), s[0].shape[-1], _ptr(s[1]) if len(s) > 1 else C.c_void_p(0),
-                         s[1].shape[-1] if len(s) > 1 else 0, B, H, W, _ptr(w.contiguous()), _ptr(b.contiguous()),
-                         cout, ksize, mode, force_bn, _ptr(res), _ptr(out), _ptr(st), C.byref(pt), C.c_void_p(0))
-    assert rc == 0, L.cdc_last_error(None).decode()
-    torch.cuda.synchronize()
-    o = out[..., :cout].float().permute(0, 3, 1, 2).contiguous()
-    part = st[: B * pt.value * 64].reshape(B, pt.value, 32, 2) if stats else None
-    return o, part
-
-
-def _ref_conv(srcs, w, b, ksize, mode, residual=None):
-    x = torch.cat(srcs, dim=1)
-    if mode == 2:
-        x = F.interpolate(x, scale_factor=2, mode="nearest")
-    y = F.conv2d(x, w, b, stride=2 if mode == 1 else 1, padding=ksize // 2)
-    if residual is not None:
-        y = y + residual
-    return y
 
 
 def _mk(shape, seed, scale=1.0):

@@ -1,0 +1,434 @@
+"""Round-2 parity tests on a real B200 (VERDICT r1 "next round" items 1, 2, 9): the headline configuration under
+driver-run oracle parity, the K = 100 schedule, the 2048 x 2048 / 16384-token shape, tensor-level context-net and FiLM
+checks, large-magnitude activations, the bf16 variant's measured miss, the sampler variants of row f4, and the hardened
+host interface.  Checker: the CPU oracle (oracle/), self-pinned -- the reference ships no code."""
+import ctypes as C
+import os
+import time
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+DEV = "cuda:0"
+TOL = 1e-2  # BASELINE.json north_star: within 1e-2 max-abs of the fp32 oracle per step
+
+_cache = {}
+
+
+def _setup(with_context=False, variant="product"):
+    key = (with_context, variant)
+    if key in _cache:
+        return _cache[key]
+    from cdc_b200 import CDCConfig, Decoder
+    from oracle.config import CDCConfig as OCfg
+    from oracle.sampler import OracleDecoder
+    from oracle.weights import build_codec, build_unet
+    torch.set_num_threads(os.cpu_count())
+    ocfg = OCfg()
+    net = build_unet(ocfg, seed=0).to(memory_format=torch.channels_last)
+    weights = dict(net.state_dict())
+    codec = None
+    if with_context:
+        codec = build_codec(ocfg, seed=1)
+        weights.update({"context." + k: v for k, v in codec.context.state_dict().items()})
+    dec = Decoder(CDCConfig(), weights, device=DEV, variant=variant)
+    orc = OracleDecoder(ocfg, net, context_net=codec.context if codec else None)
+    _cache[key] = (dec, orc, ocfg, codec)
+    return _cache[key]
+
+
+# ---------------------------------------------------------------------------------------------------- headline config
+def test_headline_768x512_all_17_steps_teacher_forced():
+    """BASELINE.json configs[1]: 1 x 512 x 768, 17-step DDIM.  The oracle runs the whole trajectory; the GPU step is fed
+    the oracle's x_t at EVERY k and x_prev must agree within 1e-2; the raw x0_hat is held to 3e-2 at noisy
+    steps (it is multiplied by c0 <= 0.3 there before it reaches x_prev) and to 1e-2 on the last step, where it IS the image."""
+    from oracle.weights import synthetic_cond, synthetic_init
+    dec, orc, ocfg, _ = _setup()
+    B, H, W, K = 1, 512, 768, 17
+    dec.set_sample_schedule(K)
+    orc.set_sample_schedule(K)
+    assert dec.idx == orc.sched.idx
+    cond = synthetic_cond(ocfg, B, H, W, index=11)
+    x = synthetic_init(B, H, W, index=11)
+    worst, worst_k, t0 = 0.0, -1, time.time()
+    sat0 = None
+    for k in range(K):
+        t = orc.sched.idx[k]
+        x0_ref = orc.predict_x0(x, t, cond)
+        xp_ref = float(orc.sched.c0[k]) * x0_ref.clamp(-1, 1) + float(orc.sched.c1[k]) * x
+        xp = dec.denoise_step(x, t, cond if k == 0 else None).cpu()
+        if sat0 is None:
+            sat0 = dec.saturation_count()
+        x0 = dec._get_x0().cpu()
+        e0 = (x0 - x0_ref).abs().max().item()
+        e1 = (xp - xp_ref).abs().max().item()
+        print(f"768x512 k={k:2d} t={t:3d}: max|x0-ref|={e0:.5f} max|x_prev-ref|={e1:.5f}")
+        assert torch.isfinite(xp).all()
+        assert e1 <= TOL, f"k={k}: x_prev max-abs {e1}"
+        assert e0 <= (TOL if k == K - 1 else 3 * TOL), f"k={k}: x0_hat max-abs {e0}"
+        if e1 > worst:
+            worst, worst_k = e1, k
+        x = xp_ref  # teacher forcing: the oracle's own next state
+    print(f"768x512: worst step k={worst_k} max-abs {worst:.5f} ({time.time() - t0:.1f} s incl. the oracle)")
+    assert dec.saturation_count() == 0 and sat0 == 0
+
+
+def test_cfg3_batch16_256_k100_schedule_and_steps():
+    """BASELINE.json configs[2]: 16 x 256 x 256, 100-step DDIM: every idx / c0 / c1 of the K = 100 schedule equals the
+    oracle's, and teacher-forced steps at the first, a middle and the last index agree within 1e-2."""
+    from oracle.weights import synthetic_cond, synthetic_init
+    dec, orc, ocfg, _ = _setup()
+    B, H, W, K = 16, 256, 256, 100
+    dec.set_sample_schedule(K)
+    orc.set_sample_schedule(K)
+    assert dec.idx == orc.sched.idx
+    for k in range(K):
+        c0, c1 = dec.coeffs(k)
+        assert c0 == float(orc.sched.c0[k]) and c1 == float(orc.sched.c1[k]), k
+    cond = synthetic_cond(ocfg, B, H, W, index=5)
+    x = synthetic_init(B, H, W, index=5)
+    for k in (0, 57, 99):
+        t = orc.sched.idx[k]
+        ref = orc.denoise_step(x, t, cond)
+        got = dec.denoise_step(x, t, cond if k == 0 else None).cpu()
+        e = (got - ref).abs().max().item()
+        print(f"16x256x256 K=100 k={k} t={t}: max|x_prev-ref|={e:.5f}")
+        assert torch.isfinite(got).all() and e <= TOL
+    dec.bind(1, 64, 64)  # release the 16-image workspace
+
+
+def test_cfg5_2048x2048_step_with_16384_attention_tokens():
+    """BASELINE.json configs[4] decode shape: one teacher-forced step at 1 x 2048 x 2048 (attention over 16384 tokens)."""
+    from oracle.weights import synthetic_cond, synthetic_init
+    dec, orc, ocfg, _ = _setup()
+    B, H, W, K = 1, 2048, 2048, 17
+    dec.set_sample_schedule(K)
+    orc.set_sample_schedule(K)
+    cond = synthetic_cond(ocfg, B, H, W, index=2)
+    x = synthetic_init(B, H, W, index=2)
+    t = 500
+    t0 = time.time()
+    ref = orc.denoise_step(x, t, cond)
+    t1 = time.time()
+    got = dec.denoise_step(x, t, cond).cpu()
+    e = (got - ref).abs().max().item()
+    print(f"2048x2048 t={t}: max|x_prev-ref|={e:.5f} (oracle {t1 - t0:.1f} s)")
+    assert torch.isfinite(got).all() and e <= TOL
+    assert dec.saturation_count() == 0
+    dec.bind(1, 64, 64)  # release the 17 GB workspace
+
+
+def test_attention_16384_tokens_matches_sdpa():
+    from cdc_b200 import _ffi
+    L = _ffi.lib()
+    dt = torch.float16 if L.cdc_act_dtype() == 1 else torch.bfloat16
+    g = torch.Generator().manual_seed(41)
+    B, N = 1, 16384
+    qkv = (1.5 * torch.randn(B, N, 768, generator=g)).bfloat16().float().to(DEV).to(dt)
+    out = torch.empty(B, N, 256, device=DEV, dtype=dt)
+    assert L.cdc_test_attention(C.c_void_p(qkv.data_ptr()), C.c_void_p(out.data_ptr()), B, N, 4, C.c_void_p(0)) == 0
+    torch.cuda.synchronize()
+    q, k, v = [t.float().reshape(B, N, 4, 64).transpose(1, 2) for t in qkv.split(256, dim=-1)]
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, 256)
+    err = (out.float() - ref).abs().max().item()
+    print(f"attention N=16384: max err {err:.5f}")
+    assert err < (2e-2 if dt == torch.bfloat16 else 4e-3)
+
+
+# ---------------------------------------------------------------------------------------------------- context net, FiLM
+def test_context_net_tensor_level_parity():
+    """cond = context_net(y_hat) on the GPU (cdc_set_latent) against oracle/codec.py ContextNet, level by level."""
+    from oracle.weights import synthetic_latent
+    dec, orc, ocfg, codec = _setup(with_context=True)
+    B, H, W = 2, 128, 192
+    lat = synthetic_latent(B, H, W, index=4)
+    with torch.no_grad():
+        ref = orc.context_net(lat)
+    dec.set_latent(lat)
+    got = dec.get_cond()
+    for i, (g, r) in enumerate(zip(got, ref)):
+        assert g.shape == r.shape
+        e = (g.cpu() - r).abs().max().item()
+        print(f"context c{i} {tuple(r.shape)}: max-abs {e:.5f} (ref max {r.abs().max().item():.2f})")
+        assert e <= 5e-3, f"c{i}: {e}"
+    # set_cond / get_cond round trip: only the 16-bit storage rounding
+    dec.set_cond(ref)
+    for g, r in zip(dec.get_cond(), ref):
+        assert (g.cpu() - r).abs().max().item() <= 2e-3 * max(1.0, r.abs().max().item())
+
+
+def test_context_net_matches_committed_golden_vectors():
+    """tests/golden/codec_128.npz (oracle/make_golden.py): y_hat = q + mu of a 128 x 128 image -> c3 and the subsampled c0."""
+    dec, _, _, _ = _setup(with_context=True)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "codec_128.npz"))
+    y_hat = torch.from_numpy(g["q"].astype(np.float32) + g["mu"])
+    dec.set_latent(y_hat)
+    c = dec.get_cond()
+    e3 = (c[3].cpu() - torch.from_numpy(g["c3"])).abs().max().item()
+    e0 = (c[0][:, :, ::8, ::8].cpu() - torch.from_numpy(g["c0_sub"])).abs().max().item()
+    print(f"golden codec_128: c3 max-abs {e3:.5f}, c0[::8, ::8] max-abs {e0:.5f}")
+    assert e3 <= 5e-3 and e0 <= 5e-3
+
+
+@pytest.mark.parametrize("K", [17, 100])
+def test_film_table_matches_oracle(K):
+    """Every step's 6144 FiLM floats (18 ResBlocks x (scale | shift)) against oracle/unet.py TimeEmbed + RB.film."""
+    dec, orc, ocfg, _ = _setup()
+    dec.set_sample_schedule(K)
+    orc.set_sample_schedule(K)
+    tab = dec.film_table().cpu()
+    net = orc.unet
+    rbs = []
+    for lvl in net.down:
+        rbs += [lvl.rb1, lvl.rb2]
+    rbs += [net.mid.rb1, net.mid.rb2]
+    for i in ("3", "2", "1", "0"):
+        rbs += [net.up[i].rb1, net.up[i].rb2]
+    assert tab.shape == (K, sum(2 * rb.film.out_features // 2 for rb in rbs)) and tab.shape[1] == 6144
+    with torch.no_grad():
+        te = net.temb(torch.tensor(orc.sched.idx, dtype=torch.int64))
+        ref = torch.cat([rb.film(F.silu(te)) for rb in rbs], dim=1)  # [K, 6144]; chunk(2) = (scale | shift) per block
+    e = (tab - ref).abs().max().item()
+    print(f"FiLM table K={K}: max-abs {e:.2e} (ref max {ref.abs().max().item():.3f})")
+    assert e <= 2e-5
+
+
+# ---------------------------------------------------------------------------------------------------- magnitude / dtype
+def _scaled_unet(scale):
+    from oracle.config import CDCConfig as OCfg
+    from oracle.sampler import OracleDecoder
+    from oracle.weights import build_unet
+    net = build_unet(OCfg(), seed=0)
+    with torch.no_grad():
+        # the residual stream is `scale` times larger from the stem to the last ResBlock (every conv sees inputs that much
+        # larger; GroupNorm normalises the branch, the identity / 1x1 residual path carries the scale on); the final conv
+        # undoes it, so x0_hat stays O(1) and comparable.  Powers of two: the weights stay bf16-exact.
+        net.stem.weight.mul_(scale)
+        net.stem.bias.mul_(scale)
+        net.final.weight.div_(scale)
+    return net, OracleDecoder(OCfg(), net)
+
+
+def test_large_magnitude_activations_x256_no_saturation_no_statistics_overflow():
+    """activations 256x larger than the synthetic weights produce (pre-GroupNorm values in the
+    hundreds to thousands) must neither saturate fp16 silently nor lose GroupNorm precision: parity still holds and the
+    saturation counter stays 0.  (GroupNorm normalises the scale away, so the oracle's output stays O(1).)"""
+    from cdc_b200 import CDCConfig, Decoder
+    from oracle.config import CDCConfig as OCfg
+    from oracle.weights import synthetic_cond, synthetic_init
+    net, orc = _scaled_unet(256.0)
+    dec = Decoder(CDCConfig(), dict(net.state_dict()), device=DEV)
+    dec.set_sample_schedule(17)
+    orc.set_sample_schedule(17)
+    B, H, W = 1, 256, 256
+    cond = synthetic_cond(OCfg(), B, H, W)
+    x = synthetic_init(B, H, W)
+    for t in (999, 0):
+        x0_ref = orc.predict_x0(x, t, cond)
+        ref = orc.denoise_step(x, t, cond)
+        got = dec.denoise_step(x, t, cond).cpu()
+        e = (got - ref).abs().max().item()
+        e0 = (dec._get_x0().cpu() - x0_ref).abs().max().item()
+        print(f"x256 activations t={t}: max|x_prev-ref|={e:.5f} max|x0-ref|={e0:.5f} (|x0_ref| max {x0_ref.abs().max().item():.2f})")
+        assert torch.isfinite(got).all() and e <= TOL and e0 <= 3 * TOL
+    assert dec.saturation_count() == 0
+
+
+def test_saturation_is_counted_not_silent():
+    """Scale far enough (2^17) and conv outputs leave the fp16 range: they are stored saturated AND counted."""
+    from cdc_b200 import CDCConfig, Decoder
+    from oracle.config import CDCConfig as OCfg
+    from oracle.weights import synthetic_cond, synthetic_init
+    if __import__("cdc_b200")._ffi.lib().cdc_act_dtype() != 1:
+        pytest.skip("bf16 build: fp32 range")
+    net, _ = _scaled_unet(float(2 ** 17))
+    dec = Decoder(CDCConfig(), dict(net.state_dict()), device=DEV)
+    dec.set_sample_schedule(17)
+    B, H, W = 1, 128, 128
+    got = dec.denoise_step(synthetic_init(B, H, W), 999, synthetic_cond(OCfg(), B, H, W))
+    assert torch.isfinite(got).all()  # saturating stores: never inf / nan
+    n = dec.saturation_count(reset=True)
+    print(f"saturation events with 2^17-scaled stem: {n}")
+    assert n > 0 and dec.saturation_count() == 0
+
+
+def test_bf16_variant_misses_the_tolerance_as_documented():
+    """north_star names bf16 AND 1e-2; DESIGN.md section 5 / BASELINE.md ratify fp16 because bf16 operands cannot meet
+    1e-2 on this network.  This runs the SAME sources built with -DCDC_ACT_FP16=0 through the same teacher-forced step
+    and pins the measured miss (0.02..0.04): if a change ever brings bf16 inside 1e-2 this test fails and the dtype
+    decision must be revisited."""
+    from oracle.weights import synthetic_cond, synthetic_init
+    dec, orc, ocfg, _ = _setup(variant="bf16")
+    assert dec.L.cdc_act_dtype() == 0
+    dec.set_sample_schedule(17)
+    orc.set_sample_schedule(17)
+    B, H, W = 1, 256, 256
+    cond, x = synthetic_cond(ocfg, B, H, W), synthetic_init(B, H, W)
+    worst = 0.0
+    for t in (999, 500, 0):
+        x0_ref = orc.predict_x0(x, t, cond)
+        dec.denoise_step(x, t, cond)
+        e0 = (dec._get_x0().cpu() - x0_ref).abs().max().item()
+        print(f"bf16 build t={t}: max|x0-ref|={e0:.5f}")
+        worst = max(worst, e0)
+    assert TOL < worst < 6e-2, worst
+
+
+# ---------------------------------------------------------------------------------------------------- sampler variants
+@pytest.mark.parametrize("K,pred,eta,ks", [(17, "x", 1.0, (0, 8, 15, 16)), (500, "eps", 0.0, (120, 250, 499)),
+                                           (500, "eps", 1.0, (120, 380, 499)), (100, "x", 0.5, (0, 50, 99))])
+def test_sampler_variants_teacher_forced(K, pred, eta, ks):
+    """eps-parameterisation, stochastic DDIM (eta > 0, Philox noise shared with the oracle),
+    500-step schedule.  All five coefficients equal the oracle's fp32 values; teacher-forced steps agree within 1e-2.
+    (eps-mode at k = 0 is not gated: abar_999 = 2.4e-9 makes x0 = 2e4 * (x_t - eps_hat), which flips clamp decisions.)"""
+    from oracle.weights import synthetic_cond, synthetic_init
+    dec, orc, ocfg, _ = _setup()
+    seed = 0x1234ABCD5678
+    dec.set_sample_schedule(K, eta=eta, pred=pred, seed=seed)
+    orc.set_sample_schedule(K, eta=eta, pred=pred, seed=seed)
+    sc = orc.sched
+    for k in range(K):
+        got = dec.coeffs5(k)
+        want = (float(sc.c0[k]), float(sc.c1[k]), float(sc.e0[k]), float(sc.e1[k]), float(sc.sg[k]))
+        assert got == want, (k, got, want)
+    B, H, W = 2, 128, 192
+    cond, x = synthetic_cond(ocfg, B, H, W, index=9), synthetic_init(B, H, W, index=9)
+    try:
+        for k in ks:
+            t = sc.idx[k]
+            ref = orc.denoise_step(x, t, cond)
+            got = dec.denoise_step(x, t, cond).cpu()
+            e = (got - ref).abs().max().item()
+            print(f"K={K} pred={pred} eta={eta} k={k} t={t} sigma={float(sc.sg[k]):.3f}: max|x_prev-ref|={e:.5f}")
+            assert torch.isfinite(got).all() and e <= TOL
+    finally:
+        dec.set_sample_schedule(17)  # back to the default sampler for the tests that share this decoder
+
+
+def test_stochastic_decode_graph_equals_eager_and_depends_on_seed():
+    from cdc_b200.synthetic import init_noise, latent
+    dec, _, _, _ = _setup(with_context=True)
+    B, H, W, K = 1, 128, 128, 6
+    lat, x = latent(B, H, W, index=1), init_noise(B, H, W, index=1)
+    try:
+        dec.set_sample_schedule(K, eta=1.0, seed=5)
+        a = dec.decode(lat.to(DEV), K, init=x.to(DEV)).clone()
+        xe = x.clone()
+        dec.set_latent(lat)
+        for k in range(K):
+            xe = dec.denoise_step(xe, dec.idx[k])
+        assert torch.equal(a, (xe.clamp(-1, 1) + 1) / 2)
+        assert torch.equal(a, dec.decode(lat.to(DEV), K, init=x.to(DEV)))
+        dec.set_sample_schedule(K, eta=1.0, seed=6)
+        b = dec.decode(lat.to(DEV), K, init=x.to(DEV))
+        assert not torch.equal(a, b) and torch.isfinite(b).all()
+    finally:
+        dec.set_sample_schedule(17)
+
+
+# ---------------------------------------------------------------------------------------------------- host interface
+def test_shape_validation_raises_before_touching_the_device():
+    from oracle.weights import synthetic_cond, synthetic_init
+    dec, _, ocfg, _ = _setup()
+    dec.set_sample_schedule(17)
+    cond = synthetic_cond(ocfg, 1, 128, 128)
+    dec.set_cond(cond)
+    with pytest.raises(ValueError):
+        dec.denoise_step(synthetic_init(1, 128, 192), 999)  # x does not match the bound size
+    with pytest.raises(ValueError):
+        dec.set_cond((cond[0], cond[1], cond[2], cond[3][:, :128]))  # wrong channels at level 3
+    with pytest.raises(ValueError):
+        dec.set_cond((cond[0], cond[1][:, :, :32], cond[2], cond[3]))  # wrong size at level 1
+    with pytest.raises(ValueError):
+        dec.decode(torch.zeros(1, 128, 8, 8), 17)  # latent channels
+    with pytest.raises(ValueError):
+        dec.decode(torch.zeros(1, 256, 8, 8), 17, init=torch.zeros(1, 3, 64, 64))
+    got = dec.denoise_step(synthetic_init(1, 128, 128), 999)  # the context is still usable
+    assert torch.isfinite(got).all()
+
+
+def test_null_arguments_are_errors_not_faults():
+    from cdc_b200 import _ffi
+    dec, _, _, _ = _setup()
+    L = dec.L
+    assert L.cdc_load_weights(dec.ctx, b"x", C.c_void_p(1), None, 2) != 0
+    dec.bind(1, 64, 64)
+    assert L.cdc_set_x(dec.ctx, None, None) != 0
+    assert L.cdc_set_cond(dec.ctx, None, None, None, None, None) != 0
+    assert L.cdc_get_x(dec.ctx, None, 0, None) != 0
+    assert b"null" in L.cdc_last_error(dec.ctx)
+    bad = _ffi.CdcConfig(64, (C.c_int32 * 4)(1, 2, 3, 8), 32, 8, 64, 256, 1000, 256, 1e-5)  # mults[3] = 8: N = 1536 qkv
+    ctx = C.c_void_p()
+    assert L.cdc_create(C.byref(bad), 0, C.byref(ctx)) != 0 and b"unsupported config" in L.cdc_last_error(None)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_decoder_on_cuda1_while_cuda0_is_current():
+    """every ABI entry guards the device; a Decoder on cuda:1 works, and leaves cuda:0 current."""
+    from cdc_b200 import CDCConfig, Decoder
+    from cdc_b200.synthetic import init_noise, latent, random_weights
+    torch.cuda.set_device(0)
+    w = random_weights(CDCConfig(), seed=0, with_context=True)
+    lat, x = latent(1, 128, 128), init_noise(1, 128, 128)
+    d0 = Decoder(CDCConfig(), w, device="cuda:0")
+    ref = d0.decode(lat, 4, init=x).clone()
+    d1 = Decoder(CDCConfig(), w, device="cuda:1")
+    assert torch.cuda.current_device() == 0
+    out = d1.decode(lat, 4, init=x)
+    assert torch.cuda.current_device() == 0
+    assert torch.equal(out, ref)
+    out_d = d1.decode(lat.to("cuda:1"), 4, init=x.to("cuda:1"))
+    assert out_d.device == torch.device("cuda:1") and torch.equal(out_d.cpu(), ref)
+    assert torch.cuda.current_device() == 0
+    del d1
+    assert torch.cuda.current_device() == 0
+
+
+# ---------------------------------------------------------------------------------------------------- in-graph timing
+def test_profile_graph_stamps_are_consistent():
+    from cdc_b200.synthetic import init_noise, latent
+    dec, _, _, _ = _setup(with_context=True)
+    B, H, W, K = 1, 256, 256, 5
+    dec.set_sample_schedule(K)
+    ref = dec.decode(latent(B, H, W).to(DEV), K, init=init_noise(B, H, W).to(DEV)).clone()
+    start, dur = dec.profile_graph(reps=3)
+    ops = dec.step_ops()
+    assert len(start) == K and len(start[0]) == len(ops)
+    flat = [(start[k][i], dur[k][i], ops[i][0]) for k in range(K) for i in range(len(ops))]
+    kern = [f for f in flat if f[2] != "gn.clear"]
+    assert all(d > 0.4 for _, d, _ in kern), [f for f in kern if f[1] <= 0.4][:3]
+    # kernels run in stream order: starts are non-decreasing, and a kernel starts after its predecessor ended
+    for (s0, d0, n0), (s1, _, n1) in zip(kern[:-1], kern[1:]):
+        assert s1 >= s0 + d0 - 1.5, (n0, s0, d0, n1, s1)
+    total = kern[-1][0] + kern[-1][1]
+    busy = sum(d for _, d, _ in kern)
+    print(f"graph {total:.1f} us, kernels {busy:.1f} us ({100 * busy / total:.1f} % busy), {len(kern)} kernels")
+    assert 0.5 * total < busy <= total + 1.0
+    # the timing graph computes the same thing
+    dec._set_x(init_noise(B, H, W))
+    assert torch.equal(dec.decode(latent(B, H, W).to(DEV), K, init=init_noise(B, H, W).to(DEV)), ref)
+
+
+# ---------------------------------------------------------------------------------------------------- integer kernels
+def test_integer_kernels_vector_and_scalar_paths_agree():
+    """16-byte vector path (aligned buffers), its scalar tail (n % 4 != 0) and the all-scalar path (unaligned views)."""
+    from cdc_b200 import cdf_lookup, quantize_symbols
+    from oracle import entropy as oe
+    from oracle.weights import synthetic_entropy_inputs
+    tb = oe.build_gaussian_tables()
+    for n in (3, 1001, 4099, 65537):
+        y, mu, sigma = synthetic_entropy_inputs(n + 1, seed=77 + n)
+        for off in (0, 1):  # off = 1: the device view starts 4 bytes past a 16-byte boundary
+            yd, md, sd = (t.to(DEV)[off:off + n] for t in (y, mu, sigma))
+            q_ref, yh_ref = oe.quantize_symbols(y[off:off + n], mu[off:off + n])
+            q, yh = quantize_symbols(yd, md, device=DEV)
+            assert torch.equal(q.cpu(), q_ref) and torch.equal(yh.cpu(), yh_ref)
+            ref = oe.cdf_lookup(q_ref, sigma[off:off + n], tb)
+            got = cdf_lookup(q, sd, tb, device=DEV)
+            for a, b_, nm in zip(got, ref, ("idx", "v", "lo", "hi", "raw")):
+                assert torch.equal(a.cpu(), b_), (n, off, nm)

@@ -84,3 +84,21 @@ def test_entropy_matches_golden_bit_exact():
         assert np.array_equal(t.numpy(), g[name]), name
     assert (g["raw"] > 0).sum() > 0, "synthetic inputs must exercise the escape path"
     assert g["idx"].min() == 0 and g["idx"].max() == 63
+
+
+def test_product_table_builder_equals_the_oracle():
+    """The product restates the table construction (it may not import the oracle): identical entry for entry."""
+    from cdc_b200.entropy_tables import gaussian_tables, tables_from_pmfs
+    from cdc_b200.synthetic import entropy_inputs
+    from oracle import entropy as oe
+    from oracle.weights import build_codec, synthetic_entropy_inputs
+    a, b = gaussian_tables(), oe.build_gaussian_tables()
+    for f in ("cdf", "row_start", "cdf_length", "offset", "scale_table"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)) and getattr(a, f).dtype == getattr(b, f).dtype, f
+    rng = np.random.default_rng(0)
+    pm = [rng.dirichlet(np.ones(21) * 0.3) * 0.999 for _ in range(8)]
+    pm[3][5] = 0.0  # an empty bin to repair
+    c, d = tables_from_pmfs(pm, [-10] * 8, [1e-3] * 8), oe.build_tables_from_pmfs(pm, [-10] * 8, [1e-3] * 8)
+    assert np.array_equal(c.cdf, d.cdf) and np.array_equal(c.row_start, d.row_start)
+    for x, y in zip(entropy_inputs(4096), synthetic_entropy_inputs(4096)):
+        assert torch.equal(x, y)

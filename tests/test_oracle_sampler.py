@@ -58,3 +58,74 @@ def test_schedule_matches_golden():
     assert list(g["idx17"]) == s17.idx and list(g["idx100"]) == s100.idx
     assert np.array_equal(g["c0_17"], s17.c0) and np.array_equal(g["c1_17"], s17.c1)
     assert np.array_equal(g["c0_100"], s100.c0) and np.array_equal(g["c1_100"], s100.c1)
+
+
+# ---- sampler variants: eps-parameterisation, stochastic DDIM, 500-step schedule ----
+def test_philox_known_answers():
+    """Random123's published Philox4x32-10 vectors pin the noise function shared with csrc/sampler.cuh."""
+    from oracle.sampler import philox4x32_10
+    w = philox4x32_10([0], [0], [0], [0], 0, 0)
+    assert [int(x[0]) for x in w] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    f = 0xFFFFFFFF
+    w = philox4x32_10([f], [f], [f], [f], f, f)
+    assert [int(x[0]) for x in w] == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    w = philox4x32_10([0x243F6A88], [0x85A308D3], [0x13198A2E], [0x03707344], 0xA4093822, 0x299F31D0)
+    assert [int(x[0]) for x in w] == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+def test_philox_normal_is_standard_normal_and_keyed():
+    from oracle.sampler import philox_normal
+    z = philox_normal(seed=7, step=3, B=2, H=64, W=96)
+    assert z.shape == (2, 3, 64, 96) and z.dtype == torch.float32
+    assert abs(z.mean().item()) < 0.02 and abs(z.std().item() - 1.0) < 0.02 and torch.isfinite(z).all()
+    assert not torch.equal(z, philox_normal(seed=8, step=3, B=2, H=64, W=96))
+    assert not torch.equal(z, philox_normal(seed=7, step=4, B=2, H=64, W=96))
+    assert torch.equal(z, philox_normal(seed=7, step=3, B=2, H=64, W=96))
+    # channels / pixels are decorrelated
+    zf = z.reshape(2, 3, -1)
+    assert abs((zf[:, 0] * zf[:, 1]).mean().item()) < 0.02 and abs((zf[:, 0, 1:] * zf[:, 0, :-1]).mean().item()) < 0.02
+
+
+def test_eps_parameterisation_identity():
+    """Feeding the TRUE noise as eps_hat must reproduce x0 and land on the (x0, eps) line at t_prev (eta = 0)."""
+    ab = alphas_cumprod(1000)
+    for K in (17, 500):
+        s = make_schedule(K, eta=0.0, pred="eps")
+        sx = make_schedule(K)
+        assert np.array_equal(s.c0, sx.c0) and np.array_equal(s.c1, sx.c1) and not s.sg.any()
+        g = torch.Generator().manual_seed(1)
+        x0 = torch.rand(1, 3, 8, 8, generator=g, dtype=torch.float64) * 1.6 - 0.8
+        eps = torch.randn(1, 3, 8, 8, generator=g, dtype=torch.float64)
+        for k in range(1, K, max(1, K // 17)):  # (k = 0 has abar = 2.4e-9: x0 = 2e4 * (...), ill-conditioned in fp32)
+            a_t = ab[s.idx[k]]
+            a_p = ab[s.idx[k + 1]] if k + 1 < K else 1.0
+            x_t = math.sqrt(a_t) * x0 + math.sqrt(1 - a_t) * eps
+            want = math.sqrt(a_p) * x0 + math.sqrt(1 - a_p) * eps
+            got = ddim_update(x_t.float(), eps.float(), s.c0[k], s.c1[k], s.e0[k], s.e1[k]).double()
+            assert (got - want).abs().max() < 2e-3 / math.sqrt(a_t), (K, k)
+
+
+def test_stochastic_ddim_preserves_the_marginal():
+    """eta > 0: with x0_hat = x0 the update is x_prev = sqrt(a_p) x0 + dir * eps + sigma * z with dir^2 + sigma^2 = 1 - a_p
+    (the DDIM family of Song et al.); eta = 1 at the last step adds no noise."""
+    ab = alphas_cumprod(1000)
+    s = make_schedule(17, eta=1.0)
+    s0 = make_schedule(17)
+    assert float(s.sg[16]) == 0.0 and float(s.c0[16]) == 1.0 and float(s.c1[16]) == 0.0
+    for k in range(16):
+        a_t, a_p = ab[s.idx[k]], ab[s.idx[k + 1]]
+        dir_ = float(s.c1[k]) * math.sqrt(1 - a_t)
+        assert abs(dir_ ** 2 + float(s.sg[k]) ** 2 - (1 - a_p)) < 1e-6
+        assert abs(float(s.c0[k]) + float(s.c1[k]) * math.sqrt(a_t) - math.sqrt(a_p)) < 1e-6
+        assert float(s.sg[k]) > 0 and float(s.c1[k]) < float(s0.c1[k])
+    x_t, x0 = torch.full((1, 3, 2, 2), 0.3), torch.full((1, 3, 2, 2), -0.2)
+    z = torch.ones(1, 3, 2, 2)
+    k = 5
+    got = ddim_update(x_t, x0, s.c0[k], s.c1[k], sg=s.sg[k], z=z)
+    assert torch.allclose(got, float(s.c0[k]) * x0 + float(s.c1[k]) * x_t + float(s.sg[k]) * z)
+
+
+def test_k500_schedule():
+    i500 = step_indices(500)
+    assert i500[0] == 999 and i500[-1] == 0 and len(set(i500)) == 500 and sorted(i500, reverse=True) == i500
+    assert all(a - b in (2, 3) for a, b in zip(i500[:-1], i500[1:]))
