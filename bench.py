@@ -196,6 +196,8 @@ def main():
     ap.add_argument("--impl", default="cdc_b200")
     ap.add_argument("--ops-out", default=None, help="write the per-kernel in-graph table of one denoise step (CSV)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--plan-opt", action="append", default=[], metavar="ID=VALUE",
+                    help="A/B a planner decision (include/cdc_b200_tools.h cdc_plan_option ids), e.g. 5=0")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -215,6 +217,8 @@ def main():
     from cdc_b200 import CDCConfig, Decoder, dp
     from cdc_b200.synthetic import init_noise as synthetic_init, latent as synthetic_latent, random_weights
     dec = Decoder(CDCConfig(), random_weights(CDCConfig(), seed=0, with_context=True), device=dev)
+    for po in args.plan_opt:
+        dec.set_plan_option(*[int(v) for v in po.split("=")])
     dec.set_sample_schedule(K_DDIM)
     # The job is a list of world * (warmup + steps) images; rank r decodes {i : i mod world == r} (cdc_b200.dp):
     # per-GPU work is fixed as N grows (weak scaling), no collective on the data path.
@@ -328,6 +332,7 @@ def main():
         n_conv = sum(is_conv)
         n_gn_in = sum(1 for (n, f, b), c in zip(ops, is_conv) if c and "+gn_in" in n)
         peak_tf, peak_gbs, which = peaks()
+        conv_us, conv_slot_us, graph_us = max(conv_us, 1e-6), max(conv_slot_us, 1e-6), max(graph_us, 1e-6)  # (a build without stamps reports 0)
         ach = conv_fl / (conv_us * 1e-6) / 1e12
         ach_slot = conv_fl / (conv_slot_us * 1e-6) / 1e12
         traffic, traffic_of = None, None

@@ -35,8 +35,16 @@ __device__ __forceinline__ uint32_t pack_act2_nosat(float lo, float hi) {
 }
 __device__ __forceinline__ float act_lo(uint32_t u) { return __half2float(__ushort_as_half(static_cast<unsigned short>(u & 0xFFFFu))); }
 __device__ __forceinline__ float act_hi(uint32_t u) { return __half2float(__ushort_as_half(static_cast<unsigned short>(u >> 16))); }
-// non-zero if either half of a packed pair holds the largest finite magnitude (i.e. was stored saturated)
-__device__ __forceinline__ uint32_t act2_is_sat(uint32_t u) { return __vcmpeq2(u & 0x7FFF7FFFu, 0x7BFF7BFFu); }
+// Saturation diagnostics on PACKED outputs: running per-half max of |x| (one or two instructions per word), and the test
+// "a half holds the largest finite magnitude", i.e. pack_act2 clamped it.
+__device__ __forceinline__ uint32_t act2_absmax(uint32_t m, uint32_t u) {
+    const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&m), __habs2(*reinterpret_cast<const __half2*>(&u)));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t act2_absmax(uint32_t m, const uint4& v) {
+    return act2_absmax(act2_absmax(act2_absmax(act2_absmax(m, v.x), v.y), v.z), v.w);
+}
+__device__ __forceinline__ bool act2_is_sat(uint32_t m) { return (m & 0xFFFFu) == 0x7BFFu || (m >> 16) == 0x7BFFu; }
 __device__ __forceinline__ act_t to_act(float v) { return __float2half_rn(sat_act(v)); }
 __device__ __forceinline__ float from_act(act_t v) { return __half2float(v); }
 #else
@@ -52,7 +60,9 @@ __device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
 __device__ __forceinline__ uint32_t pack_act2_nosat(float lo, float hi) { return pack_act2(lo, hi); }
 __device__ __forceinline__ float act_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float act_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
-__device__ __forceinline__ uint32_t act2_is_sat(uint32_t) { return 0u; }  // bf16 has fp32's range
+__device__ __forceinline__ uint32_t act2_absmax(uint32_t m, uint32_t) { return m; }  // bf16 has fp32's range: nothing to count
+__device__ __forceinline__ uint32_t act2_absmax(uint32_t m, const uint4&) { return m; }
+__device__ __forceinline__ bool act2_is_sat(uint32_t) { return false; }
 __device__ __forceinline__ act_t to_act(float v) { return __float2bfloat16_rn(v); }
 __device__ __forceinline__ float from_act(act_t v) { return __bfloat162float(v); }
 #endif

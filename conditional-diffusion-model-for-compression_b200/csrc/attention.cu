@@ -274,18 +274,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
         stamp_begin(p.stamp);
         prefetch_tensormap(&p.qkv_map);
         mbar_init(b_qf, 1);
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(b_kf + 8 * i, 1);
-            mbar_init(b_ke + 8 * i, 1);
-            mbar_init(b_vf + 8 * i, 1);
-            mbar_init(b_ve + 8 * i, 1);
-            mbar_init(b_sf + 8 * i, 1);
-            mbar_init(b_se + 8 * i, 128);
-            mbar_init(b_pf + 8 * i, 128);
-            mbar_init(b_of + 8 * i, 1);
-            mbar_init(b_oe + 8 * i, 128);
-        }
+    }
+    if (warp == 0 && lane < 2) {  // (buffer i's barriers by lane i)
+        const int i = lane;
+        mbar_init(b_kf + 8 * i, 1);
+        mbar_init(b_ke + 8 * i, 1);
+        mbar_init(b_vf + 8 * i, 1);
+        mbar_init(b_ve + 8 * i, 1);
+        mbar_init(b_sf + 8 * i, 1);
+        mbar_init(b_se + 8 * i, 128);
+        mbar_init(b_pf + 8 * i, 128);
+        mbar_init(b_of + 8 * i, 1);
+        mbar_init(b_oe + 8 * i, 128);
+    }
+    if (warp == 0) {
         fence_mbar_init();
+        __syncwarp();
     }
     if (warp == 1) {
         tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_holder)), 512);

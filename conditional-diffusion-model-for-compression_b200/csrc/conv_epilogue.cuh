@@ -93,7 +93,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const EpiArgs& e, uint32_t ta
         act_t* orow = e.out + pix * e.ldc + n0 + c0;
         const act_t* rrow = e.residual ? e.residual + pix * e.ldc + n0 + c0 : nullptr;
         const float msk = valid ? 1.0f : 0.0f;
-        float amax = 0.0f;
+        uint32_t amax2 = 0u;
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
             uint32_t v[32];
@@ -137,19 +137,28 @@ __device__ __forceinline__ void conv_epilogue_tile(const EpiArgs& e, uint32_t ta
                         f[s4 * 8 + 6] += act_lo(r.w);
                         f[s4 * 8 + 7] += act_hi(r.w);
                     }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) amax = fmaxf(amax, fabsf(f[s4 * 8 + j]));
                     uint4 o;
                     o.x = pack_act2(f[s4 * 8 + 0], f[s4 * 8 + 1]);
                     o.y = pack_act2(f[s4 * 8 + 2], f[s4 * 8 + 3]);
                     o.z = pack_act2(f[s4 * 8 + 4], f[s4 * 8 + 5]);
                     o.w = pack_act2(f[s4 * 8 + 6], f[s4 * 8 + 7]);
+                    if constexpr (EPI != EPI_STATS) amax2 = act2_absmax(amax2, o);  // (EPI_STATS: from the sums of squares below)
                     dst[s4] = o;
                 }
             }
         }
         if (dbg) dbg[2] = clock64();
-        if (amax > kActMax && e.sat) atomicAdd(e.sat, 1u);
+        {   // saturation diagnostics: exact from the packed outputs, or (EPI_STATS) conservative from the sums of squares
+            // this thread already holds -- see conv_kf.cu
+            bool sat = act2_is_sat(amax2);
+            if constexpr (EPI == EPI_STATS) {
+                float qm = gq[0];
+#pragma unroll
+                for (int g = 1; g < GH; ++g) qm = fmaxf(qm, gq[g]);
+                sat = sat || qm >= kActMax * kActMax;
+            }
+            if (valid && sat && e.sat) atomicAdd(e.sat, 1u);
+        }
         if constexpr (EPI == EPI_STATS) {
             // warp butterfly -> 8 warps through smem -> one (sum, sum of squares) per (tile, group) -> integer atomics
             const float ws = warp_group_reduce<GH>(gs, lane);

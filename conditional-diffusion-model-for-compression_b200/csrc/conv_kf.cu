@@ -103,10 +103,6 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
     // barriers: tfull[16] tempty[16] wres xfull[8] xempty[8] (x = fused residual conv) ... row_full[8] row_empty[8]
     const uint32_t bar_rfull = aux + 5376, bar_rempty = aux + 5376 + 64, bar_tfull = aux + 64, bar_tempty = aux + 192, bar_wres = aux + 320;
     const uint32_t bar_xfull = aux + 328, bar_xempty = aux + 392;
-    // weights land in consumption order, one barrier per (chunk, horizontal tap) group: the issuer starts the first input
-    // row as soon as the first group is in (p.wkw), instead of after the whole 72..166 KB block
-    constexpr int NWG = CH * (MODE == 1 ? 2 : 3);
-    const uint32_t bar_wg = aux + 5120;  // [NWG <= 12]
     const uint32_t bar_rready = aux + 5376 + 128;  // APPLY: [8] row chunk transformed (one arrive per warp of the owning group)
     const uint32_t bar_afull = APPLY ? bar_rready : bar_rfull;  // what the MMA issuer waits for
     volatile uint32_t* tmem_holder = reinterpret_cast<volatile uint32_t*>(aux_gen + 456);
@@ -141,49 +137,55 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
         prefetch_tensormap(&p.wmap);
         if (STAGE) prefetch_tensormap(&p.omap);
     }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kKfMaxSlots; ++s) {
-            mbar_init(bar_rfull + 8 * s, 1);
-            mbar_init(bar_rempty + 8 * s, 1);
-            if (APPLY) mbar_init(bar_rready + 8 * s, kKfXfThreads / 32);
+    if (warp == 1) {
+        // Barrier initialisation and the weight loads are spread over the lanes of this warp: issued by one thread, the
+        // ~60 mbarrier.init and up to 40 TMA instructions sat on the critical path of every launch (the issuer cannot
+        // start before the weights are in; a ROLLED single-thread load loop measured -1.5 % images/s against the unrolled one).
+        if (lane < kKfMaxSlots) {
+            mbar_init(bar_rfull + 8 * lane, 1);
+            mbar_init(bar_rempty + 8 * lane, 1);
+            if (APPLY) mbar_init(bar_rready + 8 * lane, kKfXfThreads / 32);
         }
-        for (int s = 0; s < static_cast<int>(NACC); ++s) {
-            mbar_init(bar_tfull + 8 * s, 1);
-            mbar_init(bar_tempty + 8 * s, EPI == EPI_DDIM ? 128 : kEpiThreads);
+        if (lane < static_cast<int>(NACC)) {
+            mbar_init(bar_tfull + 8 * lane, 1);
+            mbar_init(bar_tempty + 8 * lane, EPI == EPI_DDIM ? 128 : kEpiThreads);
         }
-        mbar_init(bar_wres, 1);
-        for (int g = 0; g < NWG; ++g) mbar_init(bar_wg + 8 * g, 1);
-        for (int s = 0; s < static_cast<int>(NRES); ++s) {
-            mbar_init(bar_xfull + 8 * s, 1);
-            mbar_init(bar_xempty + 8 * s, kEpiThreads);
+        if (lane < static_cast<int>(NRES)) {
+            mbar_init(bar_xfull + 8 * lane, 1);
+            mbar_init(bar_xempty + 8 * lane, kEpiThreads);
         }
+        if (lane == 0) mbar_init(bar_wres, 1);
         fence_mbar_init();
-        // The weight block starts loading right away -- before the TMEM allocation and the CTA-wide sync (its barriers
-        // were initialised by this thread), and before griddepcontrol.wait: weights are constants.
-        // smem block order [kw][chunk][2 - kh]: the kh taps of one (kw, chunk) form one contiguous B operand.
-        // Issue order = the order the MMAs consume them: chunk, then horizontal tap; group (chunk, kw) has its own barrier.
-        for (int ch = 0; ch < CH; ++ch)
-            for (int kw = 0; kw < NKW; ++kw) {
-                const uint32_t bar = bar_wg + 8 * (ch * NKW + kw);
-                mbar_expect_tx(bar, NKH * WB);
+        __syncwarp();
+        // The weight block starts loading right away -- before the TMEM allocation and the CTA-wide sync (its barrier
+        // was initialised by this warp), and before griddepcontrol.wait: weights are constants.
+        // smem block order [kw][chunk][2 - kh]: the kh taps of one (kw, chunk) form one contiguous B operand; the loads
+        // are numbered in the order the MMAs consume them (chunk, horizontal tap, kh), load l by lane l % 32.
+        // (Letting the issuer start on the first (chunk, kw) group while the rest is still landing was tried in round 2 --
+        // one barrier per group, first input row issued group by group: the extra issue paths made every launch ~0.9 us
+        // SLOWER (-3.5 % images/s), so: one barrier, one wait.)
+        constexpr int NLW = NKH * NKW * CH, NL = NLW + (RES1 ? CH : 0);
+        if (lane == 0) mbar_expect_tx(bar_wres, NL * WB);
+        __syncwarp();
+        for (int l = lane; l < NL; l += 32) {
+            if (l < NLW) {
+                const int e = l % NKH, kw = (l / NKH) % NKW, ch = l / (NKH * NKW);
                 if constexpr (MODE == 2) {  // block order per (kw, chunk): kh = 2, 0 (the pair an odd input row feeds), then kh = 1
-                    for (int kh = 0; kh < 3; ++kh)
-                        tma_load_2d(wbase + ((kw * CH + ch) * 3 + (kh == 2 ? 0 : kh == 0 ? 1 : 2)) * WB, &p.wmap, bar,
-                                    ((kh * 3 + kw) * CH + ch) * 64, cot * BN);
+                    tma_load_2d(wbase + ((kw * CH + ch) * 3 + (e == 2 ? 0 : e == 0 ? 1 : 2)) * WB, &p.wmap, bar_wres,
+                                ((e * 3 + kw) * CH + ch) * 64, cot * BN);
                 } else if constexpr (MODE == 0) {
-                    for (int kh = 0; kh < 3; ++kh)
-                        tma_load_2d(wbase + ((kw * CH + ch) * 3 + (2 - kh)) * WB, &p.wmap, bar,
-                                    ((p.tr ? kw * 3 + kh : kh * 3 + kw) * CH + ch) * 64, cot * BN);  // transposed walk: taps swap roles
-                } else {  // pre-summed parity weights: K index ((parity * 4 + a * 2 + b) * CH + chunk) * 64; kw = b2
-                    for (int a2 = 0; a2 < 2; ++a2)
-                        tma_load_2d(wbase + ((kw * CH + ch) * 2 + (1 - a2)) * WB, &p.wmap, bar,
-                                    (((nt & 3) * 4 + a2 * 2 + kw) * CH + ch) * 64, cot * BN);
+                    tma_load_2d(wbase + ((kw * CH + ch) * 3 + (2 - e)) * WB, &p.wmap, bar_wres,
+                                ((p.tr ? kw * 3 + e : e * 3 + kw) * CH + ch) * 64, cot * BN);  // transposed walk: taps swap roles
+                } else {  // pre-summed parity weights: K index ((parity * 4 + a * 2 + b) * CH + chunk) * 64; kw = b, e = a
+                    tma_load_2d(wbase + ((kw * CH + ch) * 2 + (1 - e)) * WB, &p.wmap, bar_wres,
+                                (((nt & 3) * 4 + e * 2 + kw) * CH + ch) * 64, cot * BN);
                 }
+            } else if constexpr (RES1) {
+                const int ch = l - NLW;
+                tma_load_2d(wres1 + ch * WB, &p.rmap, bar_wres, ch * 64, cot * BN);
             }
-        if constexpr (RES1) {  // the fused 1x1 conv's weights: used after the 3x3 taps of a chunk, loaded last
-            mbar_expect_tx(bar_wres, CH * WB);
-            for (int ch = 0; ch < CH; ++ch) tma_load_2d(wres1 + ch * WB, &p.rmap, bar_wres, ch * 64, cot * BN);
         }
+        __syncwarp();
     }
     if (warp == 2) {  // (warp-collective)
         tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_holder)), TMEM_COLS);
@@ -274,13 +276,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
             uint32_t rslot = 0, rpar = 0;
             uint32_t g = 0;  // running output-row counter: row j of the current strip uses accumulator (g + j) % NACC
             if (kdbg) p.dbg[502] = clock64();
-            // weights: all groups up front, or (p.wkw) group by group while the first input row is issued
-            bool wpend = p.wkw != 0;
-            if (!wpend)
-                for (int g = 0; g < NWG; ++g) mbar_wait(bar_wg + 8 * g, 0);
-            if constexpr (RES1) {
-                if (!wpend) mbar_wait(bar_wres, 0);
-            }
+            mbar_wait(bar_wres, 0);
             if (kdbg) p.dbg[503] = clock64();
             for (int u = cta; u < units; u += p.G1) {
                 int b, seg, si, h0, L;
@@ -348,28 +344,12 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                         const uint32_t npar = nslot == 0 ? rpar ^ 1 : rpar;
                         const uint32_t ready = more ? mbar_test_wait(bar_afull + 8 * nslot, npar) : 1u;
                         constexpr int TTH = TT / 2;
-                        if (wpend) {  // first input row of this CTA: the weight groups are still landing, issue tap by tap
-                            if constexpr (MODE == 2) {
-                                for (int kw = 0; kw < 3; ++kw) mbar_wait(bar_wg + 8 * (ch * 3 + kw), 0);
-                                if (cnt != 0 && elect_one_sync()) steps(std::integral_constant<int, 0>{}, std::integral_constant<int, TTH>{});
-                            } else {
-                                mbar_wait(bar_wg + 8 * (ch * NKW + 0), 0);
-                                if (cnt != 0 && elect_one_sync()) steps(std::integral_constant<int, 0>{}, std::integral_constant<int, 4>{});
-                                __syncwarp();
-                                if constexpr (TTH > 4) {
-                                    mbar_wait(bar_wg + 8 * (ch * NKW + 1), 0);
-                                    if (cnt != 0 && elect_one_sync()) steps(std::integral_constant<int, 4>{}, std::integral_constant<int, TTH>{});
-                                }
-                            }
-                        } else if (cnt != 0 && elect_one_sync()) {
-                            steps(std::integral_constant<int, 0>{}, std::integral_constant<int, TTH>{});
-                        }
+                        if (cnt != 0 && elect_one_sync()) steps(std::integral_constant<int, 0>{}, std::integral_constant<int, TTH>{});
                         __syncwarp();
                         if (dbg && pc == 0) p.dbg[i * 4 + 1] = clock64();
                         if (!ready) mbar_wait(bar_afull + 8 * nslot, npar);
                         if (more) tc_fence_after();
                         if (dbg && pc == 0) p.dbg[i * 4 + 2] = clock64();
-                        if (wpend && MODE != 2) mbar_wait(bar_wg + 8 * (ch * NKW + NKW - 1), 0);
                         if (elect_one_sync()) {
                             if (cnt != 0) steps(std::integral_constant<int, TTH>{}, std::integral_constant<int, TT>{});
                             if (RES1 && i >= 1 && i <= L) {  // fused 1x1 residual conv: centre tap, its own accumulator ring
@@ -396,16 +376,8 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                         if (nslot == 0) rpar ^= 1;
                     }
                     if (dbg) p.dbg[i * 4 + 3] = clock64();
-                    if (wpend) {  // every weight group has been waited for while row 0 was issued
-                        if constexpr (RES1) mbar_wait(bar_wres, 0);
-                        wpend = false;
-                    }
                 }
                 g += L;
-            }
-            if (wpend) {  // (a CTA without work must not exit under its own weight loads)
-                for (int g2 = 0; g2 < NWG; ++g2) mbar_wait(bar_wg + 8 * g2, 0);
-                if constexpr (RES1) mbar_wait(bar_wres, 0);
             }
             if (kdbg) p.dbg[505] = clock64();
         }
@@ -509,7 +481,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                 float gs[GH], gq[GH];
 #pragma unroll
                 for (int i = 0; i < GH; ++i) gs[i] = gq[i] = 0.0f;
-                float amax = 0.0f;  // largest |output| of this thread over the strip (saturation diagnostics)
+                uint32_t amax2 = 0u;  // packed running max |output| of this thread over the strip (saturation diagnostics)
                 for (int j = 0; j < L; ++j, ++tile_ctr) {
                     const uint32_t gj = g + j, slot = gj % NACC;
                     if constexpr (RES1) {  // the fused 1x1 conv's row j (complete one input row before the 3x3's)
@@ -532,6 +504,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                                 xo[s4].y = pack_act2(__uint_as_float(xv[s4 * 8 + 2]) + rbias_r[s4 * 8 + 2], __uint_as_float(xv[s4 * 8 + 3]) + rbias_r[s4 * 8 + 3]);
                                 xo[s4].z = pack_act2(__uint_as_float(xv[s4 * 8 + 4]) + rbias_r[s4 * 8 + 4], __uint_as_float(xv[s4 * 8 + 5]) + rbias_r[s4 * 8 + 5]);
                                 xo[s4].w = pack_act2(__uint_as_float(xv[s4 * 8 + 6]) + rbias_r[s4 * 8 + 6], __uint_as_float(xv[s4 * 8 + 7]) + rbias_r[s4 * 8 + 7]);
+                                amax2 = act2_absmax(amax2, xo[s4]);
                             }
                             const size_t rpix = p.tr ? (static_cast<size_t>(b) * p.W + gx) * p.H + (h0 + j)
                                                      : (static_cast<size_t>(b) * p.H + (h0 + j)) * p.W + gx;
@@ -563,10 +536,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                     if (edbg) edbg[2] = clock64();
                     float f[HC];
 #pragma unroll
-                    for (int c = 0; c < HC; ++c) {
-                        f[c] = __uint_as_float(v[c]) + bias_r[c];
-                        amax = fmaxf(amax, fabsf(f[c]));
-                    }
+                    for (int c = 0; c < HC; ++c) f[c] = __uint_as_float(v[c]) + bias_r[c];
                     if constexpr (EPI == EPI_STATS) {
 #pragma unroll
                         for (int c = 0; c < HC; ++c) {
@@ -582,6 +552,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                         o[s4].y = pack_act2(f[s4 * 8 + 2], f[s4 * 8 + 3]);
                         o[s4].z = pack_act2(f[s4 * 8 + 4], f[s4 * 8 + 5]);
                         o[s4].w = pack_act2(f[s4 * 8 + 6], f[s4 * 8 + 7]);
+                        if constexpr (EPI != EPI_STATS) amax2 = act2_absmax(amax2, o[s4]);  // (EPI_STATS: see below)
                     }
                     if (edbg) edbg[3] = clock64();
                     if constexpr (STAGE) {
@@ -621,7 +592,19 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                     if (edbg) edbg[6] = clock64();
                 }
                 g += L;
-                if (valid && amax > kActMax && p.sat) atomicAdd(p.sat, 1u);  // stored saturated (act.cuh pack_act2)
+                // Saturation diagnostics.  Without statistics: exact, from the packed outputs.  With GroupNorm statistics the
+                // per-row tracking (32 more instructions per row: -0.7 % images/s) is replaced by a test on the sums of
+                // squares this thread already holds: one saturated value makes its group's partial >= 65504^2.  That test
+                // is conservative the safe way -- it also fires when a pixel column's squares add up to 65504^2 over the
+                // strip (rms beyond ~5000: within one order of magnitude of the fp16 limit, worth reporting all the same).
+                bool sat = act2_is_sat(amax2);
+                if constexpr (EPI == EPI_STATS) {
+                    float qm = gq[0];
+#pragma unroll
+                    for (int i = 1; i < GH; ++i) qm = fmaxf(qm, gq[i]);
+                    sat = sat || qm >= kActMax * kActMax;
+                }
+                if (valid && sat && p.sat) atomicAdd(p.sat, 1u);
                 if constexpr (EPI == EPI_STATS) {
                     // one (sum, sum of squares) per (strip, group): warp butterfly -> 4 lane quarters through smem -> integer atomics
                     const float ws = warp_group_reduce<GH>(gs, lane);

@@ -41,7 +41,6 @@ struct alignas(64) KfParams {
     int step;
     long long* stamp;     // diagnostics, may be null (see ConvParams)
     unsigned int* sat;
-    int wkw;              // 1: the issuer starts as soon as the first horizontal tap's weights have landed (one barrier per kw)
     long long* dbg;       // optional: issuer / epilogue timeline of CTA 0 (clock64 stamps), tools only
 };
 

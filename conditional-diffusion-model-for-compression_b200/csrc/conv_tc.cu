@@ -68,16 +68,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
         prefetch_tensormap(&p.wmap);
         prefetch_tensormap(&p.amap[0]);
     }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < NS; ++s) {
-            mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_empty + 8 * s, 1);
+    if (warp == 1) {  // (one barrier set per lane: the serial init loop sat on every launch's critical path)
+        if (lane < NS) {
+            mbar_init(bar_full + 8 * lane, 1);
+            mbar_init(bar_empty + 8 * lane, 1);
         }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(bar_tfull + 8 * s, 1);
-            mbar_init(bar_tempty + 8 * s, EPI == EPI_DDIM ? 128 : kEpiThreads);
+        if (lane < 2) {
+            mbar_init(bar_tfull + 8 * lane, 1);
+            mbar_init(bar_tempty + 8 * lane, EPI == EPI_DDIM ? 128 : kEpiThreads);
         }
         fence_mbar_init();
+        __syncwarp();
     }
     if (warp == 2) {
         tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_holder)), Cfg::TMEM_COLS);

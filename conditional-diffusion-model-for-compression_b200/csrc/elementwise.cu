@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const uint4* x, const 
         }
         const uint4 y0 = gn_apply_vec<SILU, RES>(u0, r0, c);
         y[i] = y0;
-        if (RES) satm |= act2_is_sat(y0.x) | act2_is_sat(y0.y) | act2_is_sat(y0.z) | act2_is_sat(y0.w);
+        if (RES) satm = act2_absmax(satm, y0);
         if (has2) {
             b = single ? 0 : static_cast<int>(i2 / vecs_per_img);
             if (b != cur_b) {
@@ -195,10 +195,10 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const uint4* x, const 
             }
             const uint4 y1 = gn_apply_vec<SILU, RES>(u1, r1, c);
             y[i2] = y1;
-            if (RES) satm |= act2_is_sat(y1.x) | act2_is_sat(y1.y) | act2_is_sat(y1.z) | act2_is_sat(y1.w);
+            if (RES) satm = act2_absmax(satm, y1);
         }
     }
-    if (RES && satm != 0u && g.sat) atomicAdd(g.sat, 1u);
+    if (RES && act2_is_sat(satm) && g.sat) atomicAdd(g.sat, 1u);
     if (threadIdx.x == 0) stamp_end(g.stamp);
 }
 

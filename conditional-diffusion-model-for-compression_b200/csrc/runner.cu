@@ -31,18 +31,17 @@ static std::string g_create_err;
 // Planner decisions that tests / tools A/B through cdc_set_plan_option (include/cdc_b200_tools.h).  The product build
 // reads NO environment variables; the tools build (-DCDC_TOOLS) lets the environment override the defaults.
 struct PlanOpts {
-    int v[CDC_OPT_COUNT] = {2, 1, 1, 0, 6, 1};
+    int v[CDC_OPT_COUNT] = {2, 1, 1, 0, 6};
     int fuse_apply_max_tiles() const { return v[CDC_OPT_FUSE_APPLY]; }
     bool kf() const { return v[CDC_OPT_KF] != 0; }
     bool kf_s2() const { return v[CDC_OPT_KF_S2] != 0; }
     long kf_min_pixels() const { return v[CDC_OPT_KF_MIN_PIXELS]; }
     int kf_ring() const { return v[CDC_OPT_KF_RING]; }
-    bool weight_groups() const { return v[CDC_OPT_WEIGHT_GROUPS] != 0; }
 };
 static PlanOpts default_plan_opts() {
     PlanOpts o;
 #ifdef CDC_TOOLS
-    const char* names[CDC_OPT_COUNT] = {"CDC_FUSE_APPLY", "CDC_KF", "CDC_KF_S2", "CDC_KF_MIN_PIXELS", "CDC_KF_RING", "CDC_WEIGHT_GROUPS"};
+    const char* names[CDC_OPT_COUNT] = {"CDC_FUSE_APPLY", "CDC_KF", "CDC_KF_S2", "CDC_KF_MIN_PIXELS", "CDC_KF_RING"};
     for (int i = 0; i < CDC_OPT_COUNT; ++i)
         if (const char* e = getenv(names[i])) o.v[i] = atoi(e);
     if (getenv("CDC_NO_KF")) o.v[CDC_OPT_KF] = 0;
@@ -416,7 +415,6 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, const PlanOpts& p
             kp->x0_out = cb.x0_out;
             kp->dbg = cb.dbg;
             kp->sat = cb.sat;
-            kp->wkw = po.weight_groups() ? 1 : 0;
             kp->e1 = 1.0f;
             const double Ms = static_cast<double>(B) * gh * gw;
             op->name = cb.name;

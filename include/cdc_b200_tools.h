@@ -22,8 +22,7 @@ typedef enum {
     CDC_OPT_KF_S2 = 2,          /* 0: stride-2 convs through the general kernel.  default 1 */
     CDC_OPT_KF_MIN_PIXELS = 3,  /* levels with fewer pixels per image use the general kernel.  default 0 */
     CDC_OPT_KF_RING = 4,        /* input-ring slots of the one-chunk strip convs.  default 6 */
-    CDC_OPT_WEIGHT_GROUPS = 5,  /* 1: strip convs start issuing as soon as the first weight group landed.  default 1 */
-    CDC_OPT_COUNT = 6
+    CDC_OPT_COUNT = 5
 } cdc_plan_option;
 int cdc_set_plan_option(cdc_ctx* ctx, int option, int value);
 
