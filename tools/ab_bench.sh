@@ -5,11 +5,12 @@ set -u
 cd "$(dirname "$0")/.."
 for pass in 1 2; do
   for spec in "$@"; do
-    name="${spec%%=*}"; path="${spec#*=}"
+    name="${spec%%=*}"; rest="${spec#*=}"; path="${rest%%,*}"; envs=""
+    [ "${rest}" != "${path}" ] && envs="${rest#*,}"
     if [ "${path}" = "r1" ]; then
       (cd tools/bin/r1tree && python bench.py --steps 10 --warmup 3 --no-cpu) > "gpurun_out/ab_${name}_${pass}.json" 2>/dev/null
     else
-      CDC_LIB_PATH="${path}" python bench.py --steps 10 --warmup 3 --no-cpu > "gpurun_out/ab_${name}_${pass}.json" 2>/dev/null
+      env ${envs//,/ } CDC_LIB_PATH="${path}" python bench.py --steps 10 --warmup 3 --no-cpu > "gpurun_out/ab_${name}_${pass}.json" 2>/dev/null
     fi
     python - "$name" "$pass" <<'PY'
 import json, sys
