@@ -8,6 +8,7 @@ raises if the shared library or an sm_100 device is missing.
 """
 from .config import CDCConfig  # noqa: F401
 from .decoder import Decoder, cdf_lookup, quantize_symbols  # noqa: F401
+from .codec import Codec  # noqa: F401
 from . import _ffi, dp  # noqa: F401
 
-__all__ = ["CDCConfig", "Decoder", "quantize_symbols", "cdf_lookup"]
+__all__ = ["CDCConfig", "Decoder", "Codec", "quantize_symbols", "cdf_lookup"]

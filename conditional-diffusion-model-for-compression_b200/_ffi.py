@@ -13,6 +13,7 @@ SYMBOLS = [
     "cdc_schedule_coeffs5", "cdc_film_size", "cdc_get_film", "cdc_bind_io", "cdc_set_cond", "cdc_get_cond", "cdc_set_latent",
     "cdc_set_x", "cdc_get_x", "cdc_get_x0", "cdc_denoise_step", "cdc_decode", "cdc_decode_host", "cdc_launches_per_step",
     "cdc_launches_context", "cdc_flops_per_step", "cdc_saturation_count", "cdc_quantize", "cdc_cdf_lookup",
+    "cdc_has_codec", "cdc_encode_analysis", "cdc_hyper_encode", "cdc_hyper_decode",
 ]
 # ... and include/cdc_b200_tools.h (tests / profiling / A-B; same library)
 TOOLS_SYMBOLS = [
@@ -67,6 +68,10 @@ def _bind(L):
     L.cdc_set_cond.argtypes = [p, f32p, f32p, f32p, f32p, p]
     L.cdc_get_cond.argtypes = [p, f32p, f32p, f32p, f32p, p]
     L.cdc_set_latent.argtypes = [p, f32p, p]
+    L.cdc_has_codec.argtypes = [p]
+    L.cdc_encode_analysis.argtypes = [p, f32p, f32p, p]
+    L.cdc_hyper_encode.argtypes = [p, f32p, f32p, p]
+    L.cdc_hyper_decode.argtypes = [p, f32p, f32p, f32p, p]
     L.cdc_set_x.argtypes = [p, f32p, p]
     L.cdc_get_x.argtypes = [p, f32p, i32, p]
     L.cdc_get_x0.argtypes = [p, f32p, p]

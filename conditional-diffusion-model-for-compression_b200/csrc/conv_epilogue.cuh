@@ -19,6 +19,7 @@ struct EpiArgs {
     float* x0_out;
     SamplerCoef sc;
     unsigned int* sat;  // saturation diagnostics counter (may be null)
+    float act_slope;    // 0 = none; s in (0, 1): LeakyReLU(s) applied after the bias
 };
 
 template <int G>
@@ -112,6 +113,10 @@ __device__ __forceinline__ void conv_epilogue_tile(const EpiArgs& e, uint32_t ta
                 f[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + b4.y;
                 f[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + b4.z;
                 f[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + b4.w;
+            }
+            if (e.act_slope != 0.0f) {  // LeakyReLU: max(x, s*x) for 0 < s < 1
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], e.act_slope * f[j]);
             }
             if constexpr (EPI == EPI_STATS) {
 #pragma unroll

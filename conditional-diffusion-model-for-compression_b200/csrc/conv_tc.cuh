@@ -63,6 +63,7 @@ struct alignas(64) ConvParams {
     // number of (thread, tile) epilogue passes that met a value beyond the fp16 range (stored saturated)
     long long* stamp;
     unsigned int* sat;
+    float act_slope;  // EPI_STORE / EPI_STATS: 0 = none; s in (0, 1): LeakyReLU(s) after the bias (hyper-codec convs, oracle/codec.py)
 };
 
 // Launches the instantiation for (bn, cpg, epi).  Returns cudaErrorInvalidValue when that

@@ -401,4 +401,64 @@ cudaError_t launch_repack_weight_up2(const float* src, act_t* dst, int O, int I,
     return cudaGetLastError();
 }
 
+// ConvTranspose2d(5, stride 2, padding 2, output_padding 1): out[2h+py][2w+px] = sum over taps ky = py + 2a', kx = px + 2b'
+// of in[h + 1 - a'][w + 1 - b'] * W[ci][co][ky][kx]  (ky <= 4).  Parity 0 has three taps per axis (ky 0, 2, 4 -> rows
+// h+1, h, h-1), parity 1 two (ky 1, 3 -> rows h+1, h).  dst tap index = parity * 9 + a * 3 + b with row offset 1 - a.
+__global__ void repack_weight_convt5_kernel(const float* __restrict__ src, act_t* __restrict__ dst, int O, int I, int O_pad, int I_pad) {
+    const long long n = static_cast<long long>(O_pad) * 36 * I_pad;
+    for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < n; idx += gridDim.x * 256LL) {
+        const int i = static_cast<int>(idx % I_pad);
+        const int t = static_cast<int>((idx / I_pad) % 36);
+        const int o = static_cast<int>(idx / (static_cast<long long>(I_pad) * 36));
+        const int ph = t / 9, a = (t % 9) / 3, b = t % 3, py = ph >> 1, px = ph & 1;
+        const int ky = py + 2 * a, kx = px + 2 * b;
+        float v = 0.f;
+        if (o < O && i < I && ky <= 4 && kx <= 4) v = src[((static_cast<size_t>(i) * O + o) * 5 + ky) * 5 + kx];
+        dst[idx] = to_act(v);
+    }
+}
+cudaError_t launch_repack_weight_convt5(const float* src, act_t* dst, int O, int I, int O_pad, int I_pad, cudaStream_t s) {
+    const long long n = static_cast<long long>(O_pad) * 36 * I_pad;
+    repack_weight_convt5_kernel<<<static_cast<int>((n + 255) / 256 < 2048 ? (n + 255) / 256 : 2048), 256, 0, s>>>(src, dst, O, I, O_pad, I_pad);
+    return cudaGetLastError();
+}
+
+__global__ void img_in_kernel(const float* __restrict__ img, act_t* __restrict__ dst, long long n, int HW) {
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
+        const long long b = i / HW, p = i % HW;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dst[i * 64 + c] = to_act(2.0f * img[(b * 3 + c) * HW + p] - 1.0f);
+    }
+}
+cudaError_t launch_img_in(const float* img_nchw, act_t* dst64, int B, int HW, cudaStream_t s) {
+    const long long n = static_cast<long long>(B) * HW;
+    img_in_kernel<<<static_cast<int>((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096), 256, 0, s>>>(img_nchw, dst64, n, HW);
+    return cudaGetLastError();
+}
+
+__global__ void nhwc_slice_to_nchw_kernel(const act_t* __restrict__ src, float* __restrict__ dst, int C, int HW, int ldc, int c_off,
+                                          float min_clamp, int use_clamp) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int p = p0 + j, c = c0 + threadIdx.x;
+        tile[j][threadIdx.x] = (c < C && p < HW) ? from_act(src[(static_cast<size_t>(b) * HW + p) * ldc + c_off + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int c = c0 + j, p = p0 + threadIdx.x;
+        if (p < HW && c < C) {
+            float v = tile[threadIdx.x][j];
+            if (use_clamp) v = fmaxf(v, min_clamp);
+            dst[(static_cast<size_t>(b) * C + c) * HW + p] = v;
+        }
+    }
+}
+cudaError_t launch_nhwc_slice_to_nchw_f32(const act_t* src, float* dst, int B, int C, int HW, int ldc, int c_off, float min_clamp,
+                                          int use_clamp, cudaStream_t s) {
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, B);
+    nhwc_slice_to_nchw_kernel<<<grid, dim3(32, 8), 0, s>>>(src, dst, C, HW, ldc, c_off, min_clamp, use_clamp);
+    return cudaGetLastError();
+}
+
 }  // namespace cdc

@@ -47,6 +47,15 @@ cudaError_t launch_x_out(const float* xs, float* x_nchw, int B, int HW, int to_i
 cudaError_t launch_repack_weight(const float* src, act_t* dst, int O, int I, int taps, int O_pad, int I_pad,
                                  int split, int split_pad, cudaStream_t s);
 
+// ConvTranspose2d(k = 5, stride 2, padding 2, output_padding 1) as four output-parity convs of up to 3x3 taps on the
+// input grid: src [I][O][5][5] fp32 (PyTorch layout) -> dst [O_pad][36 = (parity, a, b)][I_pad], missing taps zero
+cudaError_t launch_repack_weight_convt5(const float* src, act_t* dst, int O, int I, int O_pad, int I_pad, cudaStream_t s);
+// image NCHW fp32 in [0, 1] -> NHWC act_t, 64-channel pixels, channels 0..2 = 2 * img - 1 (channels 3..63 untouched: zero)
+cudaError_t launch_img_in(const float* img_nchw, act_t* dst64, int B, int HW, cudaStream_t s);
+// channels [c_off, c_off + C) of an NHWC act_t tensor with ldc channels -> NCHW fp32, optionally clamped from below
+cudaError_t launch_nhwc_slice_to_nchw_f32(const act_t* src, float* dst, int B, int C, int HW, int ldc, int c_off, float min_clamp,
+                                          int use_clamp, cudaStream_t s);
+
 // nearest-x2 + conv3x3 folded into 4 parity-specific 2x2 convs: dst [O_pad][16][I_pad] (see elementwise.cu)
 cudaError_t launch_repack_weight_up2(const float* src, act_t* dst, int O, int I, int O_pad, int I_pad, cudaStream_t s);
 

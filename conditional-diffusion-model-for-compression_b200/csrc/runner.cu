@@ -88,6 +88,7 @@ struct ConvW {  // repacked conv weights: act_t [n_pad][taps][c_pad], fp32 bias 
     float* bias = nullptr;
     int n_true = 0, n_pad = 0, taps = 0, c_pad = 0, c_true = 0;
     bool up2 = false;  // taps == 16: parity-specific pre-summed 2x2 weights for nearest-x2-input convs
+    bool convt = false;  // taps == 36: ConvTranspose2d(5, stride 2) as four output-parity 3x3 convs (missing taps zero)
 };
 
 struct Op {
@@ -103,7 +104,7 @@ struct SamplerTab {
     unsigned long long seed = 0;
 };
 
-enum ConvMode { MODE_S1 = 0, MODE_S2 = 1, MODE_UP2 = 2 };
+enum ConvMode { MODE_S1 = 0, MODE_S2 = 1, MODE_UP2 = 2, MODE_CONVT = 3 };  // MODE_CONVT: ConvTranspose2d(5, 2, 2, 1), output 2H x 2W
 
 static bool stats_inst_ok(int bn, int cpg) {
     return (bn == 64 && (cpg == 2 || cpg == 4 || cpg == 8)) || (bn == 128 && (cpg == 4 || cpg == 8)) ||
@@ -141,6 +142,7 @@ struct ConvBuild {
     gn_sum_t* gn_acc = nullptr;  // EPI_STATS: this GroupNorm's accumulator slot [B][32][2]
     const act_t* residual = nullptr;
     int force_bn = 0;   // > 0: force the N tile of conv_tc.cu; -1: force conv_tc.cu with its own choice
+    float act_slope = 0.0f;  // LeakyReLU slope applied after the bias (0 = none); general kernel only
     // DDIM
     float* x = nullptr;
     act_t* xpad = nullptr;
@@ -219,7 +221,7 @@ static void conv_geometry(const ConvBuild& cb, int& gw, int& gh, int& nphase, in
     if (cb.mode == MODE_S2) {
         gw = a.W / 2;
         gh = a.H / 2;
-    } else if (cb.mode == MODE_UP2) {
+    } else if (cb.mode == MODE_UP2 || cb.mode == MODE_CONVT) {
         gw = a.W;
         gh = a.H;
         nphase = 4;
@@ -252,7 +254,7 @@ struct KfGeom {
     bool tr;  // transposed walk: strips run along image columns (less padding / halo for e.g. a 128 x 192 level)
 };
 static bool conv_uses_kf(const ConvBuild& cb, int B, int num_sms, const PlanOpts& po, KfGeom* g) {
-    if (!po.kf() || cb.ksize != 3 || cb.force_bn != 0 || cb.residual) return false;
+    if (!po.kf() || cb.ksize != 3 || cb.force_bn != 0 || cb.residual || cb.act_slope != 0.0f || cb.mode == MODE_CONVT) return false;
     g->mode = cb.mode == MODE_UP2 ? 1 : cb.mode == MODE_S2 ? 2 : 0;
     if (g->mode == 1 && (!cb.w->up2 || cb.epi != EPI_STORE)) return false;
     if (g->mode == 2 && (cb.epi != EPI_STORE || cb.res_w || cb.in_acc || ((cb.srcs[0].W | cb.srcs[0].H) & 1))) return false;
@@ -342,7 +344,8 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, const PlanOpts& p
     }
     const ConvW& w = *cb.w;
     const int taps = cb.ksize * cb.ksize;
-    if (ctot != w.c_pad || (w.up2 ? (cb.mode != MODE_UP2 || cb.ksize != 3) : taps != w.taps))
+    if (ctot != w.c_pad || (w.convt ? (cb.mode != MODE_CONVT || cb.ksize != 5)
+                                      : w.up2 ? (cb.mode != MODE_UP2 || cb.ksize != 3) : (taps != w.taps || cb.mode == MODE_CONVT)))
         return fail("weight layout does not match the sources");
     auto cp = std::shared_ptr<ConvParams>(new ConvParams());
     memset(cp.get(), 0, sizeof(ConvParams));
@@ -350,7 +353,8 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, const PlanOpts& p
     conv_geometry(cb, gw, gh, nphase, os, bwl, tiles_w, tiles_h);
     const int BW = 1 << bwl, BH = 128 >> bwl;
     if (cb.mode == MODE_S2 && ((cb.srcs[0].W | cb.srcs[0].H) & 1)) return fail("stride 2 needs even H, W");
-    const int OH = cb.mode == MODE_UP2 ? 2 * gh : gh, OW = cb.mode == MODE_UP2 ? 2 * gw : gw;
+    const bool x2 = cb.mode == MODE_UP2 || cb.mode == MODE_CONVT;
+    const int OH = x2 ? 2 * gh : gh, OW = x2 ? 2 * gw : gw;
     if (cb.epi != EPI_DDIM && (cb.out.H != OH || cb.out.W != OW || cb.out.C != w.n_pad))
         return fail("output tensor shape mismatch");
 
@@ -510,12 +514,31 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, const PlanOpts& p
     if (encode_w_map(&cp->wmap, w.w, w.taps * w.c_pad, w.n_pad, bn)) return fail("cuTensorMapEncodeTiled (weights) failed");
 
     // K-block table
-    int nkb = (w.up2 ? 4 : taps) * (ctot / 64);
+    int nkb = (w.convt ? 9 : w.up2 ? 4 : taps) * (ctot / 64);
     if (nkb * nphase > kMaxKBlocks) return fail("K-block table overflow");
     const int pad = cb.ksize / 2;
     for (int ph = 0; ph < nphase; ++ph) {
         const int py = ph >> 1, px = ph & 1;
         int i = 0;
+        if (w.convt) {  // transposed conv: 3x3 taps per output parity (zero weights where the parity has two), row offset 1 - a
+            for (int a = 0; a < 3; ++a)
+                for (int bb = 0; bb < 3; ++bb) {
+                    int soff = 0;
+                    for (size_t s = 0; s < cb.srcs.size(); ++s) {
+                        for (int c = 0; c < cb.srcs[s].C; c += 64) {
+                            KBlock& e = cp->kb[ph * nkb + i++];
+                            e.map = static_cast<int8_t>(s);
+                            e.dh = static_cast<int8_t>(1 - a);
+                            e.dw = static_cast<int8_t>(1 - bb);
+                            e.pad = 0;
+                            e.c0 = static_cast<uint16_t>(c);
+                            e.wk = static_cast<uint16_t>((ph * 9 + a * 3 + bb) * ctot + soff + c);
+                        }
+                        soff += cb.srcs[s].C;
+                    }
+                }
+            continue;
+        }
         if (w.up2) {  // pre-summed parity weights: 2x2 taps, K index = ((ph*4 + a*2 + b) * ctot + channel)
             for (int a = 0; a < 2; ++a)
                 for (int bb = 0; bb < 2; ++bb) {
@@ -585,11 +608,13 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, const PlanOpts& p
     cp->x0_out = cb.x0_out;
     cp->sat = cb.sat;
     cp->e1 = 1.0f;
+    cp->act_slope = cb.act_slope;
 
     const double M = static_cast<double>(B) * OH * OW;
     op->name = cb.name;
-    op->flops = 2.0 * M * w.n_true * (static_cast<double>(taps) * w.c_true);
     const double m_in = static_cast<double>(B) * cb.srcs[0].H * cb.srcs[0].W;
+    op->flops = w.convt ? 2.0 * m_in * w.n_true * (25.0 * w.c_true)  // every input pixel meets every tap once
+                        : 2.0 * M * w.n_true * (static_cast<double>(taps) * w.c_true);
     op->bytes = 2.0 * (m_in * w.c_true + M * w.n_true + static_cast<double>(taps) * w.c_true * w.n_true);
     const int epi = cb.epi, cpg = cb.cpg;
     const SamplerTab* samp = cb.samp;
@@ -636,7 +661,7 @@ struct cdc_ctx {
     std::map<std::string, WeightT> w;
     std::map<std::string, ConvW> convs;
     Arena warena;  // weights
-    bool finalized = false, has_ctx = false;
+    bool finalized = false, has_ctx = false, has_codec = false;
     int C[4];
 
     PlanOpts opts = default_plan_opts();
@@ -658,6 +683,11 @@ struct cdc_ctx {
     Arena arena;
     int B = 0, H = 0, W = 0;
     std::vector<Op> step_ops, ctx_ops;
+    // codec side (oracle/codec.py Encoder / HyperEncoder / HyperDecoder), present when the
+    // "codec.*" weights were loaded: analysis encoder, hyper-encoder, hyper-decoder -- three more op sequences
+    std::vector<Op> enc_ops, henc_ops, hdec_ops;
+    Act img64, enc_y, henc_in, henc_z, hdec_in, hdec_out;
+    int gn_used_enc = 0;
     Act cond[4], xpad, latent;
     float *xs = nullptr, *x0s = nullptr;
     gn_sum_t* gn_slots = nullptr;  // [2][kMaxGnSlots][B][32][kGnVals] fixed-point GroupNorm accumulators (gn_sums.cuh)
@@ -702,8 +732,8 @@ static const WeightT* find_w(cdc_ctx* ctx, const std::string& name) {
 // Repack "<pfx>.weight"/".bias" (OIHW fp32) to the K-conv layout.  `split`/`split_pad`: input channels
 // >= split start at slot split_pad (stem: 3 image channels padded to 64, then the 64 context channels).
 static int make_conv_w(cdc_ctx* ctx, Arena& ar, const float* wsrc, const float* bsrc, int O, int I, int ks, int split,
-                       int split_pad, bool is_final, ConvW* out, cudaStream_t s, bool up2 = false) {
-    const int taps = up2 ? 16 : ks * ks;
+                       int split_pad, bool is_final, ConvW* out, cudaStream_t s, bool up2 = false, bool convt = false) {
+    const int taps = convt ? 36 : up2 ? 16 : ks * ks;
     const int c_pad = (split < I && split_pad > split) ? split_pad + ((I - split + 63) / 64) * 64 : ((I + 63) / 64) * 64;
     const int n_pad = is_final ? 16 : ((O + 63) / 64) * 64;
     ConvW cw;
@@ -719,7 +749,10 @@ static int make_conv_w(cdc_ctx* ctx, Arena& ar, const float* wsrc, const float* 
     const int sp = (split < I && split_pad > split) ? split : I;
     const int spp = (split < I && split_pad > split) ? split_pad : I;
     cw.up2 = up2;
-    if (up2)
+    cw.convt = convt;
+    if (convt)
+        CK(launch_repack_weight_convt5(wsrc, cw.w, O, I, n_pad, c_pad, s));
+    else if (up2)
         CK(launch_repack_weight_up2(wsrc, cw.w, O, I, n_pad, c_pad, s));
     else
         CK(launch_repack_weight(wsrc, cw.w, O, I, taps, n_pad, c_pad, sp, spp, s));
@@ -728,15 +761,17 @@ static int make_conv_w(cdc_ctx* ctx, Arena& ar, const float* wsrc, const float* 
 }
 
 static int conv_from_store(cdc_ctx* ctx, const std::string& pfx, int O, int I, int ks, int split, int split_pad,
-                           bool is_final, bool up2 = false) {
+                           bool is_final, bool up2 = false, bool convt = false) {
     const WeightT* w = find_w(ctx, pfx + ".weight");
     const WeightT* b = find_w(ctx, pfx + ".bias");
     if (!w || !b) return ctx->fail(CDC_ERR_WEIGHT, "missing weight tensor %s.weight/.bias", pfx.c_str());
-    if (w->shape.size() != 4 || w->shape[0] != O || w->shape[1] != I || w->shape[2] != ks || w->shape[3] != ks ||
+    // (ConvTranspose2d keeps its weight as [in, out, k, k])
+    if (w->shape.size() != 4 || w->shape[0] != (convt ? I : O) || w->shape[1] != (convt ? O : I) || w->shape[2] != ks || w->shape[3] != ks ||
         b->numel != static_cast<size_t>(O))
-        return ctx->fail(CDC_ERR_WEIGHT, "%s: expected conv weight [%d,%d,%d,%d]", pfx.c_str(), O, I, ks, ks);
+        return ctx->fail(CDC_ERR_WEIGHT, "%s: expected %s weight [%d,%d,%d,%d]", pfx.c_str(), convt ? "transposed-conv" : "conv",
+                         convt ? I : O, convt ? O : I, ks, ks);
     ConvW cw;
-    int r = make_conv_w(ctx, ctx->warena, w->p, b->p, O, I, ks, split, split_pad, is_final, &cw, nullptr, up2);
+    int r = make_conv_w(ctx, ctx->warena, w->p, b->p, O, I, ks, split, split_pad, is_final, &cw, nullptr, up2, convt);
     if (r) return r;
     ctx->convs[pfx] = cw;
     return CDC_OK;
@@ -837,7 +872,7 @@ struct PlanB {
         z.name = "gn.clear";
         cdc_ctx* c = ctx;
         gn_sum_t* base = slots;
-        const int* used = ops == &ctx->step_ops ? &ctx->gn_used_step : &ctx->gn_used_ctx;
+        const int* used = ops == &ctx->step_ops ? &ctx->gn_used_step : ops == &ctx->ctx_ops ? &ctx->gn_used_ctx : &ctx->gn_used_enc;
         z.run = [c, base, used](cudaStream_t s, int, long long*) {
             return cudaMemsetAsync(base, 0, static_cast<size_t>(*used) * c->B * kGnImgStride * sizeof(gn_sum_t), s);
         };
@@ -940,7 +975,7 @@ static int build_plans(cdc_ctx* ctx) {
     const size_t px = static_cast<size_t>(B) * H * W;
     CK(ar.alloc(reinterpret_cast<void**>(&ctx->xs), px * 3 * 4));
     CK(ar.alloc(reinterpret_cast<void**>(&ctx->x0s), px * 3 * 4));
-    CK(ar.alloc(reinterpret_cast<void**>(&ctx->gn_slots), 2 * static_cast<size_t>(kMaxGnSlots) * B * kGnImgStride * sizeof(gn_sum_t)));
+    CK(ar.alloc(reinterpret_cast<void**>(&ctx->gn_slots), 3 * static_cast<size_t>(kMaxGnSlots) * B * kGnImgStride * sizeof(gn_sum_t)));
     CK(ar.alloc(reinterpret_cast<void**>(&ctx->sat_dev), 256));
     CK(cudaMemset(ctx->sat_dev, 0, 256));
 
@@ -1104,6 +1139,82 @@ static int build_plans(cdc_ctx* ctx) {
         }
         if (pc.rc) return pc.rc;
         ctx->gn_used_ctx = pc.next_slot;
+    }
+
+    // ---- codec side (oracle/codec.py Encoder, HyperEncoder, HyperDecoder): SURVEY.md section 8 row f2 ----
+    if (ctx->has_codec) {
+        const int Cl = ctx->cfg.latent_ch;
+        PlanB pe;
+        pe.ctx = ctx;
+        pe.ops = &ctx->enc_ops;
+        pe.slots = ctx->gn_slots + 2 * static_cast<size_t>(kMaxGnSlots) * B * kGnImgStride;
+        pe.clear_slots_op();
+        ctx->img64 = pe.act(64, H, W);  // 2 * img - 1 in channels 0..2, the rest stays zero
+        if (pe.rc) return pe.rc;
+        CK(cudaMemset(ctx->img64.p, 0, px * 64 * 2));
+        Act eh = pe.act(C[0], H, W);
+        {
+            ConvBuild cb;
+            cb.name = "enc.stem";
+            cb.srcs = {ctx->img64};
+            cb.w = &ctx->convs["codec.encoder.stem"];
+            cb.out = eh;
+            pe.conv(cb);
+        }
+        for (int i = 0; i < 4; ++i) {
+            const int Hl = H >> i, Wl = W >> i;
+            const std::string si = std::to_string(i);
+            Act a = pe.act(C[i], Hl, Wl);
+            pe.rb("enc.rb" + si, "codec.encoder.rbs." + si, {eh}, C[i], -1, a);
+            eh = pe.act(C[i], Hl / 2, Wl / 2);
+            ConvBuild cb;
+            cb.name = "enc.down" + si;
+            cb.srcs = {a};
+            cb.w = &ctx->convs["codec.encoder.downs." + si];
+            cb.mode = MODE_S2;
+            cb.out = eh;
+            pe.conv(cb);
+        }
+        if (pe.rc) return pe.rc;
+        ctx->enc_y = eh;
+        ctx->gn_used_enc = pe.next_slot;
+
+        auto plain = [&](PlanB& pb, const char* name, const char* wname, Act src, Act dst, int ks, int mode, float slope) {
+            ConvBuild cb;
+            cb.name = name;
+            cb.srcs = {src};
+            cb.w = &ctx->convs[wname];
+            cb.ksize = ks;
+            cb.mode = mode;
+            cb.out = dst;
+            cb.act_slope = slope;
+            cb.force_bn = -1;  // the general kernel: it has the LeakyReLU epilogue, the 5x5 taps and the transposed mode
+            pb.conv(cb);
+        };
+        const int Hy = H >> 4, Wy = W >> 4;
+        PlanB ph;
+        ph.ctx = ctx;
+        ph.ops = &ctx->henc_ops;
+        ctx->henc_in = ph.act(Cl, Hy, Wy);
+        Act h1 = ph.act(Cl, Hy, Wy), h2 = ph.act(Cl, Hy / 2, Wy / 2);
+        ctx->henc_z = ph.act(Cl, Hy / 4, Wy / 4);
+        if (ph.rc) return ph.rc;
+        plain(ph, "henc.c1", "codec.hyper_enc.c1", ctx->henc_in, h1, 3, MODE_S1, 0.2f);
+        plain(ph, "henc.c2", "codec.hyper_enc.c2", h1, h2, 5, MODE_S2, 0.2f);
+        plain(ph, "henc.c3", "codec.hyper_enc.c3", h2, ctx->henc_z, 5, MODE_S2, 0.0f);
+        if (ph.rc) return ph.rc;
+
+        PlanB pd;
+        pd.ctx = ctx;
+        pd.ops = &ctx->hdec_ops;
+        ctx->hdec_in = pd.act(Cl, Hy / 4, Wy / 4);
+        Act d1 = pd.act(Cl, Hy / 2, Wy / 2), d2 = pd.act(Cl, Hy, Wy);
+        ctx->hdec_out = pd.act(2 * Cl, Hy, Wy);
+        if (pd.rc) return pd.rc;
+        plain(pd, "hdec.t1", "codec.hyper_dec.t1", ctx->hdec_in, d1, 5, MODE_CONVT, 0.2f);
+        plain(pd, "hdec.t2", "codec.hyper_dec.t2", d1, d2, 5, MODE_CONVT, 0.2f);
+        plain(pd, "hdec.c3", "codec.hyper_dec.c3", d2, ctx->hdec_out, 3, MODE_S1, 0.0f);
+        if (pd.rc) return pd.rc;
     }
     return CDC_OK;
 }
@@ -1321,6 +1432,26 @@ int cdc_finalize_weights(cdc_ctx* ctx) {
             prev = C[i];
         }
     }
+    // optional codec side: analysis encoder + hyper-encoder / hyper-decoder ("codec." + oracle Codec.state_dict() names)
+    ctx->has_codec = find_w(ctx, "codec.encoder.stem.weight") != nullptr;
+    if (ctx->has_codec) {
+        const int Cl = ctx->cfg.latent_ch;
+        if (Cl != C[3]) return ctx->fail(CDC_ERR_WEIGHT, "codec weights need latent_ch == base * mults[3]");
+        if ((r = conv_from_store(ctx, "codec.encoder.stem", C[0], 3, 3, 3, 3, false))) return r;
+        prev = C[0];
+        for (int i = 0; i < 4; ++i) {
+            const std::string s = std::to_string(i);
+            if ((r = rb_weights(ctx, "codec.encoder.rbs." + s, prev, C[i], false))) return r;
+            if ((r = conv_from_store(ctx, "codec.encoder.downs." + s, C[i], C[i], 3, C[i], C[i], false))) return r;
+            prev = C[i];
+        }
+        if ((r = conv_from_store(ctx, "codec.hyper_enc.c1", Cl, Cl, 3, Cl, Cl, false))) return r;
+        if ((r = conv_from_store(ctx, "codec.hyper_enc.c2", Cl, Cl, 5, Cl, Cl, false))) return r;
+        if ((r = conv_from_store(ctx, "codec.hyper_enc.c3", Cl, Cl, 5, Cl, Cl, false))) return r;
+        if ((r = conv_from_store(ctx, "codec.hyper_dec.t1", Cl, Cl, 5, Cl, Cl, false, false, true))) return r;
+        if ((r = conv_from_store(ctx, "codec.hyper_dec.t2", Cl, Cl, 5, Cl, Cl, false, false, true))) return r;
+        if ((r = conv_from_store(ctx, "codec.hyper_dec.c3", 2 * Cl, Cl, 3, Cl, Cl, false))) return r;
+    }
     // FiLM offsets
     std::vector<int> couts;
     film_rb_names(ctx, &couts);
@@ -1337,6 +1468,7 @@ int cdc_finalize_weights(cdc_ctx* ctx) {
 }
 
 int cdc_has_context_net(cdc_ctx* ctx) { return ctx && ctx->has_ctx ? 1 : 0; }
+int cdc_has_codec(cdc_ctx* ctx) { return ctx && ctx->has_codec ? 1 : 0; }
 
 int cdc_set_sampler(cdc_ctx* ctx, int pred_eps, float eta, uint64_t seed) {
     if (!ctx) return CDC_ERR_STATE;
@@ -1477,6 +1609,9 @@ int cdc_bind_io(cdc_ctx* ctx, int B, int H, int W) {
     drop_graph(ctx);
     ctx->step_ops.clear();
     ctx->ctx_ops.clear();
+    ctx->enc_ops.clear();
+    ctx->henc_ops.clear();
+    ctx->hdec_ops.clear();
     ctx->arena.release();
     ctx->B = B;
     ctx->H = H;
@@ -1486,6 +1621,9 @@ int cdc_bind_io(cdc_ctx* ctx, int B, int H, int W) {
     if (r) {
         ctx->step_ops.clear();
         ctx->ctx_ops.clear();
+        ctx->enc_ops.clear();
+        ctx->henc_ops.clear();
+        ctx->hdec_ops.clear();
         ctx->arena.release();
         ctx->B = ctx->H = ctx->W = 0;
         return r;
@@ -1530,6 +1668,57 @@ int cdc_set_latent(cdc_ctx* ctx, const float* y_hat, cdc_stream s) {
         cudaError_t e = op.run(S(s), 0, nullptr);
         if (e != cudaSuccess) return ctx->fail(CDC_ERR_CUDA, "%s: %s", op.name.c_str(), cudaGetErrorString(e));
     }
+    return CDC_OK;
+}
+
+// ---- codec side (row f2) ----
+static int run_ops(cdc_ctx* ctx, std::vector<Op>& ops, cudaStream_t s) {
+    for (Op& op : ops) {
+        cudaError_t e = op.run(s, 0, nullptr);
+        if (e != cudaSuccess) return ctx->fail(CDC_ERR_CUDA, "%s: %s", op.name.c_str(), cudaGetErrorString(e));
+    }
+    return CDC_OK;
+}
+#define NEED_CODEC() \
+    if (!ctx->has_codec) return ctx->fail(CDC_ERR_WEIGHT, "codec weights (codec.encoder.* / codec.hyper_enc.* / codec.hyper_dec.*) were not loaded")
+
+int cdc_encode_analysis(cdc_ctx* ctx, const float* img01, float* y, cdc_stream s) {
+    NEED_PLAN();
+    NEED_CODEC();
+    if (!img01 || !y) return ctx->fail(CDC_ERR_SHAPE, "null buffer");
+    CK(launch_img_in(img01, ctx->img64.p, ctx->B, ctx->H * ctx->W, S(s)));
+    int r = run_ops(ctx, ctx->enc_ops, S(s));
+    if (r) return r;
+    const Act& a = ctx->enc_y;
+    CK(launch_nhwc_act_to_nchw_f32(a.p, y, ctx->B, a.C, a.H * a.W, S(s)));
+    return CDC_OK;
+}
+
+int cdc_hyper_encode(cdc_ctx* ctx, const float* y, float* z, cdc_stream s) {
+    NEED_PLAN();
+    NEED_CODEC();
+    if (!y || !z) return ctx->fail(CDC_ERR_SHAPE, "null buffer");
+    const Act& a = ctx->henc_in;
+    CK(launch_nchw_f32_to_nhwc_act(y, a.p, ctx->B, a.C, a.H * a.W, a.C, S(s)));
+    int r = run_ops(ctx, ctx->henc_ops, S(s));
+    if (r) return r;
+    const Act& zz = ctx->henc_z;
+    CK(launch_nhwc_act_to_nchw_f32(zz.p, z, ctx->B, zz.C, zz.H * zz.W, S(s)));
+    return CDC_OK;
+}
+
+int cdc_hyper_decode(cdc_ctx* ctx, const float* z_hat, float* mu, float* sigma, cdc_stream s) {
+    NEED_PLAN();
+    NEED_CODEC();
+    if (!z_hat || !mu || !sigma) return ctx->fail(CDC_ERR_SHAPE, "null buffer");
+    const Act& a = ctx->hdec_in;
+    CK(launch_nchw_f32_to_nhwc_act(z_hat, a.p, ctx->B, a.C, a.H * a.W, a.C, S(s)));
+    int r = run_ops(ctx, ctx->hdec_ops, S(s));
+    if (r) return r;
+    const Act& o = ctx->hdec_out;
+    const int Cl = o.C / 2, HW = o.H * o.W;
+    CK(launch_nhwc_slice_to_nchw_f32(o.p, mu, ctx->B, Cl, HW, o.C, 0, 0.0f, 0, S(s)));
+    CK(launch_nhwc_slice_to_nchw_f32(o.p, sigma, ctx->B, Cl, HW, o.C, Cl, 0.11f, 1, S(s)));  // sigma = max(sigma_raw, 0.11)
     return CDC_OK;
 }
 

@@ -79,3 +79,38 @@ def tables_from_pmfs(pmfs, offsets, tails):
     """Rows indexed by channel (factorised prior): the caller supplies each row's PMF, support offset and tail mass."""
     rows = [quantize_pmf(np.append(np.asarray(p, dtype=np.float64), t)) for p, t in zip(pmfs, tails)]
     return _flatten(rows, offsets, np.zeros(LEVELS, dtype=np.float32))
+
+
+def factorized_tables(mats, biases, factors, median, support=10):
+    """Rows indexed by channel for the factorised prior of z (Balle-style cumulative, oracle/codec.py FactorizedPrior):
+    logits(x) = chain of  h <- softplus(M_i) h + b_i ; h <- h + tanh(f_i) tanh(h)  per channel, evaluated in float64 at
+    median + s -+ 0.5 for s in [-support, support];  pmf = |sigmoid(sgn * upper) - sigmoid(sgn * lower)|,
+    sgn = -sign(lower + upper);  tail = sigmoid(lower at the first bin) + sigmoid(-upper at the last bin).
+    mats / biases / factors: lists of float arrays [c, f_out, f_in] / [c, f_out, 1] / [c, f_out, 1]; median [c]."""
+    mats = [np.asarray(m, dtype=np.float64) for m in mats]
+    biases = [np.asarray(b, dtype=np.float64) for b in biases]
+    factors = [np.asarray(f, dtype=np.float64) for f in factors]
+    med = np.asarray(median, dtype=np.float64)
+    c = med.shape[0]
+
+    def softplus(x):
+        return np.where(x > 20.0, x, np.log1p(np.exp(np.minimum(x, 20.0))))
+
+    def sigmoid(x):
+        return np.where(x >= 0, 1.0 / (1.0 + np.exp(-np.abs(x))), np.exp(-np.abs(x)) / (1.0 + np.exp(-np.abs(x))))
+
+    def logits(x):  # x [c, 1, n]
+        h = x
+        for i, (m, b) in enumerate(zip(mats, biases)):
+            h = np.matmul(softplus(m), h) + b
+            if i < len(factors):
+                h = h + np.tanh(factors[i]) * np.tanh(h)
+        return h
+
+    s = np.arange(-support, support + 1, dtype=np.float32).astype(np.float64)
+    samples = (med[:, None].astype(np.float32) + s[None, :].astype(np.float32)).astype(np.float64)[:, None, :]
+    lower, upper = logits(samples - 0.5), logits(samples + 0.5)
+    sgn = -np.sign(lower + upper)
+    pmf = np.abs(sigmoid(sgn * upper) - sigmoid(sgn * lower))[:, 0, :]
+    tail = (sigmoid(lower[:, 0, :1]) + sigmoid(-upper[:, 0, -1:]))[:, 0]
+    return tables_from_pmfs([pmf[i] for i in range(c)], [-support] * c, tail)

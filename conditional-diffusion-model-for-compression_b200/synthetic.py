@@ -32,7 +32,42 @@ def _rb(d, g, name, cin, cout, temb):
         _conv(d, g, name + ".res", cout, cin, 1)
 
 
-def random_weights(cfg: CDCConfig = CDCConfig(), seed: int = 0, with_context: bool = True):
+def _convt(d, g, name, cin, cout, k):
+    d[name + ".weight"] = _u(g, (cin, cout, k, k), cout * k * k)  # ConvTranspose2d layout [in, out, k, k]
+    d[name + ".bias"] = _u(g, (cout,), cout * k * k)
+
+
+def codec_weights(cfg: CDCConfig = CDCConfig(), seed: int = 1):
+    """Random-init analysis encoder, hyper-encoder / hyper-decoder and factorised prior under the names the C ABI expects
+    ("codec." + the oracle Codec.state_dict() keys)."""
+    g = torch.Generator().manual_seed(seed + 100)
+    C, c, d = cfg.channels, cfg.latent_ch, {}
+    _conv(d, g, "codec.encoder.stem", C[0], 3, 3)
+    prev = C[0]
+    for i, ch in enumerate(C):
+        _rb(d, g, f"codec.encoder.rbs.{i}", prev, ch, 0)
+        _conv(d, g, f"codec.encoder.downs.{i}", ch, ch, 3)
+        prev = ch
+    _conv(d, g, "codec.hyper_enc.c1", c, c, 3)
+    _conv(d, g, "codec.hyper_enc.c2", c, c, 5)
+    _conv(d, g, "codec.hyper_enc.c3", c, c, 5)
+    _convt(d, g, "codec.hyper_dec.t1", c, c, 5)
+    _convt(d, g, "codec.hyper_dec.t2", c, c, 5)
+    _conv(d, g, "codec.hyper_dec.c3", 2 * c, c, 3)
+    # factorised prior (Balle-style cumulative MLP, filters (3,3,3,3), untrained init): host-side only (CDF tables)
+    f = (1, 3, 3, 3, 3, 1)
+    scale = 10.0 ** (1.0 / 5)
+    for i in range(5):
+        init = math.log(math.expm1(1.0 / scale / f[i + 1]))
+        d[f"codec.prior.mats.{i}"] = torch.full((c, f[i + 1], f[i]), init).bfloat16().float()
+        d[f"codec.prior.biases.{i}"] = (torch.rand((c, f[i + 1], 1), generator=g) - 0.5).bfloat16().float()
+        if i < 4:
+            d[f"codec.prior.factors.{i}"] = torch.zeros(c, f[i + 1], 1)
+    d["codec.prior.median"] = torch.zeros(c)
+    return d
+
+
+def random_weights(cfg: CDCConfig = CDCConfig(), seed: int = 0, with_context: bool = True, with_codec: bool = False):
     g = torch.Generator().manual_seed(seed)
     C, te, d = cfg.channels, cfg.temb, {}
     d["temb.lin1.weight"], d["temb.lin1.bias"] = _u(g, (te, 64), 64), _u(g, (te,), 64)
@@ -62,7 +97,19 @@ def random_weights(cfg: CDCConfig = CDCConfig(), seed: int = 0, with_context: bo
             _conv(d, g, f"context.ups.{i}.up", C[i], prev, 3)
             _rb(d, g, f"context.rbs.{i}", C[i], C[i], 0)
             prev = C[i]
+    if with_codec:
+        d.update(codec_weights(cfg, seed + 1))
     return d
+
+def image(B, H, W, index=0):
+    """Synthetic image in [0,1]: uniform noise, low-pass filtered twice with a 3x3 box."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(1234 + index)
+    x = torch.rand(B, 3, H, W, generator=g)
+    k = torch.ones(3, 1, 3, 3) / 9.0
+    for _ in range(2):
+        x = F.conv2d(F.pad(x, (1, 1, 1, 1), mode="replicate"), k, groups=3)
+    return x
 
 
 def latent(B, H, W, index=0, ch=256):

@@ -91,6 +91,19 @@ int cdc_get_x0(cdc_ctx* ctx, float* x0_nchw, cdc_stream s); /* raw x0_hat of the
  * c_i [B, C_i, H >> i, W >> i]; any pointer may be NULL to skip that level */
 int cdc_get_cond(cdc_ctx* ctx, float* c0, float* c1, float* c2, float* c3, cdc_stream s);
 
+/* ---- codec side of the decode loop (oracle/codec.py Encoder, HyperEncoder, HyperDecoder) --
+ * Available when the weights named "codec." + oracle Codec.state_dict() keys (codec.encoder.*, codec.hyper_enc.*,
+ * codec.hyper_dec.*) were loaded; shapes follow cdc_bind_io(batch, H, W).  Deterministic: the same input gives the same
+ * bits on every run and every B200 (fixed accumulation order), so an encoder and a decoder that both run
+ * cdc_hyper_decode on the same z_hat derive identical (mu, sigma) -- what a real bitstream needs. */
+int cdc_has_codec(cdc_ctx* ctx);
+/* y = encoder(2 * img - 1): img NCHW fp32 [B,3,H,W] in [0,1] -> y NCHW fp32 [B,latent_ch,H/16,W/16] */
+int cdc_encode_analysis(cdc_ctx* ctx, const float* img01, float* y, cdc_stream s);
+/* z = hyper_enc(y): [B,latent_ch,H/16,W/16] -> [B,latent_ch,H/64,W/64] */
+int cdc_hyper_encode(cdc_ctx* ctx, const float* y, float* z, cdc_stream s);
+/* (mu, sigma) = hyper_dec(z_hat), sigma = max(sigma_raw, 0.11): [B,latent_ch,H/64,W/64] -> 2 x [B,latent_ch,H/16,W/16] */
+int cdc_hyper_decode(cdc_ctx* ctx, const float* z_hat, float* mu, float* sigma, cdc_stream s);
+
 /* ---- oracle/sampler.py OracleDecoder.denoise_step / decode ------------------------------------ */
 int cdc_denoise_step(cdc_ctx* ctx, int k, cdc_stream s); /* x <- c0_k*clamp(unet(x, idx_k, cond)) + c1_k*x */
 int cdc_decode(cdc_ctx* ctx, cdc_stream s);              /* all K steps: ONE cudaGraphLaunch */

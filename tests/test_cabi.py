@@ -86,12 +86,26 @@ def test_no_gpu_means_loud_failure(built):
 
 def test_synthetic_weights_match_the_oracle_state_dict():
     """The product's random-weight generator (bench / smoke) must produce exactly the tensor names and
-    shapes of the oracle's state dict, which is what cdc_load_weights consumes."""
+    shapes of the oracle's state dicts, which is what cdc_load_weights consumes."""
     from cdc_b200.synthetic import random_weights
     from oracle.config import CDCConfig
     from oracle.weights import build_codec, build_unet
-    w = random_weights()
+    w = random_weights(with_codec=True)
     ref = dict(build_unet(CDCConfig()).state_dict())
-    ref.update({"context." + k: v for k, v in build_codec(CDCConfig()).context.state_dict().items()})
-    assert set(w) == set(ref)
+    for k, v in build_codec(CDCConfig()).state_dict().items():
+        ref[k if k.startswith("context.") else "codec." + k] = v
+    assert set(w) == set(ref), set(w) ^ set(ref)
     assert all(w[k].shape == ref[k].shape for k in w)
+    assert set(random_weights()) == {k for k in ref if not k.startswith("codec.")}
+
+
+def test_product_factorised_table_builder_equals_the_oracle():
+    import numpy as np
+    from cdc_b200.codec import Codec
+    from oracle.config import CDCConfig
+    from oracle.weights import build_codec
+    oc = build_codec(CDCConfig(), seed=1)
+    t = Codec.prior_tables({"codec." + k: v for k, v in oc.state_dict().items()})
+    _, fact = oc.tables()
+    for f in ("cdf", "row_start", "cdf_length", "offset"):
+        assert np.array_equal(getattr(t, f), getattr(fact, f)), f
