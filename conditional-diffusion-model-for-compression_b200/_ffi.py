@@ -14,6 +14,7 @@ SYMBOLS = [
     "cdc_set_x", "cdc_get_x", "cdc_get_x0", "cdc_denoise_step", "cdc_decode", "cdc_decode_host", "cdc_launches_per_step",
     "cdc_launches_context", "cdc_flops_per_step", "cdc_saturation_count", "cdc_quantize", "cdc_cdf_lookup",
     "cdc_has_codec", "cdc_encode_analysis", "cdc_hyper_encode", "cdc_hyper_decode",
+    "cdc_rans_streams_per_channel", "cdc_rans_scratch_bytes", "cdc_rans_max_bytes", "cdc_rans_encode", "cdc_rans_decode",
 ]
 # ... and include/cdc_b200_tools.h (tests / profiling / A-B; same library)
 TOOLS_SYMBOLS = [
@@ -86,6 +87,13 @@ def _bind(L):
     L.cdc_quantize.argtypes = [f32p, f32p, i32p, f32p, i64, i64, i64, p]
     L.cdc_cdf_lookup.argtypes = [i32p, f32p, i32p, i32p, i32p, i32p, f32p, i32, i64, i32p, i32p, i32p, i32p, i32p,
                                  i64, p]
+    L.cdc_rans_streams_per_channel.argtypes = [i64]
+    L.cdc_rans_scratch_bytes.argtypes = [i64, i64, i32]
+    L.cdc_rans_scratch_bytes.restype = i64
+    L.cdc_rans_max_bytes.argtypes = [i64, i64, i32]
+    L.cdc_rans_max_bytes.restype = i64
+    L.cdc_rans_encode.argtypes = [p, p, p, p, p, p, i64, i64, i32, p, p, i64, p, p]
+    L.cdc_rans_decode.argtypes = [p, i64, p, p, p, p, p, i32, i64, i64, i32, p, p, p, p]
     # tools header
     L.cdc_set_plan_option.argtypes = [p, i32, i32]
     L.cdc_num_step_ops.argtypes = [p]

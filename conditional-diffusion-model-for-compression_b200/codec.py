@@ -110,3 +110,43 @@ class Codec:
     def decompress(self, qz, q, steps, **kw):
         y_hat, _, _ = self.latent_from_symbols(qz, q)
         return self.dec.decode(y_hat, steps, **kw)
+
+    # ---- bitstream (row f3): "CDC5" | u32 B, H, W | u64 len(z stream) | z container | y container ------------------
+    @torch.no_grad()
+    def compress(self, img01):
+        """img in [0,1] -> (bytes, enc): the on-wire representation (two CDCR rANS containers: z, then y) and the encode
+        dict.  Needs the factorised-prior tables (fact_tables)."""
+        import struct
+        from .bitstream import rans_encode
+        if self.fact is None:
+            raise RuntimeError("compress needs the factorised-prior CDF tables (fact_tables)")
+        enc = self.encode(img01)
+        B, c, h, w = enc["q"].shape
+        zs = rans_encode(enc["z_sym"], self.fact, B * c, (h // 4) * (w // 4), self.device)
+        ys = rans_encode(enc["y_sym"], self.gauss, B * c, h * w, self.device)
+        head = b"CDC5" + struct.pack("<3IQ", B, h * 16, w * 16, zs.numel())
+        return head + zs.cpu().numpy().tobytes() + ys.cpu().numpy().tobytes(), enc
+
+    @torch.no_grad()
+    def decode_symbols(self, data: bytes):
+        """bytes -> (qz, q) int32 device tensors: the decoder side of the entropy stage.  z is decoded with the
+        channel-indexed tables; its hyper-decoder output gives the CDF row of every y symbol."""
+        import struct
+        from .bitstream import rans_decode
+        if data[:4] != b"CDC5":
+            raise ValueError("not a CDC5 stream")
+        B, H, W, nz = struct.unpack_from("<3IQ", data, 4)
+        c, h, w = self.dec.cfg.latent_ch, H // 16, W // 16
+        zbytes, ybytes = data[24:24 + nz], data[24 + nz:]
+        ch = torch.arange(c, dtype=torch.int32, device=self.device)[None, :, None, None].expand(B, c, h // 4, w // 4)
+        qz = rans_decode(zbytes, ch.contiguous(), self.fact, self.device).reshape(B, c, h // 4, w // 4)
+        z_hat = qz.float() + self.median[None, :, None, None]
+        _, sigma = self.hyper_decode(z_hat)
+        idx = cdf_lookup(torch.zeros(B, c, h, w, dtype=torch.int32, device=self.device), sigma, self.gauss, device=self.device)[0]
+        q = rans_decode(ybytes, idx, self.gauss, self.device).reshape(B, c, h, w)
+        return qz, q
+
+    @torch.no_grad()
+    def decompress_bytes(self, data: bytes, steps, **kw):
+        qz, q = self.decode_symbols(data)
+        return self.decompress(qz, q, steps, **kw)

@@ -91,4 +91,16 @@ cudaError_t launch_cdf_lookup(const int32_t* q, const float* sigma, CdfTables t,
                               int32_t* v, int32_t* lo, int32_t* hi, int32_t* raw, int64_t n, int num_sms,
                               cudaStream_t s);
 
+// ---- rANS bitstream (rans.cu; oracle/rans.py pins the format) -------------------------------------------------
+long long rans_scratch_bytes(long long n_chan, long long hw, int spc);
+long long rans_max_bytes(long long n_chan, long long hw, int spc);
+// symbols (channel-row major, n_chan * hw each) -> container bytes in `out` (device), total size in *out_bytes (device)
+cudaError_t launch_rans_encode(const int32_t* idx, const int32_t* v, const int32_t* lo, const int32_t* hi, const int32_t* raw,
+                               const int32_t* cdf_length, long long n_chan, long long hw, int spc, void* scratch, uint8_t* out,
+                               unsigned long long* out_bytes, cudaStream_t s);
+// container bytes (device) + the CDF row of every element -> q; *status (device) = 1 if the container is corrupt / truncated;
+// scratch: 8 bytes per stream
+cudaError_t launch_rans_decode(const uint8_t* data, long long data_bytes, const int32_t* idx, CdfTables t, long long n_chan, long long hw,
+                               int spc, void* scratch, int32_t* q, int32_t* status, cudaStream_t s);
+
 }  // namespace cdc

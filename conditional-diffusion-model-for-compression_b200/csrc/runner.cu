@@ -1998,6 +1998,37 @@ int cdc_cdf_lookup(const int32_t* q, const float* sigma, const int32_t* cdf, con
                                                                                                         : CDC_ERR_CUDA;
 }
 
+// ---- rANS bitstream (stateless; runs on the CURRENT device) ----
+int cdc_rans_streams_per_channel(int64_t hw) {
+    int s = 1;
+    const int64_t lim = hw / 64 > 1 ? hw / 64 : 1;
+    while (2 * s <= lim && s < 32) s *= 2;
+    return s;
+}
+int64_t cdc_rans_scratch_bytes(int64_t n_chan, int64_t hw, int spc) {
+    return (n_chan < 1 || hw < 1 || spc < 1) ? -1 : rans_scratch_bytes(n_chan, hw, spc);
+}
+int64_t cdc_rans_max_bytes(int64_t n_chan, int64_t hw, int spc) {
+    return (n_chan < 1 || hw < 1 || spc < 1) ? -1 : rans_max_bytes(n_chan, hw, spc);
+}
+int cdc_rans_encode(const int32_t* idx, const int32_t* v, const int32_t* lo, const int32_t* hi, const int32_t* raw,
+                    const int32_t* cdf_length, int64_t n_chan, int64_t hw, int spc, void* scratch, uint8_t* out, int64_t out_capacity,
+                    uint64_t* out_bytes_dev, cdc_stream s) {
+    if (!idx || !v || !lo || !hi || !raw || !cdf_length || !scratch || !out || !out_bytes_dev) return CDC_ERR_SHAPE;
+    if (n_chan < 1 || hw < 1 || spc < 1 || spc > 32 || n_chan * spc > (1LL << 30) || hw > (1LL << 31) - 1) return CDC_ERR_SHAPE;
+    if (out_capacity < rans_max_bytes(n_chan, hw, spc)) return CDC_ERR_SHAPE;
+    return launch_rans_encode(idx, v, lo, hi, raw, cdf_length, n_chan, hw, spc, scratch, out,
+                              reinterpret_cast<unsigned long long*>(out_bytes_dev), S(s)) == cudaSuccess ? CDC_OK : CDC_ERR_CUDA;
+}
+int cdc_rans_decode(const uint8_t* data, int64_t data_bytes, const int32_t* idx, const int32_t* cdf, const int32_t* row_start,
+                    const int32_t* cdf_length, const int32_t* offset, int rows, int64_t n_chan, int64_t hw, int spc, void* scratch,
+                    int32_t* q, int32_t* status_dev, cdc_stream s) {
+    if (!data || !idx || !cdf || !row_start || !cdf_length || !offset || !scratch || !q || !status_dev) return CDC_ERR_SHAPE;
+    if (rows < 1 || n_chan < 1 || hw < 1 || spc < 1 || spc > 32 || data_bytes < 24 + 4 * n_chan * spc) return CDC_ERR_SHAPE;
+    CdfTables t{cdf, row_start, cdf_length, offset, nullptr, rows};
+    return launch_rans_decode(data, data_bytes, idx, t, n_chan, hw, spc, scratch, q, status_dev, S(s)) == cudaSuccess ? CDC_OK : CDC_ERR_CUDA;
+}
+
 // ---- single-op entry points for kernel-level parity tests ----
 int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1, int B, int H, int W,
                   const float* w_oihw, const float* bias, int cout, int ksize, int mode, int force_bn,

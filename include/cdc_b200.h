@@ -129,6 +129,25 @@ int cdc_cdf_lookup(const int32_t* q, const float* sigma, const int32_t* cdf, con
                    int64_t inner, int32_t* idx, int32_t* v, int32_t* lo, int32_t* hi, int32_t* raw, int64_t n,
                    cdc_stream s);
 
+/* ---- oracle/rans.py encode / decode: the on-wire bitstream of the quantised latents ------
+ * 32-bit-state rANS, 16-bit precision, 16-bit words; every channel row of `hw` symbols (n_chan = batch * channels rows) is
+ * cut into `spc` interleaved streams (stream j codes symbols j, j + spc, ...).  Byte-exact with the oracle; the container
+ * layout is in oracle/rans.py and DESIGN.md.  All pointers are device pointers; stateless, current device. */
+int cdc_rans_streams_per_channel(int64_t hw);                       /* the format's choice of spc for hw symbols per row */
+int64_t cdc_rans_scratch_bytes(int64_t n_chan, int64_t hw, int spc); /* workspace for cdc_rans_encode */
+int64_t cdc_rans_max_bytes(int64_t n_chan, int64_t hw, int spc);     /* upper bound of the container size */
+/* (idx, v, lo, hi, raw) as produced by cdc_cdf_lookup + the tables' cdf_length -> container in `out`; its size in bytes
+ * is written to *out_bytes_dev (device memory) when the stream reaches that point */
+int cdc_rans_encode(const int32_t* idx, const int32_t* v, const int32_t* lo, const int32_t* hi, const int32_t* raw,
+                    const int32_t* cdf_length, int64_t n_chan, int64_t hw, int spc, void* scratch, uint8_t* out,
+                    int64_t out_capacity, uint64_t* out_bytes_dev, cdc_stream s);
+/* container + the CDF row index of every element (from sigma, or the channel) -> q int32; n_chan / hw / spc are the
+ * header's values (the caller parses the 24-byte header); scratch: 8 bytes per stream; *status_dev = 1 if the container is
+ * truncated or corrupt */
+int cdc_rans_decode(const uint8_t* data, int64_t data_bytes, const int32_t* idx, const int32_t* cdf, const int32_t* row_start,
+                    const int32_t* cdf_length, const int32_t* offset, int rows, int64_t n_chan, int64_t hw, int spc,
+                    void* scratch, int32_t* q, int32_t* status_dev, cdc_stream s);
+
 #ifdef __cplusplus
 }
 #endif
