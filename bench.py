@@ -181,11 +181,14 @@ def int_roofline(dev, peak_gbs, n=4194304, reps=9):
     ms_c = timed(lambda: L.cdc_cdf_lookup(P(q), P(sigma), P(tb.cdf), P(tb.row_start), P(tb.cdf_length), P(tb.offset),
                                           P(tb.scale_table), tb.rows, 1, *[P(o) for o in outs], n, st))
     assert torch.equal(qo, q)
+    ms_floor = timed(lambda: L.cdc_quantize(P(y), P(mu), P(qo), P(yh), 4, 0, 0, st))  # same call on 4 symbols: launch + event floor
     gq, gc = 16.0 * n / (ms_q * 1e-3) / 1e9, 28.0 * n / (ms_c * 1e-3) / 1e9
     return {"symbols": n, "bound": "hbm", "unit": "GB/s", "peak": peak_gbs,
             "quantize_kernel": {"achieved": gq, "frac": gq / peak_gbs, "us": ms_q * 1e3, "bytes_per_symbol": 16},
             "cdf_lookup_kernel": {"achieved": gc, "frac": gc / peak_gbs, "us": ms_c * 1e3, "bytes_per_symbol": 28},
-            "how": "cdc_quantize / cdc_cdf_lookup on device buffers, CUDA events, median of %d, 256 MiB L2 flush before every launch" % reps}
+            "launch_floor_us": ms_floor * 1e3,
+            "how": "cdc_quantize / cdc_cdf_lookup on device buffers, CUDA events around ONE launch, median of %d, 256 MiB L2 flush (a write: "
+                   "the L2 is full of dirty lines the kernel has to evict) before every launch; launch_floor_us = the same call on 4 symbols" % reps}
 
 
 def main():
