@@ -2,6 +2,7 @@
 Usage: conv_bench.py H W cin cout ksize mode force_bn [stats] [cin2]   (no arguments: the sweep below)"""
 import ctypes as C, os, sys
 os.environ.setdefault("CDC_TEST_CONV_REPS", "7")
+os.environ.setdefault("CDC_LIB_PATH", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "conditional-diffusion-model-for-compression_b200", "libcdc_b200_tools.so"))  # env switches live in the tools build (-DCDC_TOOLS)
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from cdc_b200 import _ffi

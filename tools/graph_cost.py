@@ -1,5 +1,7 @@
-"""In-graph cost of classes of ops: replay time of the captured 17-step graph with the class left out (CDC_GRAPH_SKIP)
-subtracted from the full graph's.  One subprocess per variant (the variable is read at capture time)."""
+"""In-graph cost of classes of ops by DIFFERENCING: replay time of the captured 17-step graph with the class left out
+(CDC_GRAPH_SKIP) subtracted from the full graph's.  One subprocess per variant (the variable is read at capture time).
+Round 2 replaced this by per-kernel globaltimer stamps (bench.py --ops-out / Decoder.profile_graph), which do not perturb
+the caches; kept as a cross-check.  The switch exists only in the TOOLS build (libcdc_b200_tools.so, -DCDC_TOOLS)."""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CODE = r'''
@@ -31,6 +33,7 @@ if len(sys.argv) > 1:
 base = None
 for name, skip in variants:
     env = dict(os.environ)
+    env["CDC_LIB_PATH"] = os.path.join(ROOT, "conditional-diffusion-model-for-compression_b200", "libcdc_b200_tools.so")
     if skip:
         env["CDC_GRAPH_SKIP"] = skip
     out = subprocess.run([sys.executable, "-c", CODE], env=env, capture_output=True, text=True)

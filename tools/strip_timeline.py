@@ -2,6 +2,7 @@
 events (second, warm call).  Usage: strip_timeline.py [cin] [cout] [H] [W] [mode]   (mode 1 = stride 2, 2 = nearest-x2 input)"""
 import ctypes as C, os, sys
 os.environ.setdefault("CDC_STRIP_DEBUG", "1")
+os.environ.setdefault("CDC_LIB_PATH", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "conditional-diffusion-model-for-compression_b200", "libcdc_b200_tools.so"))  # env switches live in the tools build (-DCDC_TOOLS)
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from cdc_b200 import _ffi
