@@ -4,7 +4,7 @@
     graph: bench.py --ops-out),
   * the ncu launch list of one eager step (cold caches, serialised: compare shares, not absolutes),
   * tensor-pipe utilisation and DRAM bytes from the ncu --set full captures (where that launch was captured).
-Usage: per_kernel_table.py per_kernel_ingraph.csv launches.csv out.csv ncu_summary.csv[:class[:first|last]] ..."""
+Usage: per_kernel_table.py per_kernel_ingraph.csv launches.csv out.csv ncu_summary.csv[:class[:first[+k]|last]] ..."""
 import csv
 import sys
 
@@ -26,7 +26,8 @@ for spec in sys.argv[4:]:
     hdr, data = rows[0], rows[1:]
     col = {name.split(" [")[0]: i for i, name in enumerate(hdr)}
     idx = [i for i, (n, _) in enumerate(step) if any(c in n for c in cls.split("|"))]
-    idx = idx[:len(data)] if where == "first" else idx[-len(data):]
+    off = int(where.split("+")[1]) if "+" in where else 0  # "first+1": the capture started one launch into the step
+    idx = idx[off:off + len(data)] if where.startswith("first") else idx[-len(data):]
     for i, r in zip(idx, data):
         assert r[0].split("(")[0] == step[i][0].split("(")[0], (r[0], step[i][0])
         full[i] = (float(r[col["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]]),
