@@ -131,6 +131,13 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
     }
     const int units = p.batch * p.nseg * p.S;
     if (threadIdx.x == 0) stamp_begin(p.stamp);
+    // tools only (strip_timeline.py): timing experiments that break the results -- 1: epilogue drains without work, 2: issuer
+    // skips its tcgen05 fences, 4: accumulators are not re-zeroed, 8: producer ignores the accumulator ring
+#ifdef CDC_TOOLS
+    const int dmode = p.dbg != nullptr ? static_cast<int>(p.dbg[511]) : 0;
+#else
+    constexpr int dmode = 0;
+#endif
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&p.amap[0]);
@@ -230,7 +237,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                     // input row i opens the accumulator of output row i (stride 2: of row i / 2, i even): drained and re-zeroed?
                     if (MODE == 2 ? ((i & 1) == 0 && (i >> 1) < L) : i < L) {
                         const uint32_t gi = g + (MODE == 2 ? (i >> 1) : i);
-                        mbar_wait(bar_tempty + 8 * (gi % NACC), (gi / NACC) & 1);
+                        if (!(dmode & 8)) mbar_wait(bar_tempty + 8 * (gi % NACC), (gi / NACC) & 1);
                     }
                     // (the fused 1x1 conv's short accumulator ring is NOT waited for here: with only 2 slots that would tie
                     // the load of row i to the epilogue's progress three rows back -- measured 5300 instead of 2750 cycles per
@@ -262,57 +269,84 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
         __syncwarp();
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        // The warp runs the loop converged (descriptor arithmetic stays warp-uniform) and one elected lane issues.
-        // One mbarrier wait per input row (row_full also certifies that the accumulator the row opens is drained and
-        // re-zeroed: the producer checked), placed in the MIDDLE of the previous row's MMA stream so that the MMAs
-        // already queued in the tensor pipe cover its latency.  Every MMA accumulates (the epilogue re-zeroes slots).
-        {
+        // ONE elected thread runs the whole loop.  The tensor pipe queues very little: tools/exp_kf_interf.cu shows that an
+        // issue pause of 50 cycles after every 6 MMAs already costs 17 cycles, 100 cost 37, 200 cost 83 (N = 192 MMAs of 96
+        // cycles each) -- roughly one MMA is buffered behind the running one.  Round 1's issuer (warp-converged bookkeeping,
+        // two elected regions per chunk, row parameters derived at the top of every row) left ~70 instructions between the
+        // last MMA of a half chunk and the first of the next: 1305 cycles per 12-MMA row with an idle epilogue and 1570 with
+        // a busy one (the issuer shares its SM sub-partition with two epilogue warps) against the 1152-cycle tensor floor.
+        // So: everything a chunk needs (accumulator window, weight-block offsets, instruction descriptors, the ring slot's
+        // address) is computed one chunk AHEAD, between the MMAs of the previous chunk, and the only instructions between
+        // the last MMA of a chunk and the first of the next are the commits, the (already known) barrier answer and the
+        // tcgen05 fence.  Every MMA accumulates (the epilogue re-zeroes slots).
+        if (elect_one_sync()) {
             constexpr uint32_t idesc0 = make_idesc_f16(128, 0);
             constexpr uint32_t NB = static_cast<uint32_t>(BN >> 3) << 17;  // idesc increment per window slot
-            constexpr int T = 4 * NKW;  // K steps per (input row, chunk); the wait for the next chunk sits after half of them
+            constexpr int T = 4 * NKW;  // K steps per (input row, chunk)
             // (stride 2: the E slot carries kw = 1 (4 K steps), the O slot kw = 0 and kw = 2 (8 K steps))
+            constexpr int TT = MODE == 2 ? 8 : T;
+            constexpr int TH = 4;       // the next chunk's barrier is probed after this many K steps, its answer used after the last
             const uint64_t desc_hi = make_sw128_desc(0) & 0xFFFFFFFF00000000ull;
             const uint32_t wlo = wbase >> 4;
             uint32_t rslot = 0, rpar = 0;
             uint32_t g = 0;  // running output-row counter: row j of the current strip uses accumulator (g + j) % NACC
+#ifdef CDC_TOOLS
             if (kdbg) p.dbg[502] = clock64();
+#endif
             mbar_wait(bar_wres, 0);
+#ifdef CDC_TOOLS
             if (kdbg) p.dbg[503] = clock64();
+#endif
+            // accumulator window of input row i: it feeds output rows j = i - py - e, e = 0 .. NKH-1 (kh = py + e), clipped to
+            // the strip (stride 2: even i -> rows i/2 - 1 (kh = 2) and i/2 (kh = 0); odd i -> row i/2 (kh = 1)); a window
+            // that wraps around the accumulator ring is issued as two pieces (A, then B)
+            struct RowP {
+                uint32_t cnt, nB, dA, dB, bA, bB, iA, iB;
+            };
+            auto rowp = [&](int i, int L, uint32_t g_) {
+                RowP r;
+                const int jtop = MODE == 2 ? (i >> 1) : i - py;
+                const int jspan = MODE == 2 ? ((i & 1) ? 0 : 1) : NKH - 1;
+                const int jlo = jtop - jspan > 0 ? jtop - jspan : 0;
+                const int jhi = jtop < L ? jtop : L - 1;
+                r.cnt = jhi >= jlo ? static_cast<uint32_t>(jhi - jlo + 1) : 0u;  // 0: nothing to issue (UP2 edge rows)
+                const uint32_t slo = (g_ + jlo) % NACC;
+                // weight block of the first window slot (reversed kh; stride 2: blocks are ordered kh = 2, 0, 1)
+                const uint32_t khp = MODE == 2 ? ((i & 1) ? 2u : static_cast<uint32_t>(1 - (jtop - jlo)))
+                                               : static_cast<uint32_t>((NKH - 1) - (jtop - jlo));
+                const uint32_t nA = r.cnt < NACC - slo ? r.cnt : NACC - slo;
+                r.nB = r.cnt - nA;
+                r.dA = tmem_base + slo * BN;
+                r.dB = tmem_base;
+                r.bA = khp * WB16;
+                r.bB = (khp + nA) * WB16;
+                r.iA = idesc0 + nA * NB;
+                r.iB = idesc0 + r.nB * NB;
+                return r;
+            };
+#define KF_PIN(x) asm volatile("" : "+r"(x))
             for (int u = cta; u < units; u += p.G1) {
                 int b, seg, si, h0, L;
                 decode(u, b, seg, si, h0, L);
+                const int nrows = MODE == 2 ? 2 * L + 1 : L + 2;
+                RowP cur = rowp(0, L, g);
+                uint32_t alo_base = (ring + rslot * kKfRowBytes) >> 4;
                 mbar_wait(bar_afull + 8 * rslot, rpar);  // first chunk of the strip
                 tc_fence_after();
+#ifdef CDC_TOOLS
                 if (kdbg && u == cta) p.dbg[504] = clock64();
-                const int nrows = MODE == 2 ? 2 * L + 1 : L + 2;
+#endif
                 for (int i = 0; i < nrows; ++i) {
-                    // input row i feeds output rows j = i - py - e, e = 0 .. NKH-1 (kh = py + e); clipped to the strip
-                    // (stride 2: even i -> rows i/2 - 1 (kh = 2) and i/2 (kh = 0); odd i -> row i/2 (kh = 1))
-                    const int jtop = MODE == 2 ? (i >> 1) : i - py;
-                    const int jspan = MODE == 2 ? ((i & 1) ? 0 : 1) : NKH - 1;
-                    const int jlo = jtop - jspan > 0 ? jtop - jspan : 0;
-                    const int jhi = jtop < L ? jtop : L - 1;
-                    const uint32_t cnt = jhi >= jlo ? static_cast<uint32_t>(jhi - jlo + 1) : 0u;  // 0: nothing to issue (UP2 edge rows)
-                    const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && u == cta && i < 40 && lane == 0;
+#ifdef CDC_TOOLS
+                    const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && u == cta && i < 40;
                     if (dbg) p.dbg[i * 4 + 0] = clock64();
-                    const uint32_t slo = (g + jlo) % NACC;
-                    // weight block of the first window slot (reversed kh; stride 2: blocks are ordered kh = 2, 0, 1)
-                    const uint32_t khp = MODE == 2 ? ((i & 1) ? 2u : static_cast<uint32_t>(1 - (jtop - jlo)))
-                                                   : static_cast<uint32_t>((NKH - 1) - (jtop - jlo));
-                    const uint32_t nA = cnt < NACC - slo ? cnt : NACC - slo, nB = cnt - nA;
-                    const uint32_t dA = tmem_base + slo * BN, dB = tmem_base;
-                    const uint32_t bA = khp * WB16, bB = (khp + nA) * WB16;
-                    const uint32_t iA = idesc0 + nA * NB, iB = idesc0 + nB * NB;
+#endif
+                    RowP nxt = cur;
 #pragma unroll
                     for (int pc = 0; pc < CH * NSUB; ++pc) {
                         const int ch = pc / NSUB, sub = pc % NSUB;  // sub (stride 2 only): 0 = E tile, 1 = O tile
-                        constexpr int TT = MODE == 2 ? 8 : T;       // K steps of the longest slot (the E slot issues the first 4 only)
-                        const uint32_t alo_base = (ring + rslot * kKfRowBytes) >> 4;
-                        // K steps t = kw * 4 + k in [t0, t1); a wrapped window issues its two pieces back to back
-                        // per half (alternating MMA shapes costs ~30 cycles per switch).  Fully unrolled on purpose: the
-                        // straight-line stream is ~3 uniform-datapath instructions per UTCHMMA; rolling the chunk / piece
-                        // loops (8x less issuer code) measured -10 % images/s in round 2.
-                        auto steps = [&](auto t0c, auto t1c) {
+                        // K steps t = kw * 4 + k in [t0, t1) of one window piece
+                        auto steps = [&](auto t0c, auto t1c, uint32_t d, uint32_t bo, uint32_t id) {
                             constexpr int t0 = decltype(t0c)::value, t1 = decltype(t1c)::value;
 #pragma unroll
                             for (int t = t0; t < t1; ++t) {
@@ -324,65 +358,72 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                                 if (XK16 && ch == 0 && k != 0) continue;  // stem: chunk 0 = x_t, channels 16..63 are zero
                                 const uint32_t alo = alo_base + ashift * 8 + 2 * k;
                                 const uint32_t blo = wlo + ((kw * CH + ch) * NKH) * WB16 + 2 * k;
-                                umma_f16_ss(dA, desc_hi | alo, desc_hi | (blo + bA), iA, 1u);
-                            }
-                            if (nB != 0) {
-#pragma unroll
-                                for (int t = t0; t < t1; ++t) {
-                                    const int k = t & 3;
-                                    const int kw = MODE == 2 ? (sub == 0 ? 1 : (t >> 2) * 2) : t >> 2;
-                                    const int ashift = MODE == 2 ? (sub == 1 && (t >> 2) == 1 ? 1 : 0) : kw + px;
-                                    if (MODE == 2 && sub == 0 && t >= 4) continue;
-                                    if (XK16 && ch == 0 && k != 0) continue;
-                                    const uint32_t alo = alo_base + ashift * 8 + 2 * k;
-                                    const uint32_t blo = wlo + ((kw * CH + ch) * NKH) * WB16 + 2 * k;
-                                    umma_f16_ss(dB, desc_hi | alo, desc_hi | (blo + bB), iB, 1u);
-                                }
+                                umma_f16_ss(d, desc_hi | alo, desc_hi | (blo + bo), id, 1u);
                             }
                         };
-                        // probe the next chunk's barrier now, use the answer after the first half of the MMAs
                         const uint32_t nslot = rslot + 1 == static_cast<uint32_t>(NS) ? 0u : rslot + 1;
-                        const bool more = pc + 1 < CH * NSUB || i + 1 < nrows;  // (a new row's first chunk also certifies its accumulator)
                         const uint32_t npar = nslot == 0 ? rpar ^ 1 : rpar;
+                        const bool lastpc = pc == CH * NSUB - 1;
+                        const bool more = !lastpc || i + 1 < nrows;  // (a new row's first chunk also certifies its accumulator)
+                        if (cur.cnt != 0) steps(std::integral_constant<int, 0>{}, std::integral_constant<int, TH>{}, cur.dA, cur.bA, cur.iA);
+                        // probe the next chunk's barrier now, use the answer after the last MMA of this chunk
                         const uint32_t ready = more ? mbar_test_wait(bar_afull + 8 * nslot, npar) : 1u;
-                        constexpr int TTH = TT / 2;
-                        if (cnt != 0 && elect_one_sync()) steps(std::integral_constant<int, 0>{}, std::integral_constant<int, TTH>{});
-                        __syncwarp();
+                        // ... and derive what the next chunk's MMAs need while this chunk's are in the tensor pipe
+                        uint32_t alo_next = (ring + nslot * kKfRowBytes) >> 4;
+                        KF_PIN(alo_next);
+                        if (lastpc) {
+                            nxt = rowp(i + 1, L, g);
+                            KF_PIN(nxt.cnt);
+                            KF_PIN(nxt.nB);
+                            KF_PIN(nxt.dA);
+                            KF_PIN(nxt.bA);
+                            KF_PIN(nxt.iA);
+                        }
+#ifdef CDC_TOOLS
                         if (dbg && pc == 0) p.dbg[i * 4 + 1] = clock64();
+#endif
+                        if (cur.cnt != 0) steps(std::integral_constant<int, TH>{}, std::integral_constant<int, TT>{}, cur.dA, cur.bA, cur.iA);
+                        if (cur.nB != 0) steps(std::integral_constant<int, 0>{}, std::integral_constant<int, TT>{}, cur.dB, cur.bB, cur.iB);
+                        if (RES1 && i >= 1 && i <= L) {  // fused 1x1 residual conv: centre tap, its own accumulator ring
+                            const uint32_t gr = g + i - 1;
+                            const uint32_t dR = tmem_base + (NACC + gr % NRESD) * BN;
+                            if (ch == 0) {  // slot drained and re-zeroed?  (two rows of MMAs ago: practically never blocks)
+                                mbar_wait(bar_xempty + 8 * (gr % NRESD), (gr / NRESD) & 1);
+                                tc_fence_after();
+                            }
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_f16_ss(dR, desc_hi | (alo_base + 8 + 2 * k), desc_hi | ((wres1 >> 4) + ch * WB16 + 2 * k), idesc0 + NB, 1u);
+                            if (ch == CH - 1) umma_commit(bar_xfull + 8 * (gr % NRESD));
+                        }
+                        umma_commit(bar_rempty + 8 * rslot);  // chunk consumed
+                        if constexpr (MODE == 2) {  // output row i/2 - 1 is complete after the odd-numbered input row 2h+1 (even i)
+                            if (lastpc && (i & 1) == 0 && i >= 2) umma_commit(bar_tfull + 8 * ((g + (i >> 1) - 1) % NACC));
+                        } else if (ch == CH - 1 && i >= 2) {
+                            umma_commit(bar_tfull + 8 * ((g + i - 2) % NACC));  // output row i-2 complete
+                        }
+#ifdef CDC_TOOLS
+                        if (dbg && pc == 0) p.dbg[i * 4 + 2] = clock64();
+#endif
                         if (!ready) mbar_wait(bar_afull + 8 * nslot, npar);
                         if (more) tc_fence_after();
-                        if (dbg && pc == 0) p.dbg[i * 4 + 2] = clock64();
-                        if (elect_one_sync()) {
-                            if (cnt != 0) steps(std::integral_constant<int, TTH>{}, std::integral_constant<int, TT>{});
-                            if (RES1 && i >= 1 && i <= L) {  // fused 1x1 residual conv: centre tap, its own accumulator ring
-                                const uint32_t gr = g + i - 1;
-                                const uint32_t dR = tmem_base + (NACC + gr % NRESD) * BN;
-                                if (ch == 0) {  // slot drained and re-zeroed?  (two rows of MMAs ago: practically never blocks)
-                                    mbar_wait(bar_xempty + 8 * (gr % NRESD), (gr / NRESD) & 1);
-                                    tc_fence_after();
-                                }
-#pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    umma_f16_ss(dR, desc_hi | (alo_base + 8 + 2 * k), desc_hi | ((wres1 >> 4) + ch * WB16 + 2 * k), idesc0 + NB, 1u);
-                                if (ch == CH - 1) umma_commit(bar_xfull + 8 * (gr % NRESD));
-                            }
-                            umma_commit(bar_rempty + 8 * rslot);  // chunk consumed
-                            if constexpr (MODE == 2) {  // output row i/2 - 1 is complete after the odd-numbered input row 2h+1 (even i)
-                                if (pc == CH * NSUB - 1 && (i & 1) == 0 && i >= 2) umma_commit(bar_tfull + 8 * ((g + (i >> 1) - 1) % NACC));
-                            } else if (ch == CH - 1 && i >= 2) {
-                                umma_commit(bar_tfull + 8 * ((g + i - 2) % NACC));  // output row i-2 complete
-                            }
-                        }
-                        __syncwarp();
                         rslot = nslot;
-                        if (nslot == 0) rpar ^= 1;
+                        rpar = npar;
+                        alo_base = alo_next;
                     }
+                    cur = nxt;
+#ifdef CDC_TOOLS
                     if (dbg) p.dbg[i * 4 + 3] = clock64();
+#endif
                 }
                 g += L;
             }
+#undef KF_PIN
+#ifdef CDC_TOOLS
             if (kdbg) p.dbg[505] = clock64();
+#endif
         }
+        __syncwarp();
     }
     } else if (warp < 12) {
         // ------------------------------------------------------------ epilogue (8 warps)
@@ -520,9 +561,11 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                     mbar_wait(bar_tfull + 8 * slot, (gj / NACC) & 1);
                     tc_fence_after();
                     if (edbg) edbg[1] = clock64();
-                    if (p.dbg != nullptr && p.dbg[511] == 1) {  // tools only: MMA phase without epilogue work
-                        tmem_zero<HC>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * BN + half * HC);
-                        tmem_st_wait();
+                    if (dmode & 1) {  // tools only: MMA phase without epilogue work
+                        if (!(dmode & 4)) {
+                            tmem_zero<HC>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * BN + half * HC);
+                            tmem_st_wait();
+                        }
                         tc_fence_before();
                         mbar_arrive(bar_tempty + 8 * slot);
                         continue;

@@ -2134,7 +2134,7 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
         // plain device memory (managed memory would page-fault inside the timed regions)
         cudaMalloc(&dbg_dev, 2048 * sizeof(long long));
         std::vector<long long> init(2048, 0);
-        if (atoi(getenv("CDC_STRIP_DEBUG")) == 2) init[511] = 1;
+        init[511] = atoi(getenv("CDC_STRIP_DEBUG")) / 2;  // 2: no epilogue work; 6 / 10 / 18: + no fences / no re-zero / no ring wait
         cudaMemcpy(dbg_dev, init.data(), 2048 * sizeof(long long), cudaMemcpyHostToDevice);
         cb.dbg = dbg_dev;
     }

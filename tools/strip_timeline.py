@@ -14,8 +14,8 @@ mode = a[4] if len(a) >= 5 else 0
 OH, OW = (2 * H, 2 * W) if mode == 2 else (H // 2, W // 2) if mode == 1 else (H, W)
 B = 1
 dt = torch.float16 if L.cdc_act_dtype() == 1 else torch.bfloat16
-x = torch.randn(B, H, W, cin, device="cuda").to(dt)
-w = (torch.randn(cout, cin, 3, 3, device="cuda") / 24).float()
+x = (torch.randn(B, H, W, cin, device="cuda") * float(os.environ.get("XSCALE", "1"))).to(dt)
+w = (torch.randn(cout, cin, 3, 3, device="cuda") / 24 * float(os.environ.get("XSCALE", "1"))).float()
 b = torch.zeros(cout, device="cuda")
 out = torch.empty(B, OH, OW, (cout + 63) // 64 * 64, device="cuda", dtype=dt)
 st = torch.zeros(B, 32, 2, device="cuda", dtype=torch.int64)
