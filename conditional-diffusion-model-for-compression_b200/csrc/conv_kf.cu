@@ -302,6 +302,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
             // that wraps around the accumulator ring is issued as two pieces (A, then B)
             struct RowP {
                 uint32_t cnt, nB, dA, dB, bA, bB, iA, iB;
+                uint32_t tf;  // accumulator-complete barrier this row's last chunk commits to (0: none)
             };
             auto rowp = [&](int i, int L, uint32_t g_) {
                 RowP r;
@@ -322,14 +323,23 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                 r.bB = (khp + nA) * WB16;
                 r.iA = idesc0 + nA * NB;
                 r.iB = idesc0 + r.nB * NB;
+                // output row i-2 is complete after input row i (stride 2: row i/2 - 1 after the even-numbered input row i)
+                if constexpr (MODE == 2)
+                    r.tf = ((i & 1) == 0 && i >= 2) ? bar_tfull + 8 * ((g_ + (i >> 1) - 1) % NACC) : 0u;
+                else
+                    r.tf = i >= 2 ? bar_tfull + 8 * ((g_ + i - 2) % NACC) : 0u;
                 return r;
             };
-#define KF_PIN(x) asm volatile("" : "+r"(x))
+            // The scheduler sinks plain arithmetic to its first use, i.e. into the gap after a chunk's last MMA.  A (dead)
+            // shared-memory store of the values pins their computation where the source has it: between the MMAs.
+            const uint32_t pin_word = aux + 460;
+            auto pin = [&](uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(pin_word), "r"(v) : "memory"); };
             for (int u = cta; u < units; u += p.G1) {
                 int b, seg, si, h0, L;
                 decode(u, b, seg, si, h0, L);
                 const int nrows = MODE == 2 ? 2 * L + 1 : L + 2;
                 RowP cur = rowp(0, L, g);
+                uint32_t sfull = g % NACC;  // first accumulator slot of the next full window (input row 2: output rows 0 .. 2)
                 uint32_t alo_base = (ring + rslot * kKfRowBytes) >> 4;
                 mbar_wait(bar_afull + 8 * rslot, rpar);  // first chunk of the strip
                 tc_fence_after();
@@ -369,15 +379,29 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                         // probe the next chunk's barrier now, use the answer after the last MMA of this chunk
                         const uint32_t ready = more ? mbar_test_wait(bar_afull + 8 * nslot, npar) : 1u;
                         // ... and derive what the next chunk's MMAs need while this chunk's are in the tensor pipe
-                        uint32_t alo_next = (ring + nslot * kKfRowBytes) >> 4;
-                        KF_PIN(alo_next);
+                        const uint32_t alo_next = (ring + nslot * kKfRowBytes) >> 4;
+                        const uint32_t rempty_bar = bar_rempty + 8 * rslot;
                         if (lastpc) {
-                            nxt = rowp(i + 1, L, g);
-                            KF_PIN(nxt.cnt);
-                            KF_PIN(nxt.nB);
-                            KF_PIN(nxt.dA);
-                            KF_PIN(nxt.bA);
-                            KF_PIN(nxt.iA);
+                            const int i1 = i + 1;
+                            if (MODE == 0 && i1 >= 2 && i1 < L) {
+                                // full window (output rows i1-2 .. i1, all inside the strip): no clamps, slot counted up
+                                const uint32_t nA = NACC - sfull < 3u ? NACC - sfull : 3u;
+                                nxt.cnt = 3u;
+                                nxt.nB = 3u - nA;
+                                nxt.dA = tmem_base + sfull * BN;
+                                nxt.dB = tmem_base;
+                                nxt.bA = 0u;
+                                nxt.bB = nA * WB16;
+                                nxt.iA = idesc0 + nA * NB;
+                                nxt.iB = idesc0 + nxt.nB * NB;
+                                nxt.tf = bar_tfull + 8 * sfull;
+                                sfull = sfull + 1 == NACC ? 0u : sfull + 1;
+                            } else {
+                                nxt = rowp(i1, L, g);
+                            }
+                            pin(nxt.cnt ^ nxt.nB ^ nxt.dA ^ nxt.bA ^ nxt.iA ^ nxt.bB ^ nxt.iB ^ nxt.tf ^ alo_next ^ rempty_bar);
+                        } else {
+                            pin(alo_next ^ rempty_bar);
                         }
 #ifdef CDC_TOOLS
                         if (dbg && pc == 0) p.dbg[i * 4 + 1] = clock64();
@@ -396,12 +420,8 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                                 umma_f16_ss(dR, desc_hi | (alo_base + 8 + 2 * k), desc_hi | ((wres1 >> 4) + ch * WB16 + 2 * k), idesc0 + NB, 1u);
                             if (ch == CH - 1) umma_commit(bar_xfull + 8 * (gr % NRESD));
                         }
-                        umma_commit(bar_rempty + 8 * rslot);  // chunk consumed
-                        if constexpr (MODE == 2) {  // output row i/2 - 1 is complete after the odd-numbered input row 2h+1 (even i)
-                            if (lastpc && (i & 1) == 0 && i >= 2) umma_commit(bar_tfull + 8 * ((g + (i >> 1) - 1) % NACC));
-                        } else if (ch == CH - 1 && i >= 2) {
-                            umma_commit(bar_tfull + 8 * ((g + i - 2) % NACC));  // output row i-2 complete
-                        }
+                        umma_commit(rempty_bar);                          // chunk consumed
+                        if (lastpc && cur.tf != 0u) umma_commit(cur.tf);  // an output row is complete
 #ifdef CDC_TOOLS
                         if (dbg && pc == 0) p.dbg[i * 4 + 2] = clock64();
 #endif
@@ -418,7 +438,6 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                 }
                 g += L;
             }
-#undef KF_PIN
 #ifdef CDC_TOOLS
             if (kdbg) p.dbg[505] = clock64();
 #endif
