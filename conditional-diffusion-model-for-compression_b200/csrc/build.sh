@@ -36,6 +36,7 @@ case "${what}" in
   product) build_variant product ;;
   bf16)    build_variant bf16 -DCDC_ACT_FP16=0 ;;
   tools)   build_variant tools -DCDC_TOOLS ;;
+  x2)      build_variant x2 -DCDC_XF_F32X2=1 ;;   # A/B experiment (tools/ab_bench.sh): packed fp32 pairs in the GroupNorm transform
   all)     build_variant product & p1=$!; build_variant bf16 -DCDC_ACT_FP16=0 & p2=$!; build_variant tools -DCDC_TOOLS & p3=$!
            wait $p1; wait $p2; wait $p3 ;;
   *) echo "usage: build.sh [product|bf16|tools|all]" >&2; exit 2 ;;

@@ -110,18 +110,25 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
     float* red_s = reinterpret_cast<float*>(aux_gen + 1024);
     float2* coef_s = reinterpret_cast<float2*>(aux_gen + 3072);      // APPLY: [CH * 64] (a, b) of the current image
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Roles by LOGICAL warp index: 0..3 control (producer, issuer, TMEM allocator, idle), 4..11 epilogue, 12..19 input
+    // transform.  The control warps sit at the END of the CTA: a sub-partition's arbiter prefers its eligible warp with
+    // the highest id, and the one-thread MMA issue stream must not queue behind the epilogue / transform warps it shares
+    // a sub-partition with (the tensor pipe buffers ~1 MMA: every delayed issue is a bubble).  (w + 4) % 4 == w % 4: the
+    // epilogue warps keep their TMEM lane quarter.
+    constexpr int kCtrlWarp0 = kThreads / 32 - 4;
+    const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = pwarp >= kCtrlWarp0 ? pwarp - kCtrlWarp0 : pwarp + 4;
     const int nt = blockIdx.x / p.G1, cta = blockIdx.x % p.G1;
     const int py = MODE == 1 ? (nt & 3) >> 1 : 0, px = MODE == 1 ? nt & 1 : 0;  // output parity (UP2)
     const int cot = MODE == 1 ? nt >> 2 : nt;                                     // output-channel tile
-    const bool kdbg = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 32;
+    const bool kdbg = p.dbg != nullptr && blockIdx.x == 0 && warp == 1 && lane == 0;
     if (kdbg) {
         p.dbg[500] = clock64();
         unsigned long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         p.dbg[508] = static_cast<long long>(gt);
     }
-    if (p.dbg != nullptr && threadIdx.x == 32 && blockIdx.x < 160) {  // every CTA: lifetime in globaltimer ns, SM id
+    if (p.dbg != nullptr && warp == 1 && lane == 0 && blockIdx.x < 160) {  // every CTA: lifetime in globaltimer ns, SM id
         unsigned long long gt;
         uint32_t smid;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -518,28 +525,40 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
             constexpr int HC = BN / 2;                             // columns per thread
             constexpr int GH = (EPI == EPI_STATS) ? HC / CPG : 1;  // groups per thread
             static_assert(HC == 32 || HC == 24 || HC == 16, "BN must be 64, 48 or 32");
-            float bias_r[HC];
+            // The accumulators are armed with the BIAS, not with zeros: every MMA accumulates on top of it and the drained
+            // value needs no add (32 FADDs per thread and row less on an FMA pipe the kernel keeps busy).
+            // (not with the fused residual conv: that epilogue is at the register limit, and the 32-register block the
+            // tcgen05.st wants made it spill -- 48 -> 54 us for the level-0 128 -> 64 + res conv; there: zeros + an add)
+            constexpr bool kBiasAcc = !RES1;
+            uint32_t bias_r[HC];
 #pragma unroll
-            for (int c = 0; c < HC; ++c) bias_r[c] = bias_s[half * HC + c];
-            const bool store_leader = warp == 4 && lane == 0;
-            // arm every accumulator: zero them all, ONE wait, then the first "drained" arrives
-            for (int s_ = 0; s_ < static_cast<int>(NACC + NRES); ++s_)
-                tmem_zero<HC>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + s_ * BN + half * HC);
-            tmem_st_wait();
-            tc_fence_before();
-            for (int s_ = 0; s_ < static_cast<int>(NACC + NRES); ++s_)
-                mbar_arrive(s_ < static_cast<int>(NACC) ? bar_tempty + 8 * s_ : bar_xempty + 8 * (s_ - NACC));
+            for (int c = 0; c < HC; ++c) bias_r[c] = __float_as_uint(bias_s[half * HC + c]);
             float rbias_r[RES1 ? HC : 1];
             if constexpr (RES1) {
 #pragma unroll
                 for (int c = 0; c < HC; ++c) rbias_r[c] = bias_s[BN + half * HC + c];
             }
+            const bool store_leader = warp == 4 && lane == 0;
+            // arm every accumulator, ONE wait, then the first "drained" arrives
+            for (int s_ = 0; s_ < static_cast<int>(NACC); ++s_) {
+                if constexpr (kBiasAcc)
+                    tmem_st_cols<HC>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + s_ * BN + half * HC, bias_r);
+                else
+                    tmem_zero<HC>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + s_ * BN + half * HC);
+            }
+            if constexpr (RES1) {
+                for (int s_ = static_cast<int>(NACC); s_ < static_cast<int>(NACC + NRES); ++s_)
+                    tmem_zero<HC>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + s_ * BN + half * HC);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            for (int s_ = 0; s_ < static_cast<int>(NACC + NRES); ++s_)
+                mbar_arrive(s_ < static_cast<int>(NACC) ? bar_tempty + 8 * s_ : bar_xempty + 8 * (s_ - NACC));
             for (int u = cta; u < units; u += p.G1, ++unit_ctr) {
                 int b, seg, si, h0, L;
                 decode(u, b, seg, si, h0, L);
                 const int gx = seg * 128 + row;
                 const bool valid = gx < p.W;
-                const float msk = valid ? 1.0f : 0.0f;
                 float gs[GH], gq[GH];
 #pragma unroll
                 for (int i = 0; i < GH; ++i) gs[i] = gq[i] = 0.0f;
@@ -593,20 +612,26 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                     uint32_t v[HC];
                     tmem_ld_cols<HC>(taddr, v);
                     tmem_ld_wait();
-                    tmem_zero<HC>(taddr);  // re-arm the slot: every MMA accumulates
+                    if constexpr (kBiasAcc)
+                        tmem_st_cols<HC>(taddr, bias_r);  // re-arm the slot (with the bias): every MMA accumulates
+                    else
+                        tmem_zero<HC>(taddr);
                     tmem_st_wait();
                     tc_fence_before();
                     mbar_arrive(bar_tempty + 8 * slot);
                     if (edbg) edbg[2] = clock64();
                     float f[HC];
 #pragma unroll
-                    for (int c = 0; c < HC; ++c) f[c] = __uint_as_float(v[c]) + bias_r[c];
+                    for (int c = 0; c < HC; ++c) f[c] = kBiasAcc ? __uint_as_float(v[c]) : __uint_as_float(v[c]) + __uint_as_float(bias_r[c]);
                     if constexpr (EPI == EPI_STATS) {
+                        if (valid) {  // (pixels past the image edge hold bias + 0: not part of the statistics)
+                            // (packed fp32 pairs -- FADD2 / FFMA2 with (even, odd) lane accumulators -- measured no
+                            // faster and doubled the accumulator registers: scalar)
 #pragma unroll
-                        for (int c = 0; c < HC; ++c) {
-                            const float x = f[c] * msk;
-                            gs[c / CPG] += x;
-                            gq[c / CPG] = fmaf(x, x, gq[c / CPG]);
+                            for (int c = 0; c < HC; ++c) {
+                                gs[c / CPG] += f[c];
+                                gq[c / CPG] = fmaf(f[c], f[c], gq[c / CPG]);
+                            }
                         }
                     }
                     uint4 o[HC / 8];
@@ -738,7 +763,14 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                 const uint32_t slot = n % static_cast<uint32_t>(NS), par = (n / static_cast<uint32_t>(NS)) & 1u;
                 const int h = h0 - 1 + i;
                 const bool row_in = h >= 0 && h < p.H;
+#ifdef CDC_TOOLS
+                long long* xdbg = (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && (warp & 3) == 0 && u == cta && n < 48) ? p.dbg + 1024 + n * 4 : nullptr;
+                if (xdbg) xdbg[0] = clock64();
+#endif
                 mbar_wait(bar_rfull + 8 * slot, par);
+#ifdef CDC_TOOLS
+                if (xdbg) xdbg[1] = clock64();
+#endif
                 if (row_in) {
                     const uint32_t sb = ring + slot * kKfRowBytes + toff;
                     // per half: all loads, all arithmetic, all stores, with distinct registers per vector -- a store that
@@ -768,12 +800,18 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                         }
                     };
                     part(std::integral_constant<int, 0>{}, std::integral_constant<int, 3>{});
+#ifdef CDC_TOOLS
+                    if (xdbg) xdbg[2] = clock64();
+#endif
                     part(std::integral_constant<int, 3>{}, std::integral_constant<int, 6>{});
                     part(std::integral_constant<int, 6>{}, std::integral_constant<int, 9>{});
                 }
                 fence_proxy_async_smem();  // generic-proxy writes -> visible to the MMA's async-proxy reads
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_rready + 8 * slot);
+#ifdef CDC_TOOLS
+                if (xdbg) xdbg[3] = clock64();
+#endif
             }
         }
     }
@@ -787,7 +825,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         p.dbg[509] = static_cast<long long>(gt);
     }
-    if (p.dbg != nullptr && threadIdx.x == 32 && blockIdx.x < 160) {
+    if (p.dbg != nullptr && warp == 1 && lane == 0 && blockIdx.x < 160) {
         unsigned long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         p.dbg[513 + 3 * blockIdx.x] = static_cast<long long>(gt);

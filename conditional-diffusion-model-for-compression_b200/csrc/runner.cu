@@ -2193,6 +2193,15 @@ int cdc_test_conv(int device, const void* src0, int c0, const void* src1, int c1
                dbg[501] - dbg[500], dbg[502] - dbg[501], dbg[503] - dbg[502], dbg[504] - dbg[503], dbg[505] - dbg[504], dbg[506] - dbg[505]);
         printf("kf CTA 0: %lld cycles in %lld ns -> SM clock %.0f MHz\n", dbg[506] - dbg[500], dbg[509] - dbg[508],
                1e3 * static_cast<double>(dbg[506] - dbg[500]) / static_cast<double>(dbg[509] - dbg[508]));
+        if (dbg[1024 + 3] || dbg[1024 + 7]) {
+            printf("kf input-transform timeline (first warp of each group; chunk n belongs to group n %% 2): chunk: wait part1 parts2+3+arrive | total, start since the group's previous chunk\n");
+            for (int n = 0; n < 48 && (dbg[1024 + n * 4 + 3] || n < 2); ++n) {
+                const long long* e = dbg + 1024 + n * 4;
+                if (!e[3]) continue;
+                printf("  %2d: %6lld %6lld %6lld | %6lld %6lld\n", n, e[1] - e[0], e[2] ? e[2] - e[1] : 0LL, e[2] ? e[3] - e[2] : e[3] - e[1], e[3] - e[0],
+                       n >= 2 && (e - 8)[3] ? e[0] - (e - 8)[0] : 0LL);
+            }
+        }
         printf("kf epilogue warp 4 timeline: tile: wait_tfull ldtm math sts+fence bar tma | total, since previous\n");
         for (int i = 0; i < 30 && dbg[256 + i * 8 + 1]; ++i) {
             const long long* e = dbg + 256 + i * 8;
