@@ -59,7 +59,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     float* bias_s = reinterpret_cast<float*>(aux_gen + Cfg::BAR_BYTES);
     float* red_s = reinterpret_cast<float*>(aux_gen + Cfg::BAR_BYTES + Cfg::BIAS_BYTES);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // logical roles: 0..3 control, 4..11 epilogue; the control warps are the LAST physical warps (the sub-partition
+    // arbiter prefers high warp ids and the MMA issue stream must not queue behind the epilogue: see conv_kf.cu)
+    const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = pwarp >= 8 ? pwarp - 8 : pwarp + 4;
     const int BWl = p.bw_log2, BW = 1 << BWl, BH = 128 >> BWl;
     const int total_tiles = p.n_tiles * p.nphase * p.batch * p.tiles_h * p.tiles_w;
     if (threadIdx.x == 0) stamp_begin(p.stamp);
@@ -129,35 +132,44 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
         }
     } else if (warp == 1) {
         // ---------------------------------------------------------------- MMA issuer
-        constexpr uint32_t idesc = make_idesc_f16(128, BN);
-        const uint64_t desc_hi = make_sw128_desc(0) & 0xFFFFFFFF00000000ull;
-        uint32_t stage = 0, phase = 0, it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-            mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
-            for (int i = 0; i < p.nkb; ++i) {
-                mbar_wait(bar_full + 8 * stage, phase);
+        // One elected thread.  The tensor pipe buffers about one MMA behind the running one (tools/exp_kf_interf.cu), so
+        // the blocking barrier wait + fence + descriptor arithmetic that round 1 had in front of every K block's four MMAs
+        // was a bubble per K block: the next stage's barrier is now probed right after the block's first MMA and its answer
+        // used after the last one (also across tiles: the next tile's first K block does not depend on its accumulator).
+        if (elect_one_sync()) {
+            constexpr uint32_t idesc = make_idesc_f16(128, BN);
+            const uint64_t desc_hi = make_sw128_desc(0) & 0xFFFFFFFF00000000ull;
+            uint32_t stage = 0, phase = 0, it = 0;
+            if (static_cast<int>(blockIdx.x) < total_tiles) {
+                mbar_wait(bar_full + 8 * stage, phase);  // the CTA's first K block
                 tc_fence_after();
-                const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
-                const uint32_t alo = (sa >> 4) & 0x3FFFu, blo = ((sa + Cfg::A_BYTES) >> 4) & 0x3FFFu;
-                if (leader) {  // elected-lane region, 32-bit descriptor math (see conv_kf.cu)
+            }
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
+                const bool more_tiles = tile + static_cast<int>(gridDim.x) < total_tiles;
+                for (int i = 0; i < p.nkb; ++i) {
+                    const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t alo = (sa >> 4) & 0x3FFFu, blo = ((sa + Cfg::A_BYTES) >> 4) & 0x3FFFu;
+                    const uint32_t nstage = stage + 1 == NS ? 0u : stage + 1, nphase = nstage == 0 ? phase ^ 1 : phase;
+                    const bool more = i + 1 < p.nkb || more_tiles;
                     umma_f16_ss(d_tmem, desc_hi | alo, desc_hi | blo, idesc, i != 0 ? 1u : 0u);
+                    const uint32_t ready = more ? mbar_test_wait(bar_full + 8 * nstage, nphase) : 1u;
 #pragma unroll
                     for (int k = 1; k < 4; ++k)  // 4 x (K = 16): +32 B inside the 128 B swizzle row
                         umma_f16_ss(d_tmem, desc_hi | (alo + 2 * k), desc_hi | (blo + 2 * k), idesc, 1u);
                     umma_commit(bar_empty + 8 * stage);  // frees the smem slot once these MMAs retire
-                }
-                __syncwarp();
-                if (++stage == NS) {
-                    stage = 0;
-                    phase ^= 1;
+                    if (i + 1 == p.nkb) umma_commit(bar_tfull + 8 * as);  // accumulator complete -> epilogue
+                    if (!ready) mbar_wait(bar_full + 8 * nstage, nphase);
+                    if (more) tc_fence_after();
+                    stage = nstage;
+                    phase = nphase;
                 }
             }
-            if (leader) umma_commit(bar_tfull + 8 * as);  // accumulator complete -> epilogue
-            __syncwarp();
         }
+        __syncwarp();
     } else if (warp >= 4) {
         // ---------------------------------------------------------------- epilogue (8 warps)
         const int q = warp & 3;            // TMEM sub-partition: lanes 32q .. 32q+31
