@@ -72,8 +72,15 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
     // ring of accumulators (its output row is complete one input row earlier than the 3x3's)
     constexpr uint32_t NRES = RES1 ? (BN == 64 ? 2 : 8) : 0;
     constexpr uint32_t NRESD = NRES ? NRES : 1;  // divisor (the fused-residual code is dead when NRES == 0)
-    constexpr uint32_t NACC = RES1 ? (BN == 64 ? 6 : 8) : (512 / BN < kKfAccMax ? 512 / BN : kKfAccMax);
-    constexpr int TMEM_COLS = (NACC + NRES) * BN <= 128 ? 128 : (NACC + NRES) * BN <= 256 ? 256 : 512;  // power of two
+    // ALIAS (64-column tiles without the fused residual conv): a ring of SIX logical accumulators in EIGHT physical slots.
+    // The window of input row i starts at logical slot s = (first output row) % 6 and always covers the physical slots
+    // s, s+1, s+2 <= 7 -- it never wraps, so no window is split into an N = 128 and an N = 64 MMA (119 instead of 96
+    // cycles per K step on two rows in eight).  Physical slots 6 and 7 are second homes of logical rows 0 and 1 (what
+    // they receive as the 2nd / 3rd row of a window that starts at slot 4 or 5); the epilogue adds the two homes.
+    constexpr bool ALIAS = BN == 64 && !RES1 && MODE == 0 && EPI != EPI_DDIM;
+    constexpr uint32_t NALIAS = ALIAS ? 2 : 0;
+    constexpr uint32_t NACC = RES1 ? (BN == 64 ? 6 : 8) : ALIAS ? 6 : (512 / BN < kKfAccMax ? 512 / BN : kKfAccMax);
+    constexpr int TMEM_COLS = (NACC + NALIAS + NRES) * BN <= 128 ? 128 : (NACC + NALIAS + NRES) * BN <= 256 ? 256 : 512;  // power of two
     static_assert(!RES1 || (MODE == 0 && !STAGE && EPI != EPI_DDIM && (BN == 64 || BN == 32)), "fused residual conv: 3x3 stats/store convs");
     constexpr int STAGE_BYTES = STAGE ? 2 * 128 * BN * 2 : 0;
     static_assert(!STAGE || BN == 64, "staged TMA store is built for 128-byte output rows");
@@ -322,7 +329,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                 // weight block of the first window slot (reversed kh; stride 2: blocks are ordered kh = 2, 0, 1)
                 const uint32_t khp = MODE == 2 ? ((i & 1) ? 2u : static_cast<uint32_t>(1 - (jtop - jlo)))
                                                : static_cast<uint32_t>((NKH - 1) - (jtop - jlo));
-                const uint32_t nA = r.cnt < NACC - slo ? r.cnt : NACC - slo;
+                const uint32_t nA = ALIAS ? r.cnt : (r.cnt < NACC - slo ? r.cnt : NACC - slo);
                 r.nB = r.cnt - nA;
                 r.dA = tmem_base + slo * BN;
                 r.dB = tmem_base;
@@ -392,7 +399,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                             const int i1 = i + 1;
                             if (MODE == 0 && i1 >= 2 && i1 < L) {
                                 // full window (output rows i1-2 .. i1, all inside the strip): no clamps, slot counted up
-                                const uint32_t nA = NACC - sfull < 3u ? NACC - sfull : 3u;
+                                const uint32_t nA = ALIAS ? 3u : (NACC - sfull < 3u ? NACC - sfull : 3u);
                                 nxt.cnt = 3u;
                                 nxt.nB = 3u - nA;
                                 nxt.dA = tmem_base + sfull * BN;
@@ -546,8 +553,8 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                 else
                     tmem_zero<HC>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + s_ * BN + half * HC);
             }
-            if constexpr (RES1) {
-                for (int s_ = static_cast<int>(NACC); s_ < static_cast<int>(NACC + NRES); ++s_)
+            if constexpr (RES1 || ALIAS) {  // residual-conv accumulators / second homes: zeros
+                for (int s_ = static_cast<int>(NACC); s_ < static_cast<int>(NACC + NALIAS + NRES); ++s_)
                     tmem_zero<HC>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + s_ * BN + half * HC);
             }
             tmem_st_wait();
@@ -602,6 +609,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                     if (dmode & 1) {  // tools only: MMA phase without epilogue work
                         if (!(dmode & 4)) {
                             tmem_zero<HC>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * BN + half * HC);
+                            if (ALIAS && slot < NALIAS) tmem_zero<HC>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (NACC + slot) * BN + half * HC);
                             tmem_st_wait();
                         }
                         tc_fence_before();
@@ -616,6 +624,15 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                         tmem_st_cols<HC>(taddr, bias_r);  // re-arm the slot (with the bias): every MMA accumulates
                     else
                         tmem_zero<HC>(taddr);
+                    if (ALIAS && slot < NALIAS) {  // logical rows 0 and 1: add what landed in the second home
+                        const uint32_t t2 = taddr + NACC * BN;
+                        uint32_t v2[HC];
+                        tmem_ld_cols<HC>(t2, v2);
+                        tmem_ld_wait();
+                        tmem_zero<HC>(t2);
+#pragma unroll
+                        for (int c = 0; c < HC; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(v2[c]));
+                    }
                     tmem_st_wait();
                     tc_fence_before();
                     mbar_arrive(bar_tempty + 8 * slot);
