@@ -14,13 +14,15 @@
 //   B operand : the N tile's whole [kw][chunk][kh reversed][BN][64] weight block, resident in shared memory
 //   D         : ring of 512 / BN (at most 16) accumulators (BN TMEM columns each); output row j of the running row counter g
 //               lives in slot (g + j) % ring, so the window {r-1, r, r+1} is contiguous except when it wraps
-//               (then the MMA is split in two)
-//   first use : every MMA accumulates; the epilogue re-zeroes an accumulator (tcgen05.st) right after draining it,
-//               so the issue stream has no special first K step
+//               (then the MMA is split in two).  BN = 64: six logical rows in eight physical slots, windows never wrap
+//               (ALIAS below)
+//   first use : every MMA accumulates; the epilogue re-arms an accumulator (tcgen05.st of the bias) right after
+//               draining it, so the issue stream has no special first K step
 //
-//   warp 0 : input-row producer (TMA)   warp 1 : barrier init + weight load (TMA, once), then tcgen05.mma issuer
-//   warp 2 : TMEM allocator             warps 4-11 : epilogue
-//   warps 12-19 (APPLY only) : GroupNorm + FiLM + SiLU of the INPUT rows, in shared memory, two groups on alternate chunks
+//   logical warp 0 : input-row producer (TMA)   1 : barrier init + weight load (TMA, once), then tcgen05.mma issuer
+//   logical warp 2 : TMEM allocator             4-11 : epilogue
+//   logical warps 12-19 (APPLY only) : GroupNorm + FiLM + SiLU of the INPUT rows, in shared memory, two groups on
+//   alternate chunks.  PHYSICALLY the control warps 0-3 are the CTA's LAST four warps (highest issue priority).
 //
 // Modes: 0 = 3x3 / stride 1 (optionally with the ResBlock's 1x1 residual conv riding along, RES1);
 //        1 = nearest-x2 upsample + 3x3 as four parity 2x2 convs;  2 = 3x3 / stride 2 (even / odd pixel tiles).
