@@ -2,6 +2,7 @@
 // TMEM -> registers -> (+bias, GroupNorm sums, residual, DDIM update) -> global.
 // Called by the 4 epilogue warps (128 threads); thread = TMEM lane = output pixel.
 #pragma once
+#include "kernels.cuh"
 #include "conv_tc.cuh"
 #include "gn_sums.cuh"
 #include "ptx.cuh"
@@ -78,7 +79,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const EpiArgs& e, uint32_t ta
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 e.x[pix * 3 + c] = xn[c];
-                e.xpad[pix * 64 + c] = to_act(xn[c]);
+                e.xpad[pix * kXpadC + c] = to_act(xn[c]);
                 if (e.x0_out) e.x0_out[pix * 3 + c] = x0[c];
             }
         }

@@ -40,6 +40,7 @@
 
 #include "conv_epilogue.cuh"
 #include "conv_kf.cuh"
+#include "kernels.cuh"
 #include "gn_apply.cuh"
 #include "launch.cuh"
 #include "ptx.cuh"
@@ -79,9 +80,12 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
     // s, s+1, s+2 <= 7 -- it never wraps, so no window is split into an N = 128 and an N = 64 MMA (119 instead of 96
     // cycles per K step on two rows in eight).  Physical slots 6 and 7 are second homes of logical rows 0 and 1 (what
     // they receive as the 2nd / 3rd row of a window that starts at slot 4 or 5); the epilogue adds the two homes.
-    constexpr bool ALIAS = BN == 64 && !RES1 && MODE == 0 && EPI != EPI_DDIM;
+    // The BN = 32 convs with the fused residual conv (whose 8 accumulators share TMEM) use the same ring: 6 + 2 + 8 slots
+    // (43.0 / 58.2 -> 40.5 / 55.0 us for the two level-1 convs).  The BN = 64 one would be left with a four-row ring and
+    // its epilogue, already at the register limit, spills on the second load: 47.6 -> 49.7 us; it keeps 6 + 2 residual slots.
+    constexpr bool ALIAS = MODE == 0 && EPI != EPI_DDIM && ((BN == 64 && !RES1) || (BN == 32 && RES1));
     constexpr uint32_t NALIAS = ALIAS ? 2 : 0;
-    constexpr uint32_t NACC = RES1 ? (BN == 64 ? 6 : 8) : ALIAS ? 6 : (512 / BN < kKfAccMax ? 512 / BN : kKfAccMax);
+    constexpr uint32_t NACC = RES1 ? 6 : ALIAS ? 6 : (512 / BN < kKfAccMax ? 512 / BN : kKfAccMax);
     constexpr int TMEM_COLS = (NACC + NALIAS + NRES) * BN <= 128 ? 128 : (NACC + NALIAS + NRES) * BN <= 256 ? 256 : 512;  // power of two
     static_assert(!RES1 || (MODE == 0 && !STAGE && EPI != EPI_DDIM && (BN == 64 || BN == 32)), "fused residual conv: 3x3 stats/store convs");
     constexpr int STAGE_BYTES = STAGE ? 2 * 128 * BN * 2 : 0;
@@ -426,7 +430,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                         if (cur.nB != 0) steps(std::integral_constant<int, 0>{}, std::integral_constant<int, TT>{}, cur.dB, cur.bB, cur.iB);
                         if (RES1 && i >= 1 && i <= L) {  // fused 1x1 residual conv: centre tap, its own accumulator ring
                             const uint32_t gr = g + i - 1;
-                            const uint32_t dR = tmem_base + (NACC + gr % NRESD) * BN;
+                            const uint32_t dR = tmem_base + (NACC + NALIAS + gr % NRESD) * BN;
                             if (ch == 0) {  // slot drained and re-zeroed?  (two rows of MMAs ago: practically never blocks)
                                 mbar_wait(bar_xempty + 8 * (gr % NRESD), (gr / NRESD) & 1);
                                 tc_fence_after();
@@ -519,11 +523,10 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                             p.x[pix * 3 + c] = xn[c];
                             if (p.x0_out) p.x0_out[pix * 3 + c] = x0[c];
                         }
-                        // channels 0..2 of the stem's 64-channel x_t copy and the (always zero) channel 3: one 8-byte store
-                        uint2 pk;
-                        pk.x = pack_act2(xn[0], xn[1]);
-                        pk.y = pack_act2(xn[2], 0.0f);
-                        *reinterpret_cast<uint2*>(p.xpad + pix * 64) = pk;
+                        // the stem's x_t copy (kernels.cuh kXpadC = 16 channels per pixel, 3 real): one whole 32-byte sector
+                        static_assert(kXpadC == 16, "one st.global.v8 per pixel");
+                        st_global_v8(p.xpad + pix * kXpadC, make_uint4(pack_act2(xn[0], xn[1]), pack_act2(xn[2], 0.0f), 0u, 0u),
+                                     make_uint4(0u, 0u, 0u, 0u));
                     }
 #pragma unroll
                     for (int c = 0; c < 3; ++c) xt[c] = xnext[c];
@@ -562,7 +565,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
             tmem_st_wait();
             tc_fence_before();
             for (int s_ = 0; s_ < static_cast<int>(NACC + NRES); ++s_)
-                mbar_arrive(s_ < static_cast<int>(NACC) ? bar_tempty + 8 * s_ : bar_xempty + 8 * (s_ - NACC));
+                mbar_arrive(s_ < static_cast<int>(NACC) ? bar_tempty + 8 * s_ : bar_xempty + 8 * (s_ - NACC));  // (barrier indices, not slots)
             for (int u = cta; u < units; u += p.G1, ++unit_ctr) {
                 int b, seg, si, h0, L;
                 decode(u, b, seg, si, h0, L);
@@ -578,7 +581,7 @@ __global__ void __launch_bounds__(128 + kEpiThreads + (APPLY ? kKfXfExtra : 0), 
                         const uint32_t xs = gj % NRES;
                         mbar_wait(bar_xfull + 8 * xs, (gj / NRES) & 1);
                         tc_fence_after();
-                        const uint32_t xaddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (NACC + xs) * BN + half * HC;
+                        const uint32_t xaddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (NACC + NALIAS + xs) * BN + half * HC;
                         uint32_t xv[HC];
                         tmem_ld_cols<HC>(xaddr, xv);
                         tmem_ld_wait();

@@ -319,7 +319,7 @@ __global__ void x_in_kernel(const float* __restrict__ x, float* __restrict__ xs,
         for (int c = 0; c < 3; ++c) {
             const float v = x[(b * 3 + c) * HW + p];
             xs[i * 3 + c] = v;
-            xpad[i * 64 + c] = to_act(v);
+            xpad[i * kXpadC + c] = to_act(v);
         }
     }
 }

@@ -81,6 +81,9 @@ static EncodeTiledFn get_encode() {
 struct Act {  // NHWC act_t activation, batch implied by the plan
     act_t* p = nullptr;
     int C = 0, H = 0, W = 0;
+    int Cphys = 0;  // channels actually stored per pixel (0: C).  The stem's x_t copy stores kXpadC of its 64 logical
+                    // channels: tensor maps get this extent and pitch, TMA zero-fills the rest of the 64-channel box
+    int cs() const { return Cphys ? Cphys : C; }
 };
 
 struct ConvW {  // repacked conv weights: act_t [n_pad][taps][c_pad], fp32 bias [n_pad]
@@ -369,16 +372,16 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, const PlanOpts& p
                 const Act& a = cb.srcs[s];
                 if (kg.mode == 2) {  // even-pixel and odd-pixel views of the source: pixel stride 2, W/2 pixels each
                     for (int eo = 0; eo < 2; ++eo)
-                        if (encode_act_map(&kp->amap[2 * s + eo], a.p + static_cast<size_t>(eo) * a.C, a.C, a.W / 2, a.H, B,
-                                           2 * static_cast<size_t>(a.C), static_cast<size_t>(a.W) * a.C,
-                                           static_cast<size_t>(a.H) * a.W * a.C, 130, 1))
+                        if (encode_act_map(&kp->amap[2 * s + eo], a.p + static_cast<size_t>(eo) * a.cs(), a.cs(), a.W / 2, a.H, B,
+                                           2 * static_cast<size_t>(a.cs()), static_cast<size_t>(a.W) * a.cs(),
+                                           static_cast<size_t>(a.H) * a.W * a.cs(), 130, 1))
                             return fail("cuTensorMapEncodeTiled (kf stride-2 activation) failed");
                     continue;
                 }
-                const int rc_map = kg.tr ? encode_act_map(&kp->amap[s], a.p, a.C, a.H, a.W, B, static_cast<size_t>(a.W) * a.C,
-                                                          static_cast<size_t>(a.C), static_cast<size_t>(a.H) * a.W * a.C, 130, 1)
-                                         : encode_act_map(&kp->amap[s], a.p, a.C, a.W, a.H, B, static_cast<size_t>(a.C),
-                                                          static_cast<size_t>(a.W) * a.C, static_cast<size_t>(a.H) * a.W * a.C, 130, 1);
+                const int rc_map = kg.tr ? encode_act_map(&kp->amap[s], a.p, a.cs(), a.H, a.W, B, static_cast<size_t>(a.W) * a.cs(),
+                                                          static_cast<size_t>(a.cs()), static_cast<size_t>(a.H) * a.W * a.cs(), 130, 1)
+                                         : encode_act_map(&kp->amap[s], a.p, a.cs(), a.W, a.H, B, static_cast<size_t>(a.cs()),
+                                                          static_cast<size_t>(a.W) * a.cs(), static_cast<size_t>(a.H) * a.W * a.cs(), 130, 1);
                 if (rc_map) return fail("cuTensorMapEncodeTiled (kf activation) failed");
             }
             if (encode_w_map(&kp->wmap, w.w, w.taps * w.c_pad, w.n_pad, kg.bn)) return fail("cuTensorMapEncodeTiled (weights) failed");
@@ -500,14 +503,14 @@ static int build_conv(const ConvBuild& cb, int B, int num_sms, const PlanOpts& p
         if (cb.mode == MODE_S2) {
             for (int py = 0; py < 2; ++py)
                 for (int px = 0; px < 2; ++px) {
-                    const act_t* base = a.p + (static_cast<size_t>(py) * a.W + px) * a.C;
-                    if (encode_act_map(&cp->amap[nmaps++], base, a.C, a.W / 2, a.H / 2, B, 2 * static_cast<size_t>(a.C),
-                                       2 * static_cast<size_t>(a.W) * a.C, static_cast<size_t>(a.H) * a.W * a.C, BW, BH))
+                    const act_t* base = a.p + (static_cast<size_t>(py) * a.W + px) * a.cs();
+                    if (encode_act_map(&cp->amap[nmaps++], base, a.cs(), a.W / 2, a.H / 2, B, 2 * static_cast<size_t>(a.cs()),
+                                       2 * static_cast<size_t>(a.W) * a.cs(), static_cast<size_t>(a.H) * a.W * a.cs(), BW, BH))
                         return fail("cuTensorMapEncodeTiled (stride-2 view) failed");
                 }
         } else {
-            if (encode_act_map(&cp->amap[nmaps++], a.p, a.C, a.W, a.H, B, static_cast<size_t>(a.C),
-                               static_cast<size_t>(a.W) * a.C, static_cast<size_t>(a.H) * a.W * a.C, BW, BH))
+            if (encode_act_map(&cp->amap[nmaps++], a.p, a.cs(), a.W, a.H, B, static_cast<size_t>(a.cs()),
+                               static_cast<size_t>(a.W) * a.cs(), static_cast<size_t>(a.H) * a.W * a.cs(), BW, BH))
                 return fail("cuTensorMapEncodeTiled (activation) failed");
         }
     }
@@ -987,9 +990,11 @@ static int build_plans(cdc_ctx* ctx) {
     pb.ops = &ctx->step_ops;
     pb.slots = ctx->gn_slots;
     pb.clear_slots_op();
-    ctx->xpad = pb.act(64, H, W);
+    ctx->xpad = pb.act(kXpadC, H, W);  // physically kXpadC channels per pixel ...
     if (pb.rc) return pb.rc;
-    CK(cudaMemset(ctx->xpad.p, 0, px * 64 * 2));
+    CK(cudaMemset(ctx->xpad.p, 0, px * kXpadC * 2));
+    ctx->xpad.Cphys = kXpadC;          // ... logically one 64-channel chunk of the stem's input (kernels.cuh)
+    ctx->xpad.C = 64;
     for (int i = 0; i < 4; ++i) ctx->cond[i] = pb.act(C[i], H >> i, W >> i);
     ctx->latent = pb.act(ctx->cfg.latent_ch, H >> 4, W >> 4);
     if (pb.rc) return pb.rc;
