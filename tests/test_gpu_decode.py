@@ -59,7 +59,9 @@ def test_teacher_forced_step_parity(shape):
         worst = max(worst, e1)
         assert torch.isfinite(xp).all()
         assert e1 <= TOL, f"t={t}: x_prev max-abs {e1}"
-        assert e0 <= 3 * TOL, f"t={t}: x0_hat max-abs {e0}"
+        # (raw x0_hat: 1e-2 on the last step, where it IS the image; 3e-2 at noisy steps, where it is multiplied by
+        # c0 <= 0.3 before it reaches x_prev -- the same gate as the headline test in test_gpu_parity_r2.py)
+        assert e0 <= (TOL if t == 0 else 3 * TOL), f"t={t}: x0_hat max-abs {e0}"
     try:
         dec.denoise_step(x, 998, cond)
         assert False, "t outside the schedule must raise"
