@@ -110,6 +110,10 @@ CONV_CASES = [
     ("kf_units_gt_ctas", 40, 16, 512, [64], 64, 3, 0, 0),
     ("kf_c128_n128_two_tiles", 1, 96, 384, [128], 128, 3, 0, 0),
     ("kf_dual_64+64_long", 2, 130, 256, [64, 64], 64, 3, 0, 0),
+    # long strips (20+ rows per CTA): the six-in-eight accumulator ring of the 64-column tiles goes round several times
+    # (rows 0 and 1 of every cycle are summed from two TMEM slots); the 32-column tiles' 16-slot ring wraps
+    ("kf_c128_n128_long_strips", 8, 48, 512, [128], 128, 3, 0, 0),
+    ("kf_c192_n128_bn32_long_strips", 4, 64, 256, [192], 128, 3, 0, 0),
     # nearest-x2 + conv3x3 through the kh-fused kernel (four parity 2x2 convs, scattered store)
     ("kf_up2_c128_n64", 1, 40, 128, [128], 64, 3, 2, 0),
     ("kf_up2_c192_n128_ragged", 2, 21, 192, [192], 128, 3, 2, 0),
